@@ -1,0 +1,5 @@
+"""crackle_b200: B200-native (sm_100a) implementation of seung-lab/crackle's per-z-slice compress / decompress
+hot path behind the reference's own interface.  See DESIGN.md and INTEGRATION.md."""
+from .codec import Context, compress, decompress, decompress_range, default_context, header  # noqa: F401
+
+__all__ = ["Context", "compress", "decompress", "decompress_range", "default_context", "header"]

@@ -1,0 +1,187 @@
+"""Host-side mirror of the reference's operator interface for the per-z-slice path.
+
+Names, argument meaning and error behaviour follow crackle/codec.py (compress :689-733, decompress :616-687,
+decompress_range :632-687) and src/fastcrackle.cpp (compress :163-210, decompress :84-129).  All compute goes
+through the C-ABI (libcrackle_b200.so); numpy arrays / bytes in and out like the reference, plus torch CUDA tensors
+for device-resident volumes (the benchmark's `value` path)."""
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+
+
+class Context:
+    """One per GPU: owns the CUDA stream and the reusable device workspace (ckl_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._h = ctypes.c_void_p()
+        L = _capi.lib()
+        if L.ckl_device_count() <= 0:
+            raise RuntimeError("crackle_b200: no CUDA device available (there is no CPU fallback)")
+        rc = L.ckl_ctx_create(int(device), ctypes.byref(self._h))
+        if rc:
+            raise RuntimeError(f"crackle_b200: ckl_ctx_create failed ({rc})")
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            _capi.lib().ckl_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            msg = _capi.lib().ckl_ctx_error(self._h).decode()
+            if rc == 2:
+                raise ValueError(msg)
+            raise RuntimeError(msg)
+
+    # -- compress ------------------------------------------------------------------------------------------
+    def compress_ptr(self, ptr, on_device, data_width, sx, sy, sz, fortran_order=True, markov_model_order=0) -> int:
+        n = ctypes.c_uint64()
+        self._check(_capi.lib().ckl_compress(self._h, ptr, int(on_device), int(data_width), sx, sy, sz,
+                                             int(bool(fortran_order)), int(markov_model_order), ctypes.byref(n)))
+        return n.value
+
+    def result_bytes(self) -> bytes:
+        n = ctypes.c_uint64()
+        _capi.lib().ckl_result_device(self._h, ctypes.byref(n))
+        buf = ctypes.create_string_buffer(n.value)
+        self._check(_capi.lib().ckl_result_copy(self._h, buf, 0, n.value))
+        return buf.raw
+
+    def result_to(self, ptr, on_device, capacity):
+        self._check(_capi.lib().ckl_result_copy(self._h, ptr, int(on_device), capacity))
+
+    def result_device(self):
+        n = ctypes.c_uint64()
+        p = _capi.lib().ckl_result_device(self._h, ctypes.byref(n))
+        return p, n.value
+
+    def compress(self, labels, markov_model_order=0, fortran_order=None) -> bytes:
+        """labels: numpy array (host) or torch CUDA tensor laid out (sz,sy,sx) C-contiguous (= Fortran x-fastest)."""
+        ptr, on_dev, width, (sx, sy, sz), f_order, keep = _as_fortran_volume(labels)
+        if fortran_order is not None:
+            f_order = fortran_order
+        self.compress_ptr(ptr, on_dev, width, sx, sy, sz, f_order, markov_model_order)
+        del keep
+        return self.result_bytes()
+
+    # -- decompress ----------------------------------------------------------------------------------------
+    def decompress_into(self, bin_ptr, bin_on_device, nbytes, z_start, z_end, label, out_ptr, out_on_device, out_cap):
+        self._check(_capi.lib().ckl_decompress(self._h, bin_ptr, int(bin_on_device), nbytes, int(z_start), int(z_end),
+                                               int(label is not None), int(label or 0), out_ptr, int(out_on_device), out_cap))
+
+    def decompress(self, binary, z_start=0, z_end=-1, label=None) -> np.ndarray:
+        """fastcrackle.decompress(binary, z_start, z_end, parallel, label): returns a 1-D numpy array."""
+        h = header(binary)
+        szr = _clamp_range(h, z_start, z_end)
+        buf = np.frombuffer(binary, dtype=np.uint8)
+        dt = np.uint8 if label is not None else np.dtype(f"u{h['data_width']}")
+        out = np.empty(h["sx"] * h["sy"] * szr, dtype=dt)
+        self.decompress_into(buf.ctypes.data, 0, buf.size, z_start, z_end, label, out.ctypes.data, 0, out.nbytes)
+        return out
+
+
+_default: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default
+    if _default is None:
+        dev = 0
+        try:
+            import torch
+            if torch.cuda.is_available():
+                dev = torch.cuda.current_device()
+        except Exception:
+            pass
+        _default = Context(dev)
+    return _default
+
+
+def _as_fortran_volume(labels):
+    """-> (pointer, on_device, itemsize, (sx,sy,sz), f_order flag, keepalive)"""
+    if isinstance(labels, np.ndarray):
+        if np.issubdtype(labels.dtype, np.signedinteger):
+            raise TypeError("Signed integer data types are not currently supported.")   # codec.py:720-721
+        if labels.dtype.kind not in "ub":
+            raise TypeError("crackle_b200: labels must be an unsigned integer array")
+        f_order = labels.flags.f_contiguous
+        a = np.asfortranarray(labels)                                                   # codec.py:723-724
+        s = list(a.shape) + [1, 1, 1]
+        return a.ctypes.data, 0, a.dtype.itemsize, (s[0], s[1], s[2]), f_order, a
+    import torch
+    if isinstance(labels, torch.Tensor):
+        if not labels.is_cuda or not labels.is_contiguous():
+            raise TypeError("crackle_b200: torch input must be a contiguous CUDA tensor shaped (sz, sy, sx)")
+        if labels.dtype not in (torch.uint8, torch.uint16, torch.uint32, torch.uint64):
+            raise TypeError("Signed integer data types are not currently supported.")
+        s = [1, 1, 1] + list(labels.shape)
+        sz, sy, sx = s[-3], s[-2], s[-1]
+        return labels.data_ptr(), 1, labels.element_size(), (sx, sy, sz), True, labels
+    raise TypeError("crackle_b200: unsupported input type")
+
+
+def header(binary) -> dict:
+    buf = np.frombuffer(binary, dtype=np.uint8)
+    info = _capi.HeaderInfo()
+    err = ctypes.create_string_buffer(256)
+    rc = _capi.lib().crackle_b200_header(buf.ctypes.data if buf.size else None, buf.size, ctypes.byref(info), err, 256)
+    if rc:
+        raise RuntimeError(err.value.decode())
+    return {n: getattr(info, n) for n, _ in _capi.HeaderInfo._fields_}
+
+
+def _clamp_range(h, z_start, z_end):
+    sz = h["sz"]
+    zs = max(min(z_start, sz - 1), 0)
+    ze = sz if z_end < 0 else max(min(z_end, sz), 0)
+    if zs >= ze:
+        if h["sx"] * h["sy"] * sz == 0:
+            return 0
+        raise RuntimeError(f"crackle: Invalid range: {zs} - {ze}")
+    return ze - zs
+
+
+# ---- the reference's public operator interface ---------------------------------------------------------------
+def compress(labels, allow_pins: int = 0, markov_model_order: int = 0, bgcolor: Optional[int] = None,
+             parallel: int = 0) -> bytes:
+    """crackle.compress (codec.py:689-733).  Flat labels only: allow_pins must be 0 on this path."""
+    if allow_pins:
+        raise NotImplementedError("crackle_b200: pin label formats are outside the flat-label hot path; "
+                                  "use the reference for allow_pins != 0")
+    return default_context().compress(labels, markov_model_order)
+
+
+def decompress_range(binary, z_start: Optional[int], z_end: Optional[int], parallel: int = 0,
+                     label: Optional[int] = None) -> np.ndarray:
+    """crackle.decompress_range (codec.py:632-687)."""
+    h = header(binary)
+    sx, sy, sz = h["sx"], h["sy"], h["sz"]
+    z_start = 0 if z_start is None else int(z_start)
+    z_end = sz if z_end is None else int(z_end)
+    order = "F" if h["fortran_order"] else "C"
+    dtype = np.dtype(f"u{h['data_width']}")
+    if sx * sy * sz == 0:
+        return np.zeros((0,), dtype=dtype).reshape((sx, sy, max(z_end - z_start, 0)), order=order)
+    out = default_context().decompress(binary, z_start, z_end, label)
+    szr = out.size // (sx * sy)
+    out = out.reshape((sx, sy, szr), order=order)
+    if label is not None:
+        return out.view(bool)
+    if h["is_signed"]:
+        out = out.view(np.dtype(f"i{h['data_width']}"))
+    return out
+
+
+def decompress(binary, label: Optional[int] = None, parallel: int = 0, crop: bool = False) -> np.ndarray:
+    """crackle.decompress (codec.py:616-630)."""
+    return decompress_range(binary, None, None, parallel, label)

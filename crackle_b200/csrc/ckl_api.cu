@@ -1,0 +1,673 @@
+// ckl_api.cu -- host orchestration and the C-ABI of libcrackle_b200.so.
+//
+// Stream assembly follows crackle::compress_helper (src/crackle.hpp:34-217) and the prologue of
+// crackle::decompress (src/crackle.hpp:503-582); header emit/parse follows src/header.hpp:98-267.
+// Error strings match the reference's std::runtime_error texts so a binding can re-raise them unchanged.
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "ckl_internal.cuh"
+
+void launch_exscan_u32_u64(const u32* in, u32 n, u32 stride, u64* out, ull* total_out, u64 add_each, cudaStream_t st);
+void launch_ccl_resolve(const Geom& g, const u32* DV, CclBufs& B, u64 total_runs, const CrcTables* d_tables, u32 crc_init_term, cudaStream_t st);
+void launch_markov_copy(const Geom& g, TraceBufs& T, MarkovBufs& M, u8* dst, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------------
+struct ShardJob {
+  bool active = false;
+  Geom g{};
+  const void* labels = nullptr;    // device pointer
+  int width = 0;
+  int permissible = 0, stored_width = 0, order = 0;
+  u64 runs = 0, ncomp = 0, nuniq_local = 0, ncp = 0;
+  u64 keys_bytes = 0, codes_bytes = 0;
+  int key_width = 0;
+  bool encoded = false, finished = false;
+};
+
+struct ckl_ctx {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  std::string err;
+  CrcTables htab;
+  CrcTables* dtab = nullptr;
+  ull* scal = nullptr;     // device scalars
+  ull* hscal = nullptr;    // pinned mirror
+  DBuf labels_dev, DV, DH;
+  CclBufs ccl;
+  TraceBufs tr;
+  MarkovBufs mk;
+  LabelBufs lb;
+  DecodeBufs dc;
+  DBuf result; u64 result_bytes = 0;
+  DBuf stream_dev, out_dev, tmp32, keys, codes;
+  ShardJob job;
+};
+
+static void set_err(char* err, size_t n, const std::string& m) {
+  if (err && n) { strncpy(err, m.c_str(), n - 1); err[n - 1] = 0; }
+}
+
+static void read_scalars(ckl_ctx* c) {
+  CUDA_CHECK(cudaMemcpyAsync(c->hscal, c->scal, SC_COUNT * sizeof(ull), cudaMemcpyDeviceToHost, c->st));
+  CUDA_CHECK(cudaStreamSynchronize(c->st));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// header (src/header.hpp)
+static int ilog2w(int w) { return w == 1 ? 0 : w == 2 ? 1 : w == 4 ? 2 : 3; }
+static void header_bytes_v1(u8* b, int data_width, int stored_width, int crack_format, int fortran, int order,
+                            u32 sx, u32 sy, u32 sz, u64 num_label_bytes) {
+  memcpy(b, "crkl", 4);
+  b[4] = 1;
+  const u32 fmt = (u32)ilog2w(data_width) | ((u32)ilog2w(stored_width) << 2) | ((u32)crack_format << 4) | (0u << 5) |
+                  ((u32)(fortran ? 1 : 0) << 7) | (0u << 8) | (((u32)order & 15u) << 9) | (0u << 13);
+  b[5] = (u8)fmt; b[6] = (u8)(fmt >> 8);
+  for (int i = 0; i < 4; i++) { b[7 + i] = (u8)(sx >> (8 * i)); b[11 + i] = (u8)(sy >> (8 * i)); b[15 + i] = (u8)(sz >> (8 * i)); }
+  b[19] = 31;                                                   // log2(grid_size = 2^31), crackle.hpp:87
+  for (int i = 0; i < 8; i++) b[20 + i] = (u8)(num_label_bytes >> (8 * i));
+  b[28] = crc8_header(b + 5, 23);
+}
+static u64 le_host(const u8* p, int w) { u64 v = 0; for (int i = 0; i < w; i++) v |= (u64)p[i] << (8 * i); return v; }
+
+static int parse_header(const u8* b, u64 n, ckl_header_info* h, std::string& err) {
+  if (n < 29) {   // crackle.hpp:513-517
+    err = "crackle: Input too small to be a valid stream. Bytes: " + std::to_string(n);
+    return CKL_ERR_STREAM;
+  }
+  if (memcmp(b, "crkl", 4) != 0 || b[4] > 1) {   // header.hpp:99-104
+    err = "crackle: Data stream is not valid. Unable to decompress.";
+    return CKL_ERR_STREAM;
+  }
+  h->format_version = b[4];
+  const u32 fmt = (u32)le_host(b + 5, 2);
+  h->sx = (u32)le_host(b + 7, 4); h->sy = (u32)le_host(b + 11, 4); h->sz = (u32)le_host(b + 15, 4);
+  h->num_label_bytes = h->format_version == 0 ? le_host(b + 20, 4) : le_host(b + 20, 8);
+  h->data_width = 1u << (fmt & 3); h->stored_data_width = 1u << ((fmt >> 2) & 3);
+  h->crack_format = (fmt >> 4) & 1; h->label_format = (fmt >> 5) & 3; h->fortran_order = (fmt >> 7) & 1;
+  h->is_signed = (fmt >> 8) & 1; h->markov_model_order = (fmt >> 9) & 15; h->is_sorted = !((fmt >> 13) & 1);
+  if (h->format_version > 0 && crc8_header(b + 5, 23) != b[28]) {   // header.hpp:145-149
+    err = "crackle: CRC8 check failed. Header may be corrupted. (~4.1% chance of a false positive for a single bit flip).";
+    return CKL_ERR_STREAM;
+  }
+  return CKL_OK;
+}
+static u64 model_bytes_for(int order) {   // header.hpp:284-297
+  if (order == 0) return 0;
+  return (((u64)1 << (2 * order)) * 5 + 4) / 8;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int ckl_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" int ckl_ctx_create(int device, ckl_ctx** out) {
+  if (!out) return CKL_ERR_ARG;
+  *out = nullptr;
+  if (ckl_device_count() <= device || device < 0) return CKL_ERR_CUDA;
+  ckl_ctx* c = new ckl_ctx();
+  try {
+    c->device = device;
+    CUDA_CHECK(cudaSetDevice(device));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    crc_build_tables(c->htab);
+    CUDA_CHECK(cudaMalloc(&c->dtab, sizeof(CrcTables)));
+    CUDA_CHECK(cudaMemcpy(c->dtab, &c->htab, sizeof(CrcTables), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&c->scal, SC_COUNT * sizeof(ull)));
+    CUDA_CHECK(cudaMallocHost(&c->hscal, SC_COUNT * sizeof(ull)));
+  } catch (const CklError& e) {
+    delete c;
+    return e.code;
+  }
+  *out = c;
+  return CKL_OK;
+}
+
+extern "C" void ckl_ctx_destroy(ckl_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->st) { cudaStreamSynchronize(c->st); cudaStreamDestroy(c->st); }
+  if (c->dtab) cudaFree(c->dtab);
+  if (c->scal) cudaFree(c->scal);
+  if (c->hscal) cudaFreeHost(c->hscal);
+  delete c;
+}
+extern "C" const char* ckl_ctx_error(const ckl_ctx* c) { return c ? c->err.c_str() : "null context"; }
+extern "C" const char* crackle_b200_version(void) { return "crackle_b200 0.1 (sm_100a)"; }
+
+#define API_BEGIN(c)                      \
+  if (!(c)) return CKL_ERR_ARG;           \
+  (c)->err.clear();                       \
+  try {                                   \
+    CUDA_CHECK(cudaSetDevice((c)->device));
+#define API_END(c)                                                                     \
+  }                                                                                    \
+  catch (const CklError& e) { (c)->err = e.what(); (c)->job.active = false; cudaGetLastError(); return e.code; } \
+  catch (const std::exception& e) { (c)->err = e.what(); (c)->job.active = false; return CKL_ERR_CUDA; }      \
+  return CKL_OK;
+
+// ---------------------------------------------------------------------------------------------------------
+// sharded compress stages
+static void shard_begin_impl(ckl_ctx* c, const void* labels, int on_device, int width, u64 sx, u64 sy, u64 sz, ckl_shard_summary* s) {
+  if (width != 1 && width != 2 && width != 4 && width != 8) throw CklError(CKL_ERR_ARG, "crackle_b200: data_width must be 1, 2, 4 or 8");
+  if (sx == 0 || sy == 0 || sz == 0) throw CklError(CKL_ERR_ARG, "crackle_b200: empty shard");
+  if (sx > 0xFFFFFFFFull || sy > 0xFFFFFFFFull || sz > 0xFFFFFFFFull || sx * sy >= (1ull << 30))
+    throw CklError(CKL_ERR_ARG, "crackle_b200: slice too large (sx*sy must be < 2^30)");
+  ShardJob& J = c->job;
+  J = ShardJob();
+  J.g.sx = (u32)sx; J.g.sy = (u32)sy; J.g.sz = (u32)sz; J.g.W = (u32)((sx + 31) / 32); J.g.sxy = sx * sy;
+  J.width = width;
+  const u64 voxels = sx * sy * sz;
+  if (on_device) J.labels = labels;
+  else {
+    c->labels_dev.ensure(voxels * (u64)width);
+    CUDA_CHECK(cudaMemcpyAsync(c->labels_dev.p, labels, voxels * (u64)width, cudaMemcpyHostToDevice, c->st));
+    J.labels = c->labels_dev.p;
+  }
+  const Geom& g = J.g;
+  c->DV.ensure(g.words() * 4);
+  c->DH.ensure(g.words() * 4);
+  CUDA_CHECK(cudaMemsetAsync(c->scal, 0, SC_COUNT * sizeof(ull), c->st));
+  launch_edges(J.labels, width, g, c->DV.as<u32>(), c->DH.as<u32>(), c->scal, c->st);
+  launch_ccl_count(g, c->DV.as<u32>(), c->ccl, c->scal, c->st);
+  // first / last voxel of the shard (for the pixel pair straddling shard boundaries)
+  u64 fl[2] = {0, 0};
+  CUDA_CHECK(cudaMemcpyAsync(&fl[0], J.labels, width, cudaMemcpyDeviceToHost, c->st));
+  CUDA_CHECK(cudaMemcpyAsync(&fl[1], (const u8*)J.labels + (voxels - 1) * (u64)width, width, cudaMemcpyDeviceToHost, c->st));
+  read_scalars(c);
+  J.runs = c->hscal[SC_RUNS];
+  s->max_label = c->hscal[SC_MAX];
+  s->pairs = c->hscal[SC_PAIRS];
+  s->first_voxel = fl[0];
+  s->last_voxel = fl[1];
+  s->voxels = voxels;
+  s->reserved[0] = s->reserved[1] = s->reserved[2] = 0;
+  J.active = true;
+}
+
+static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int order) {
+  ShardJob& J = c->job;
+  if (!J.active) throw CklError(CKL_ERR_ARG, "crackle_b200: ckl_shard_encode without ckl_shard_begin");
+  if (order < 0 || order > 12) throw CklError(CKL_ERR_ARG, "crackle_b200: markov_model_order must be in [0, 12]");
+  J.permissible = permissible ? 1 : 0;
+  J.stored_width = stored_width;
+  J.order = order;
+  const Geom& g = J.g;
+  cudaStream_t st = c->st;
+  // capacities for the tracer, components
+  launch_trace_prepare(g, c->DV.as<u32>(), c->DH.as<u32>(), J.permissible, c->tr, c->scal, st);
+  c->ccl.parent.ensure(J.runs * 4);
+  c->ccl.runStart.ensure(J.runs * 4);
+  c->ccl.compRank.ensure(J.runs * 4);
+  c->ccl.runComp.ensure(J.runs * 4);
+  c->ccl.compPix.ensure(J.runs * 4);
+  launch_ccl_solve(g, c->DV.as<u32>(), c->DH.as<u32>(), c->ccl, c->dtab, c->scal, st);
+  read_scalars(c);
+  J.ncomp = c->hscal[SC_COMPONENTS];
+  const u64 symCap = c->hscal[SC_SYMCAP], stackCap = c->hscal[SC_STACKCAP], chainCap = c->hscal[SC_CHAINCAP], cpCap = c->hscal[SC_CPCAP];
+  c->tr.sym.ensure(symCap);
+  c->tr.cpPrefix.ensure(symCap * 4);
+  c->tr.stack.ensure(stackCap * 8);
+  c->tr.chain.ensure(chainCap * sizeof(ChainRec));
+  c->tr.cp.ensure(cpCap);
+  launch_trace(g, c->tr, c->scal, st);
+  // component ranks, crcs, component labels
+  const u32 init_term = gf_mul(gf_xpow32(c->htab.pw, (u32)g.sxy), 0xFFFFFFFFu);
+  launch_ccl_resolve(g, c->DV.as<u32>(), c->ccl, J.runs, c->dtab, init_term, st);
+  c->lb.mapping.ensure(J.ncomp * 8 + 8);
+  launch_gather_mapping(J.labels, J.width, g, c->ccl, J.ncomp, c->lb.mapping.as<u64>(), st);
+  J.nuniq_local = labels_sort_unique(c->lb, J.ncomp, stored_width, st);
+  read_scalars(c);
+  if (c->hscal[SC_ERROR]) throw CklError(CKL_ERR_CUDA, "crackle_b200: internal tracer capacity error " + std::to_string(c->hscal[SC_ERROR]));
+  J.ncp = c->hscal[SC_CODEPOINTS];
+  if (order > 0) {
+    const u64 rows = 1ull << (2 * order);
+    c->mk.stats.ensure(rows * 16);
+    launch_markov_stats(g, c->tr, order, c->mk.stats.as<u32>(), st);
+  }
+  J.encoded = true;
+}
+
+// keys_dst / codes_dst: device destinations (may point into the final stream)
+static void shard_finish_impl(ckl_ctx* c, const u64* guniq_dev, u64 nuniq_global, const u32* gstats_dev, int order,
+                              bool materialise) {
+  ShardJob& J = c->job;
+  if (!J.encoded) throw CklError(CKL_ERR_ARG, "crackle_b200: ckl_shard_finish without ckl_shard_encode");
+  const Geom& g = J.g;
+  cudaStream_t st = c->st;
+  J.order = order;
+  J.key_width = ckl_byte_width(nuniq_global);
+  J.keys_bytes = J.ncomp * (u64)J.key_width;
+  if (materialise) {
+    c->keys.ensure(J.keys_bytes + 8);
+    launch_write_keys(c->lb.mapping.as<u64>(), J.ncomp, guniq_dev, nuniq_global, J.key_width, c->keys.as<u8>(), st);
+  }
+  if (order > 0) {
+    const u64 rows = 1ull << (2 * order);
+    c->mk.model.ensure(rows * 4);
+    c->mk.stored.ensure(model_bytes_for(order) + 16);
+    launch_markov_model(order, gstats_dev, c->mk.model.as<u8>(), c->mk.stored.as<u8>(), model_bytes_for(order), st);
+    launch_markov_sizes(g, c->tr, order, c->mk.model.as<u8>(), c->mk, c->scal, st);
+    const u64 scratch_words = (3 * J.ncp) / 32 + 2ull * g.sz + 64;
+    c->mk.scratch.ensure(scratch_words * 4);
+    CUDA_CHECK(cudaMemsetAsync(c->mk.scratch.p, 0, scratch_words * 4, st));
+    launch_markov_encode(g, c->tr, order, c->mk.model.as<u8>(), c->mk, nullptr, st);
+  }
+  launch_code_sizes_order0(g, c->tr, c->scal, st);     // scans sliceInfo[.codeBytes] (either format)
+  read_scalars(c);
+  J.codes_bytes = c->hscal[SC_CODE_BYTES];
+  J.finished = true;
+  if (!materialise) return;                              // single-GPU path places keys and codes in the stream itself
+  c->codes.ensure(J.codes_bytes + 8);
+  if (order > 0) launch_markov_copy(g, c->tr, c->mk, c->codes.as<u8>(), st);
+  else launch_pack_order0(g, c->tr, c->codes.as<u8>(), st);
+}
+
+__global__ void k_gather_stride4(const u32* __restrict__ src, u32 n, u32 off, u32* __restrict__ dst) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[(u64)i * 4 + off];
+}
+__global__ void k_store_bytes_u32(u8* dst, const u32* src) {
+  const u32 v = *src;
+  dst[0] = (u8)v; dst[1] = (u8)(v >> 8); dst[2] = (u8)(v >> 16); dst[3] = (u8)(v >> 24);
+}
+
+extern "C" int ckl_shard_begin(ckl_ctx* c, const void* labels, int labels_on_device, int data_width, uint64_t sx, uint64_t sy,
+                               uint64_t sz_local, ckl_shard_summary* summary) {
+  API_BEGIN(c)
+  if (!summary) throw CklError(CKL_ERR_ARG, "crackle_b200: null summary");
+  shard_begin_impl(c, labels, labels_on_device, data_width, sx, sy, sz_local, summary);
+  API_END(c)
+}
+extern "C" int ckl_shard_encode(ckl_ctx* c, int permissible, int stored_width, int markov_model_order, uint64_t* n_unique_local,
+                                uint64_t* n_components_local, uint64_t* n_codepoints_local) {
+  API_BEGIN(c)
+  shard_encode_impl(c, permissible, stored_width, markov_model_order);
+  if (n_unique_local) *n_unique_local = c->job.nuniq_local;
+  if (n_components_local) *n_components_local = c->job.ncomp;
+  if (n_codepoints_local) *n_codepoints_local = c->job.ncp;
+  API_END(c)
+}
+extern "C" int ckl_shard_unique(ckl_ctx* c, uint64_t* dst, int dst_on_device) {
+  API_BEGIN(c)
+  if (!c->job.encoded) throw CklError(CKL_ERR_ARG, "crackle_b200: no encoded shard");
+  if (c->job.nuniq_local) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, c->lb.uniq.p, c->job.nuniq_local * 8, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
+    CUDA_CHECK(cudaStreamSynchronize(c->st));
+  }
+  API_END(c)
+}
+extern "C" int ckl_shard_stats(ckl_ctx* c, uint32_t* dst, int dst_on_device) {
+  API_BEGIN(c)
+  if (!c->job.encoded || c->job.order <= 0) throw CklError(CKL_ERR_ARG, "crackle_b200: no markov statistics for this shard");
+  const u64 rows = 1ull << (2 * c->job.order);
+  CUDA_CHECK(cudaMemcpyAsync(dst, c->mk.stats.p, rows * 16, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
+  CUDA_CHECK(cudaStreamSynchronize(c->st));
+  API_END(c)
+}
+extern "C" int ckl_shard_finish(ckl_ctx* c, const uint64_t* global_unique, int unique_on_device, uint64_t n_unique_global,
+                                const uint32_t* global_stats, int stats_on_device, ckl_shard_pieces* pieces) {
+  API_BEGIN(c)
+  if (!pieces) throw CklError(CKL_ERR_ARG, "crackle_b200: null pieces");
+  const u64* gu = global_unique;
+  if (!unique_on_device) {
+    c->lb.sorted.ensure(n_unique_global * 8 + 8);
+    CUDA_CHECK(cudaMemcpyAsync(c->lb.sorted.p, global_unique, n_unique_global * 8, cudaMemcpyHostToDevice, c->st));
+    gu = c->lb.sorted.as<u64>();
+  }
+  int order = global_stats ? c->job.order : 0;
+  const u32* gs = global_stats;
+  if (order > 0 && !stats_on_device) {
+    const u64 rows = 1ull << (2 * order);
+    CUDA_CHECK(cudaMemcpyAsync(c->mk.stats.p, global_stats, rows * 16, cudaMemcpyHostToDevice, c->st));
+    gs = c->mk.stats.as<u32>();
+  }
+  shard_finish_impl(c, gu, n_unique_global, gs, order, true);
+  pieces->keys_bytes = c->job.keys_bytes;
+  pieces->codes_bytes = c->job.codes_bytes;
+  pieces->sz_local = c->job.g.sz;
+  API_END(c)
+}
+extern "C" int ckl_shard_fetch(ckl_ctx* c, uint8_t* keys, uint64_t* components_per_slice, uint32_t* code_sizes, uint32_t* slice_crcs,
+                               uint8_t* codes, int dst_on_device) {
+  API_BEGIN(c)
+  ShardJob& J = c->job;
+  if (!J.finished) throw CklError(CKL_ERR_ARG, "crackle_b200: ckl_shard_fetch without ckl_shard_finish");
+  const cudaMemcpyKind k = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  const u32 sz = J.g.sz;
+  if (keys && J.keys_bytes) CUDA_CHECK(cudaMemcpyAsync(keys, c->keys.p, J.keys_bytes, k, c->st));
+  if (codes && J.codes_bytes) CUDA_CHECK(cudaMemcpyAsync(codes, c->codes.p, J.codes_bytes, k, c->st));
+  if (slice_crcs) CUDA_CHECK(cudaMemcpyAsync(slice_crcs, c->ccl.sliceCrc.p, (u64)sz * 4, k, c->st));
+  std::vector<u32> nz;
+  if (components_per_slice) {
+    if (dst_on_device) throw CklError(CKL_ERR_ARG, "crackle_b200: components_per_slice is host-only");
+    nz.resize(sz);
+    CUDA_CHECK(cudaMemcpyAsync(nz.data(), c->ccl.nz.p, (u64)sz * 4, cudaMemcpyDeviceToHost, c->st));
+  }
+  if (code_sizes) {
+    c->tmp32.ensure((u64)sz * 4);
+    k_gather_stride4<<<(sz + 255) / 256, 256, 0, c->st>>>(c->tr.sliceInfo.as<u32>(), sz, 3, c->tmp32.as<u32>());
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(code_sizes, c->tmp32.p, (u64)sz * 4, k, c->st));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(c->st));
+  if (components_per_slice) for (u32 z = 0; z < sz; z++) components_per_slice[z] = nz[z];
+  API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// single-GPU compress = the three shard stages + stream assembly on the device
+extern "C" int ckl_compress(ckl_ctx* c, const void* labels, int labels_on_device, int data_width, uint64_t sx, uint64_t sy, uint64_t sz,
+                            int fortran_order, int markov_model_order, uint64_t* out_bytes) {
+  API_BEGIN(c)
+  if (data_width != 1 && data_width != 2 && data_width != 4 && data_width != 8)
+    throw CklError(CKL_ERR_ARG, "crackle_b200: data_width must be 1, 2, 4 or 8");
+  if (sx > 0xFFFFFFFFull || sy > 0xFFFFFFFFull || sz > 0xFFFFFFFFull) throw CklError(CKL_ERR_ARG, "crackle_b200: dimension exceeds uint32");
+  if (markov_model_order < 0 || markov_model_order > 12) throw CklError(CKL_ERR_ARG, "crackle_b200: markov_model_order must be in [0, 12]");
+  const u64 voxels = sx * sy * sz;
+  cudaStream_t st = c->st;
+  if (voxels == 0) {   // crackle.hpp:96-98: header only (crack format from pairs(0) < 0 == false)
+    u8 hb[29];
+    header_bytes_v1(hb, data_width, 1, 0, fortran_order, markov_model_order, (u32)sx, (u32)sy, (u32)sz, 0);
+    c->result.ensure(29);
+    CUDA_CHECK(cudaMemcpyAsync(c->result.p, hb, 29, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    c->result_bytes = 29;
+    if (out_bytes) *out_bytes = 29;
+    return CKL_OK;
+  }
+  ckl_shard_summary s;
+  shard_begin_impl(c, labels, labels_on_device, data_width, sx, sy, sz, &s);
+  const int permissible = (i64)s.pairs < (i64)voxels / 2;        // crackle.hpp:50-55
+  const int stored = ckl_byte_width(s.max_label);                // crackle.hpp:233-235
+  shard_encode_impl(c, permissible, stored, markov_model_order);
+  ShardJob& J = c->job;
+  int order = markov_model_order;
+  if (order > 0 && J.ncp == 0) order = 0;                        // crackle.hpp:107-118
+  const Geom& g = J.g;
+  const u64 nu = J.nuniq_local;
+  const int kw = ckl_byte_width(nu), cw = ckl_byte_width(g.sxy);
+  const u64 labels_bytes = 8 + nu * (u64)stored + (u64)g.sz * cw + J.ncomp * (u64)kw;
+  const u64 off_z = 29, off_lab = off_z + 4ull * (g.sz + 1), off_model = off_lab + labels_bytes;
+  const u64 off_codes = off_model + model_bytes_for(order);
+  // keys go straight into the stream; codes are placed once their total size is known
+  const u64 off_keys = off_lab + 8 + nu * (u64)stored + (u64)g.sz * cw;
+  shard_finish_impl(c, c->lb.uniq.as<u64>(), nu, order > 0 ? c->mk.stats.as<u32>() : nullptr, order, false);
+  const u64 total = off_codes + J.codes_bytes + 4 + 4ull * g.sz;
+  c->result.ensure(total + 16);
+  u8* R = c->result.as<u8>();
+  // header
+  u8 hb[29];
+  header_bytes_v1(hb, data_width, stored, permissible, fortran_order, order, g.sx, g.sy, g.sz, labels_bytes);
+  CUDA_CHECK(cudaMemcpyAsync(R, hb, 29, cudaMemcpyHostToDevice, st));
+  // z index: u32 code size per slice + crc32c of those bytes (crackle.hpp:173-185)
+  c->tmp32.ensure((u64)g.sz * 4 + 16);
+  k_gather_stride4<<<(g.sz + 255) / 256, 256, 0, st>>>(c->tr.sliceInfo.as<u32>(), g.sz, 3, c->tmp32.as<u32>());
+  CUDA_CHECK(cudaGetLastError());
+  launch_write_le_u32(c->tmp32.as<u32>(), g.sz, 4, R + off_z, st);
+  u32* crc_tmp = c->tmp32.as<u32>() + g.sz;
+  launch_crc_bytes(R + off_z, 4ull * g.sz, c->dtab, c->htab, crc_tmp, st);
+  k_store_bytes_u32<<<1, 1, 0, st>>>(R + off_z + 4ull * g.sz, crc_tmp);
+  // labels section (labels.hpp:123-152)
+  u8 nub[8];
+  for (int i = 0; i < 8; i++) nub[i] = (u8)(nu >> (8 * i));
+  CUDA_CHECK(cudaMemcpyAsync(R + off_lab, nub, 8, cudaMemcpyHostToDevice, st));
+  launch_write_uniq(c->lb.uniq.as<u64>(), nu, stored, R + off_lab + 8, st);
+  launch_write_le_u32(c->ccl.nz.as<u32>(), g.sz, cw, R + off_lab + 8 + nu * (u64)stored, st);
+  launch_write_keys(c->lb.mapping.as<u64>(), J.ncomp, c->lb.uniq.as<u64>(), nu, kw, R + off_keys, st);
+  // markov model + crack codes
+  if (order > 0) {
+    CUDA_CHECK(cudaMemcpyAsync(R + off_model, c->mk.stored.p, model_bytes_for(order), cudaMemcpyDeviceToDevice, st));
+    launch_markov_copy(g, c->tr, c->mk, R + off_codes, st);
+  } else {
+    launch_pack_order0(g, c->tr, R + off_codes, st);
+  }
+  // trailing crcs (crackle.hpp:187, 211-214)
+  launch_crc_bytes(R + off_lab, labels_bytes, c->dtab, c->htab, crc_tmp + 1, st);
+  k_store_bytes_u32<<<1, 1, 0, st>>>(R + off_codes + J.codes_bytes, crc_tmp + 1);
+  launch_write_le_u32(c->ccl.sliceCrc.as<u32>(), g.sz, 4, R + off_codes + J.codes_bytes + 4, st);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  c->result_bytes = total;
+  if (out_bytes) *out_bytes = total;
+  J.active = false;
+  API_END(c)
+}
+
+extern "C" int ckl_result_copy(ckl_ctx* c, void* dst, int dst_on_device, uint64_t capacity) {
+  API_BEGIN(c)
+  if (capacity < c->result_bytes) throw CklError(CKL_ERR_ARG, "crackle_b200: result buffer too small");
+  if (c->result_bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, c->result.p, c->result_bytes, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
+    CUDA_CHECK(cudaStreamSynchronize(c->st));
+  }
+  API_END(c)
+}
+extern "C" const void* ckl_result_device(ckl_ctx* c, uint64_t* bytes) {
+  if (!c) return nullptr;
+  if (bytes) *bytes = c->result_bytes;
+  return c->result.p;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// decompress
+__global__ void k_crc_compare(const u32* __restrict__ computed, const u8* __restrict__ stored, u32 n, ull* scal) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u8* p = stored + (u64)i * 4;
+  const u32 s = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
+  if (s != computed[i]) atomicMin(&scal[SC_CRC_BAD], (ull)i);
+}
+
+extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_device, uint64_t num_bytes, int64_t z_start, int64_t z_end,
+                              int has_label, uint64_t label, void* out, int out_on_device, uint64_t out_capacity) {
+  API_BEGIN(c)
+  cudaStream_t st = c->st;
+  if (num_bytes < 29) throw CklError(CKL_ERR_STREAM, "crackle: Input too small to be a valid stream. Bytes: " + std::to_string(num_bytes));
+  // the small sections are parsed on the host
+  std::vector<u8> hostcopy;
+  const u8* hb = (const u8*)binary;
+  if (binary_on_device) {
+    hostcopy.resize(num_bytes);
+    CUDA_CHECK(cudaMemcpyAsync(hostcopy.data(), binary, num_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    hb = hostcopy.data();
+  }
+  ckl_header_info h;
+  std::string perr;
+  int rc = parse_header(hb, num_bytes, &h, perr);
+  if (rc) throw CklError(rc, perr);
+  if (h.label_format != 0) throw CklError(CKL_ERR_UNSUPPORTED, "crackle_b200: pin label formats are outside the flat-label hot path; use the reference decoder");
+  const i64 sz = (i64)h.sz;
+  // crackle.hpp:527-537
+  z_start = std::max(std::min(z_start, sz - 1), (i64)0);
+  z_end = z_end < 0 ? sz : z_end;
+  z_end = std::max(std::min(z_end, sz), (i64)0);
+  if (z_start >= z_end) throw CklError(CKL_ERR_STREAM, "crackle: Invalid range: " + std::to_string(z_start) + " - " + std::to_string(z_end));
+  const u64 szr = (u64)(z_end - z_start);
+  const u64 sx = h.sx, sy = h.sy, sxy = sx * sy;
+  const u64 voxels = sxy * szr;
+  if (voxels == 0) return CKL_OK;
+  if (sxy >= (1ull << 30)) throw CklError(CKL_ERR_ARG, "crackle_b200: slice too large (sx*sy must be < 2^30)");
+  const int ow = has_label ? 1 : (int)h.data_width;
+  if (out_capacity < voxels * (u64)ow) throw CklError(CKL_ERR_ARG, "crackle_b200: output buffer too small");
+  const u64 hbytes = h.format_version == 0 ? 24 : 29;
+  const u64 zbytes = 4ull * (h.sz + (h.format_version == 0 ? 0 : 1));
+  if (hbytes + zbytes > num_bytes) throw CklError(CKL_ERR_STREAM, "crackle: get_crack_code_offsets: Unable to read past end of buffer.");
+  if (h.format_version > 0) {   // crackle.hpp:276-291
+    const u32 stored = (u32)le_host(hb + hbytes + 4ull * h.sz, 4);
+    const u32 computed = crc32c_host(c->htab, hb + hbytes, 4ull * h.sz);
+    if (stored != computed)
+      throw CklError(CKL_ERR_STREAM, "crackle: grid index crc32c did not match. stored: " + std::to_string(stored) + " computed: " + std::to_string(computed));
+  }
+  const int order = (int)h.markov_model_order;
+  const u64 mbytes = model_bytes_for(order);
+  std::vector<u64> off((u64)sz + 1);
+  off[0] = hbytes + zbytes + h.num_label_bytes + mbytes;
+  for (i64 z = 0; z < sz; z++) off[z + 1] = off[z] + le_host(hb + hbytes + 4ull * z, 4);
+  if (off[sz] > num_bytes) throw CklError(CKL_ERR_STREAM, "crackle: get_crack_codes: Unable to read past end of buffer.");
+  if (h.format_version > 0 && off[sz] + 4 + 4ull * h.sz > num_bytes)
+    throw CklError(CKL_ERR_STREAM, "crackle: get_crack_codes: Unable to read past end of buffer.");
+  // labels section (labels.hpp:453-506)
+  const u64 lab_off = hbytes + zbytes;
+  if (h.num_label_bytes < 8) throw CklError(CKL_ERR_STREAM, "crackle: labels section too small.");
+  const u64 nu = le_host(hb + lab_off, 8);
+  const int sw = (int)h.stored_data_width, kw = ckl_byte_width(nu), cw = ckl_byte_width(sxy);
+  const u64 uniq_off = lab_off + 8, nz_off = uniq_off + nu * (u64)sw, keys_off = nz_off + (u64)cw * h.sz;
+  if (nu > h.num_label_bytes || keys_off > lab_off + h.num_label_bytes)
+    throw CklError(CKL_ERR_STREAM, "crackle: labels section is inconsistent with the header.");
+  const u64 n_keys = (lab_off + h.num_label_bytes - keys_off) / (u64)kw;
+  std::vector<u64> keyBase(szr), stackOff(szr + 1), codeOff(szr + 1);
+  {
+    u64 kb = 0;
+    for (i64 z = 0; z < z_start; z++) kb += le_host(hb + nz_off + (u64)cw * z, cw);
+    stackOff[0] = 0;
+    for (u64 i = 0; i < szr; i++) {
+      const u64 z = (u64)z_start + i;
+      keyBase[i] = kb;
+      kb += le_host(hb + nz_off + (u64)cw * z, cw);
+      codeOff[i] = off[z];
+      stackOff[i + 1] = stackOff[i] + 2 * (off[z + 1] - off[z]) + 4;
+    }
+    codeOff[szr] = off[z_end];
+  }
+  // markov model: symbol of rank per context row (markov.hpp:382-420)
+  std::vector<u8> model;
+  if (order > 0) {
+    static const u8 perm_init = 0; (void)perm_init;
+    u8 lut[24]; int k = 0;
+    for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) for (int cc = 0; cc < 4; cc++) for (int d = 0; d < 4; d++) {
+      if (a == b || a == cc || a == d || b == cc || b == d || cc == d) continue;
+      lut[k++] = (u8)(a | b << 2 | cc << 4 | d << 6);
+    }
+    const u64 rows = 1ull << (2 * order);
+    model.resize(rows * 4);
+    const u8* ms = hb + lab_off + h.num_label_bytes;
+    for (u64 r = 0; r < rows; r++) {
+      const u64 bit = r * 5;
+      u32 v = ms[bit >> 3];
+      if ((bit >> 3) + 1 < mbytes) v |= (u32)ms[(bit >> 3) + 1] << 8;
+      const u8 packed = lut[((v >> (bit & 7)) & 31) % 24];
+      for (int q = 0; q < 4; q++) model[r * 4 + q] = (packed >> (2 * q)) & 3;
+    }
+  }
+  // device copies
+  const u8* dstream = (const u8*)binary;
+  if (!binary_on_device) {
+    c->stream_dev.ensure(num_bytes + 8);
+    CUDA_CHECK(cudaMemcpyAsync(c->stream_dev.p, binary, num_bytes, cudaMemcpyHostToDevice, st));
+    dstream = c->stream_dev.as<u8>();
+  }
+  DecodeBufs& D = c->dc;
+  D.codeOff.ensure((szr + 1) * 8); D.keyBase.ensure(szr * 8); D.stackOff.ensure((szr + 1) * 8);
+  CUDA_CHECK(cudaMemcpyAsync(D.codeOff.p, codeOff.data(), (szr + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(D.keyBase.p, keyBase.data(), szr * 8, cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(D.stackOff.p, stackOff.data(), (szr + 1) * 8, cudaMemcpyHostToDevice, st));
+  D.stack.ensure(stackOff[szr] * 4 + 16);
+  if (order > 0) {
+    D.model.ensure(model.size());
+    CUDA_CHECK(cudaMemcpyAsync(D.model.p, model.data(), model.size(), cudaMemcpyHostToDevice, st));
+  }
+  Geom g;
+  g.sx = h.sx; g.sy = h.sy; g.sz = (u32)szr; g.W = (u32)((sx + 31) / 32); g.sxy = sxy;
+  c->DV.ensure(g.words() * 4);
+  c->DH.ensure(g.words() * 4);
+  CUDA_CHECK(cudaMemsetAsync(c->scal, 0, SC_COUNT * sizeof(ull), st));
+  const ull none = ~0ull;
+  CUDA_CHECK(cudaMemcpyAsync(&c->scal[SC_CRC_BAD], &none, 8, cudaMemcpyHostToDevice, st));
+  launch_decode_slices(g, dstream, D.codeOff.as<u64>(), (int)h.crack_format, order, D.model.as<u8>(), c->DV.as<u32>(), c->DH.as<u32>(),
+                       D.stack.as<u32>(), D.stackOff.as<u64>(), c->scal, st);
+  launch_planes_from_cracks(g, (int)h.crack_format, c->DV.as<u32>(), c->DH.as<u32>(), st);
+  launch_ccl_count(g, c->DV.as<u32>(), c->ccl, c->scal, st);
+  read_scalars(c);
+  if (c->hscal[SC_ERROR]) {
+    if (h.crack_format) throw CklError(CKL_ERR_STREAM, "crackle: decode_permissible_crack_code: index out of range.");
+    throw CklError(CKL_ERR_STREAM, "crackle: decode_impermissible_crack_code: index out of range.");
+  }
+  const u64 runs = c->hscal[SC_RUNS];
+  c->ccl.parent.ensure(runs * 4); c->ccl.runStart.ensure(runs * 4); c->ccl.compRank.ensure(runs * 4);
+  c->ccl.runComp.ensure(runs * 4); c->ccl.compPix.ensure(runs * 4);
+  launch_ccl_solve(g, c->DV.as<u32>(), c->DH.as<u32>(), c->ccl, c->dtab, c->scal, st);
+  const u32 init_term = gf_mul(gf_xpow32(c->htab.pw, (u32)g.sxy), 0xFFFFFFFFu);
+  launch_ccl_resolve(g, c->DV.as<u32>(), c->ccl, runs, c->dtab, init_term, st);
+  if (h.format_version > 0) {   // crackle.hpp:599-611
+    k_crc_compare<<<(g.sz + 255) / 256, 256, 0, st>>>(c->ccl.sliceCrc.as<u32>(), dstream + num_bytes - 4ull * h.sz + 4ull * (u64)z_start, g.sz, c->scal);
+    CUDA_CHECK(cudaGetLastError());
+    read_scalars(c);
+    if (c->hscal[SC_CRC_BAD] != none) {
+      const u64 zi = c->hscal[SC_CRC_BAD];
+      u32 computed = 0;
+      CUDA_CHECK(cudaMemcpy(&computed, c->ccl.sliceCrc.as<u32>() + zi, 4, cudaMemcpyDeviceToHost));
+      const u32 stored = (u32)le_host(hb + num_bytes - 4ull * h.sz + 4ull * ((u64)z_start + zi), 4);
+      throw CklError(CKL_ERR_STREAM, "crackle: crack code crc mismatch on z=" + std::to_string((u64)z_start + zi) + " computed: " +
+                                         std::to_string(computed) + " stored: " + std::to_string(stored));
+    }
+  }
+  D.runLabel.ensure(runs * 8 + 8);
+  launch_run_labels(g, c->ccl, dstream, uniq_off, keys_off, nu, n_keys, sw, kw, D.keyBase.as<u64>(), D.runLabel.as<u64>(), st);
+  void* dout = out;
+  if (!out_on_device) { c->out_dev.ensure(voxels * (u64)ow); dout = c->out_dev.p; }
+  launch_paint(g, c->DV.as<u32>(), c->ccl, D.runLabel.as<u64>(), ow, has_label, label, (int)h.fortran_order, dout, st);
+  if (!out_on_device) CUDA_CHECK(cudaMemcpyAsync(out, dout, voxels * (u64)ow, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// one-shot host API on a lazily created default context (device = current CUDA device)
+static std::mutex g_mu;
+static ckl_ctx* g_default = nullptr;
+static ckl_ctx* default_ctx(std::string& err, int& code) {
+  if (!g_default) {
+    int dev = 0;
+    if (ckl_device_count() <= 0) { err = "crackle_b200: no CUDA device available (there is no CPU fallback)"; code = CKL_ERR_CUDA; return nullptr; }
+    cudaGetDevice(&dev);
+    code = ckl_ctx_create(dev, &g_default);
+    if (code) { err = "crackle_b200: failed to create a CUDA context"; return nullptr; }
+  }
+  return g_default;
+}
+
+extern "C" int crackle_b200_compress(const void* labels, int data_width, uint64_t sx, uint64_t sy, uint64_t sz, int fortran_order,
+                                     int markov_model_order, uint8_t** out, uint64_t* out_bytes, char* err, size_t err_len) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out || !out_bytes) { set_err(err, err_len, "crackle_b200: null output pointer"); return CKL_ERR_ARG; }
+  *out = nullptr; *out_bytes = 0;
+  std::string e; int code = 0;
+  ckl_ctx* c = default_ctx(e, code);
+  if (!c) { set_err(err, err_len, e); return code; }
+  u64 n = 0;
+  code = ckl_compress(c, labels, 0, data_width, sx, sy, sz, fortran_order, markov_model_order, &n);
+  if (code) { set_err(err, err_len, c->err); return code; }
+  u8* buf = (u8*)malloc(n ? n : 1);
+  if (!buf) { set_err(err, err_len, "crackle_b200: out of host memory"); return CKL_ERR_NOMEM; }
+  code = ckl_result_copy(c, buf, 0, n);
+  if (code) { free(buf); set_err(err, err_len, c->err); return code; }
+  *out = buf; *out_bytes = n;
+  return CKL_OK;
+}
+
+extern "C" int crackle_b200_decompress(const uint8_t* binary, uint64_t num_bytes, int64_t z_start, int64_t z_end, int has_label,
+                                       uint64_t label, void* out, uint64_t out_capacity, char* err, size_t err_len) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::string e; int code = 0;
+  ckl_ctx* c = default_ctx(e, code);
+  if (!c) { set_err(err, err_len, e); return code; }
+  code = ckl_decompress(c, binary, 0, num_bytes, z_start, z_end, has_label, label, out, 0, out_capacity);
+  if (code) set_err(err, err_len, c->err);
+  return code;
+}
+
+extern "C" void crackle_b200_free(void* p) { free(p); }
+
+extern "C" int crackle_b200_header(const uint8_t* binary, uint64_t num_bytes, ckl_header_info* info, char* err, size_t err_len) {
+  if (!binary || !info) { set_err(err, err_len, "crackle_b200: null argument"); return CKL_ERR_ARG; }
+  std::string e;
+  const int rc = parse_header(binary, num_bytes, info, e);
+  if (rc) set_err(err, err_len, e);
+  return rc;
+}

@@ -1,0 +1,104 @@
+// ckl_internal.cuh -- internal interfaces between the translation units of libcrackle_b200.so
+#pragma once
+#include "ckl_common.cuh"
+
+struct Geom {
+  u32 sx, sy, sz;     // sz = slices held by this context (a z-slab for sharded jobs)
+  u32 W;              // 32-pixel words per row = ceil(sx/32)
+  u64 sxy;            // sx*sy  (< 2^31)
+  __host__ __device__ u64 rows() const { return (u64)sy * sz; }
+  __host__ __device__ u64 words() const { return (u64)sy * sz * W; }
+};
+
+// ---- device scalars written by kernels and read back in one small copy --------------------------------
+enum {
+  SC_MAX = 0, SC_PAIRS, SC_RUNS, SC_COMPONENTS, SC_EDGES, SC_SYMCAP, SC_STACKCAP, SC_CHAINCAP, SC_CPCAP,
+  SC_CODEPOINTS, SC_CODE_BYTES, SC_ERROR, SC_UNIQUE, SC_FIRST, SC_LAST, SC_CRC_BAD, SC_COUNT = 24
+};
+
+// ---- planes + CCL (ckl_planes.cu) ------------------------------------------------------------------------
+struct CclBufs {
+  DBuf wordPrefix, rowRuns, rowBase, sliceRuns, runBase;   // per word / row / slice
+  DBuf parent, runStart, compRank, runComp;                // per run (allocated once the run total is known)
+  DBuf nz, compBase, compPix;                              // per slice / per component
+  DBuf sliceCrc;                                           // raw CRC accumulators, per slice
+};
+
+void launch_edges(const void* labels, int width, const Geom& g, u32* DV, u32* DH, ull* scal, cudaStream_t st);
+// phase 1: per-row run prefixes, per-slice run counts and bases; writes scal[SC_RUNS]
+void launch_ccl_count(const Geom& g, const u32* DV, CclBufs& B, ull* scal, cudaStream_t st);
+// phase 2 (parent/runStart/compRank/runComp/compPix must hold `total_runs`): union-find, ranks, N_z, crcs;
+// writes scal[SC_COMPONENTS]
+void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, const CrcTables* d_tables,
+                      ull* scal, cudaStream_t st);
+// generic device CRC-32C of a byte buffer: result (finalised) written to *d_out
+void launch_crc_bytes(const u8* d, u64 n, const CrcTables* d_tables, const CrcTables& h_tables, u32* d_out, cudaStream_t st);
+// finalise per-slice raw registers into standard CRCs (in place)
+void launch_crc_finalize_slices(u32* sliceCrc, u32 sz, u32 init_term, cudaStream_t st);
+
+// ---- tracing + packing (ckl_trace.cu) ------------------------------------------------------------------
+struct TraceBufs {
+  DBuf EV, EH;                                  // mutable crack planes
+  DBuf bounds;                                  // per slice: E, B, C  (3 x u32 x sz)
+  DBuf offs;                                    // per slice u64 offsets: sym, stack, chain, cp  (4 x (sz+1))
+  DBuf sym, stack, chain, cp, cpPrefix;         // sized from scal[SC_*CAP]
+  DBuf sliceInfo;                               // per slice: ncp, nchains, boc_bytes, code_bytes (4 x u32 x sz)
+  DBuf codeOff;                                 // u64 x (sz+1) byte offsets of each slice's crack code
+};
+struct ChainRec { u32 adjStart, symBegin, symEnd, t2f; u32 ncp, outBase, sortedIdx, sortedStart; };
+
+void launch_trace_prepare(const Geom& g, const u32* DV, const u32* DH, int permissible, TraceBufs& T, ull* scal, cudaStream_t st);
+void launch_trace(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st);
+// order 0: per-slice code sizes -> codeOff (exclusive scan, total in scal[SC_CODE_BYTES]) then pack into dst
+void launch_code_sizes_order0(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st);
+void launch_pack_order0(const Geom& g, TraceBufs& T, u8* dst, cudaStream_t st);
+
+// ---- markov (ckl_markov.cu) ------------------------------------------------------------------------------
+struct MarkovBufs {
+  DBuf stats;      // u32[4^order][4]
+  DBuf model;      // u8[4^order][4]  rank of symbol
+  DBuf stored;     // stored model bytes
+  DBuf bitlen;     // per slice u64 bit counts
+  DBuf scratch;    // per-slice word-aligned bitstreams
+  DBuf scratchOff; // u64 x (sz+1) word offsets
+};
+void launch_markov_stats(const Geom& g, TraceBufs& T, int order, u32* stats, cudaStream_t st);
+void launch_markov_model(int order, const u32* stats, u8* model, u8* stored, u64 stored_bytes, cudaStream_t st);
+void launch_markov_sizes(const Geom& g, TraceBufs& T, int order, const u8* model, MarkovBufs& M, ull* scal, cudaStream_t st);
+void launch_markov_encode(const Geom& g, TraceBufs& T, int order, const u8* model, MarkovBufs& M, u8* dst, cudaStream_t st);
+
+// ---- label table (ckl_labels.cu) -------------------------------------------------------------------------
+struct LabelBufs {
+  DBuf mapping;    // u64 per component (z order)
+  DBuf sorted;     // u64 per component
+  DBuf uniq;       // u64 per unique label
+  DBuf tmp;        // cub temp storage
+  DBuf flags;
+};
+void launch_gather_mapping(const void* labels, int width, const Geom& g, const CclBufs& B, u64 ncomp, u64* mapping, cudaStream_t st);
+// sorts + uniques `mapping` (n items) into L.uniq; returns count on host (synchronises the stream)
+u64 labels_sort_unique(LabelBufs& L, u64 n, int stored_width, cudaStream_t st);
+// keys[i] = index of mapping[i] in uniq (n_uniq entries), written little-endian with key_width bytes
+void launch_write_keys(const u64* mapping, u64 n, const u64* uniq, u64 n_uniq, int key_width, u8* dst, cudaStream_t st);
+// uniq table written little-endian with `stored_width` bytes per entry
+void launch_write_uniq(const u64* uniq, u64 n_uniq, int stored_width, u8* dst, cudaStream_t st);
+// little-endian packing of u32 / u64 arrays with an arbitrary byte width
+void launch_write_le_u32(const u32* src, u64 n, int width, u8* dst, cudaStream_t st);
+
+// ---- decode (ckl_decode.cu) ------------------------------------------------------------------------------
+struct DecodeBufs {
+  DBuf codeOff;     // u64 x (szr+1): absolute offsets of each decoded slice's crack code inside the stream
+  DBuf keyBase;     // u64 x szr: first key index of each decoded slice
+  DBuf storedNz;    // u32 x szr
+  DBuf model;       // u8[4^order][4]: symbol of rank
+  DBuf stack;       // per-slice revisit stacks
+  DBuf stackOff;
+  DBuf runLabel;    // u64 per run
+};
+void launch_decode_slices(const Geom& g, const u8* stream, const u64* codeOff, int permissible, int order,
+                          const u8* model, u32* EV, u32* EH, u32* stack, const u64* stackOff, ull* scal, cudaStream_t st);
+void launch_planes_from_cracks(const Geom& g, int permissible, u32* EV, u32* EH, cudaStream_t st);
+void launch_run_labels(const Geom& g, const CclBufs& B, const u8* stream, u64 uniq_off, u64 keys_off, u64 n_uniq,
+                       u64 n_keys_total, int stored_width, int key_width, const u64* keyBase, u64* runLabel, cudaStream_t st);
+void launch_paint(const Geom& g, const u32* DV, const CclBufs& B, const u64* runLabel, int out_width, int has_label,
+                  u64 label, int fortran_order, void* out, cudaStream_t st);

@@ -1,0 +1,443 @@
+// ckl_planes.cu -- label volume -> "differ" bit-planes (the only full-width read of compress), run-based
+// per-slice 4-connected component labelling on the bit-planes, raster-order component ranks, and the
+// CRC-32C of each slice's (virtual) uint32 component image.
+//
+// Reference behaviour reproduced (results, not code):
+//   lib::max_label / lib::pixel_pairs                  src/lib.hpp:224-256
+//   Graph::init edge predicate                         src/crackcodes.hpp:66-125
+//   cc3d::connected_components2d_4 / color_connectivity_graph + relabel   src/cc3d.hpp:114-369
+//       final ids = rank of each component's first pixel in x-fastest raster order
+//   crc32c(cc_labels)                                  src/labels.hpp:81, src/crackle.hpp:599-611
+#include "ckl_internal.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T shfl_up1(T v) {
+  if constexpr (sizeof(T) == 8) return (T)__shfl_up_sync(FULL_MASK, (ull)v, 1);
+  else return (T)__shfl_up_sync(FULL_MASK, (u32)v, 1);
+}
+
+// One warp owns a strip of RS rows of one 32-pixel word column: lane <-> x, rows walked in registers so the
+// up-neighbour is the previous iteration's value; the left neighbour comes from the lane below (lane 0 reads
+// it).  DV bit x of row y: label(x,y) != label(x-1,y) (x>0).  DH bit: label(x,y) != label(x,y-1) (y>0).
+template <typename T, int RS>
+__global__ void __launch_bounds__(256) k_edges(const T* __restrict__ L, Geom g, u32* __restrict__ DV,
+                                                u32* __restrict__ DH, ull* scal) {
+  const u32 lane = threadIdx.x & 31;
+  const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
+  const u32 ntile = (g.sy + RS - 1) / RS;
+  const u64 items = (u64)g.sz * ntile * g.W;
+  u64 mx = 0, pairs = 0;
+  for (u64 it = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < items; it += nwarps) {
+    const u32 w = (u32)(it % g.W);
+    const u64 t = it / g.W;
+    const u32 tile = (u32)(t % ntile), z = (u32)(t / ntile);
+    const u32 y0 = tile * RS;
+    const u32 nr = min((u32)RS, g.sy - y0);
+    const u32 x = w * 32 + lane;
+    const bool inx = x < g.sx;
+    const T* base = L + (u64)z * g.sxy;
+    T cur[RS], lf[RS];
+    T up = 0;
+    if (inx && y0 > 0) up = base[(u64)(y0 - 1) * g.sx + x];
+#pragma unroll
+    for (int r = 0; r < RS; r++) {
+      cur[r] = 0;
+      if (r < (int)nr && inx) cur[r] = base[(u64)(y0 + r) * g.sx + x];
+    }
+#pragma unroll
+    for (int r = 0; r < RS; r++) {
+      lf[r] = 0;
+      if (lane == 0 && r < (int)nr) {
+        const u64 flat = (u64)z * g.sxy + (u64)(y0 + r) * g.sx + x;
+        if (flat > 0) lf[r] = L[flat - 1];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RS; r++) {
+      if (r < (int)nr) {
+        const u32 y = y0 + r;
+        const T v = cur[r];
+        T l = shfl_up1<T>(v);
+        if (lane == 0) l = lf[r];
+        const bool has_prev = x > 0 || y > 0 || z > 0;          // flat index > 0
+        pairs += (inx && has_prev && v == l) ? 1 : 0;
+        const bool vd = inx && x > 0 && v != l;
+        const bool hd = inx && y > 0 && v != up;
+        const u32 vb = __ballot_sync(FULL_MASK, vd), hb = __ballot_sync(FULL_MASK, hd);
+        if (lane == 0) {
+          const u64 o = ((u64)z * g.sy + y) * g.W + w;
+          DV[o] = vb;
+          DH[o] = hb;
+        }
+        up = v;
+        if (inx) mx = max(mx, (u64)v);
+      }
+    }
+  }
+  // block reduction -> two atomics per block
+  __shared__ u64 s_mx[8], s_pr[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = max(mx, (u64)__shfl_xor_sync(FULL_MASK, (ull)mx, o));
+    pairs += (u64)__shfl_xor_sync(FULL_MASK, (ull)pairs, o);
+  }
+  if (lane == 0) { s_mx[threadIdx.x >> 5] = mx; s_pr[threadIdx.x >> 5] = pairs; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (u32 i = 1; i < (blockDim.x >> 5); i++) { mx = max(mx, s_mx[i]); pairs += s_pr[i]; }
+    atomicMax(&scal[SC_MAX], (ull)mx);
+    atomicAdd(&scal[SC_PAIRS], (ull)pairs);
+  }
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+static u32 grid_for(u64 items, u32 per_block, u32 blocks_per_sm) {
+  u64 need = (items + per_block - 1) / per_block;
+  u64 cap = (u64)num_sms() * blocks_per_sm;
+  if (need < 1) need = 1;
+  return (u32)(need < cap ? need : cap);
+}
+
+void launch_edges(const void* labels, int width, const Geom& g, u32* DV, u32* DH, ull* scal, cudaStream_t st) {
+  constexpr int RS = 16;
+  const u64 items = (u64)g.sz * ((g.sy + RS - 1) / RS) * g.W;
+  const u32 grid = grid_for(items, 8, 8);
+  switch (width) {
+    case 1: k_edges<u8, RS><<<grid, 256, 0, st>>>((const u8*)labels, g, DV, DH, scal); break;
+    case 2: k_edges<u16, RS><<<grid, 256, 0, st>>>((const u16*)labels, g, DV, DH, scal); break;
+    case 4: k_edges<u32, RS><<<grid, 256, 0, st>>>((const u32*)labels, g, DV, DH, scal); break;
+    default: k_edges<u64, RS><<<grid, 256, 0, st>>>((const u64*)labels, g, DV, DH, scal); break;
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// runs: a run is a maximal horizontal segment without a vertical crack.  Run index inside a row = number of DV
+// bits at positions <= x; slice-local run id = rowBase[row] + that.
+__global__ void __launch_bounds__(256) k_row_prefix(Geom g, const u32* __restrict__ DV, u32* __restrict__ wordPrefix,
+                                                     u32* __restrict__ rowRuns) {
+  const u32 lane = threadIdx.x & 31;
+  const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
+  const u64 rows = g.rows();
+  for (u64 row = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += nwarps) {
+    u32 carry = 0;
+    for (u32 w0 = 0; w0 < g.W; w0 += 32) {
+      const u32 w = w0 + lane;
+      const u32 v = w < g.W ? DV[row * g.W + w] : 0;
+      const u32 c = __popc(v);
+      const u32 inc = warp_incl_scan(c);
+      if (w < g.W) wordPrefix[row * g.W + w] = carry + inc - c;
+      carry += __shfl_sync(FULL_MASK, inc, 31);
+    }
+    if (lane == 0) rowRuns[row] = carry + 1;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_slice_scan(Geom g, const u32* __restrict__ rowRuns, u32* __restrict__ rowBase,
+                                                     u32* __restrict__ sliceRuns) {
+  __shared__ u32 sm[33];
+  for (u32 z = blockIdx.x; z < g.sz; z += gridDim.x) {
+    u32 carry = 0;
+    for (u32 y0 = 0; y0 < g.sy; y0 += blockDim.x) {
+      const u32 y = y0 + threadIdx.x;
+      const u32 v = y < g.sy ? rowRuns[(u64)z * g.sy + y] : 0;
+      u32 tot;
+      const u32 ex = block_excl_scan(v, sm, tot);
+      if (y < g.sy) rowBase[(u64)z * g.sy + y] = carry + ex;
+      carry += tot;
+    }
+    if (threadIdx.x == 0) sliceRuns[z] = carry;
+  }
+}
+
+// single-block exclusive scan of n strided u32 values into u64 out[0..n] (out[n] = total), total also to *total_out
+__global__ void __launch_bounds__(1024) k_exscan_u32_u64(const u32* __restrict__ in, u32 n, u32 stride, u64* __restrict__ out,
+                                                          ull* total_out, u64 add_each) {
+  __shared__ u64 swarp[33];
+  const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  u64 carry = 0;
+  for (u32 i0 = 0; i0 < n; i0 += blockDim.x) {
+    const u32 i = i0 + threadIdx.x;
+    const u64 v = i < n ? (u64)in[(u64)i * stride] + add_each : 0;
+    u64 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      u64 t = __shfl_up_sync(FULL_MASK, (ull)inc, o);
+      if (lane >= (u32)o) inc += t;
+    }
+    if (lane == 31) swarp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      u64 s = swarp[lane];
+      u64 si = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        u64 t = __shfl_up_sync(FULL_MASK, (ull)si, o);
+        if (lane >= (u32)o) si += t;
+      }
+      swarp[lane] = si - s;
+      if (lane == 31) swarp[32] = si;
+    }
+    __syncthreads();
+    if (i < n) out[i] = carry + swarp[wid] + inc - v;
+    carry += swarp[32];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[n] = carry;
+    if (total_out) *total_out = carry;
+  }
+}
+void launch_exscan_u32_u64(const u32* in, u32 n, u32 stride, u64* out, ull* total_out, u64 add_each, cudaStream_t st) {
+  k_exscan_u32_u64<<<1, 1024, 0, st>>>(in, n, stride, out, total_out, add_each);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_ccl_count(const Geom& g, const u32* DV, CclBufs& B, ull* scal, cudaStream_t st) {
+  B.wordPrefix.ensure(g.words() * 4);
+  B.rowRuns.ensure(g.rows() * 4);
+  B.rowBase.ensure(g.rows() * 4);
+  B.sliceRuns.ensure((u64)g.sz * 4);
+  B.runBase.ensure(((u64)g.sz + 1) * 8);
+  k_row_prefix<<<grid_for(g.rows(), 8, 8), 256, 0, st>>>(g, DV, B.wordPrefix.as<u32>(), B.rowRuns.as<u32>());
+  CUDA_CHECK(cudaGetLastError());
+  k_slice_scan<<<grid_for(g.sz, 1, 8), 256, 0, st>>>(g, B.rowRuns.as<u32>(), B.rowBase.as<u32>(), B.sliceRuns.as<u32>());
+  CUDA_CHECK(cudaGetLastError());
+  launch_exscan_u32_u64(B.sliceRuns.as<u32>(), g.sz, 1, B.runBase.as<u64>(), &scal[SC_RUNS], 0, st);
+}
+
+__device__ __forceinline__ u32 mask_le(u32 b) { return (2u << b) - 1u; }   // bits 0..b (b = 31 -> all ones)
+
+__global__ void __launch_bounds__(256) k_run_init(Geom g, const u32* __restrict__ DV, const u32* __restrict__ wordPrefix,
+                                                   const u32* __restrict__ rowBase, const u64* __restrict__ runBase,
+                                                   u32* __restrict__ parent, u32* __restrict__ runStart) {
+  const u64 nwords = g.words(), stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) {
+    const u64 row = i / g.W;
+    const u32 w = (u32)(i - row * g.W);
+    const u32 z = (u32)(row / g.sy), y = (u32)(row - (u64)z * g.sy);
+    const u32 dv = DV[i];
+    u32 starts = dv | (w == 0 ? 1u : 0u);
+    const u32 rb = rowBase[row] + wordPrefix[i];
+    const u64 gb = runBase[z];
+    while (starts) {
+      const u32 b = __ffs(starts) - 1;
+      starts &= starts - 1;
+      const u32 rid = rb + __popc(dv & mask_le(b));
+      parent[gb + rid] = rid;
+      runStart[gb + rid] = y * g.sx + w * 32 + b;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_run_union(Geom g, const u32* __restrict__ DV, const u32* __restrict__ DH,
+                                                    const u32* __restrict__ wordPrefix, const u32* __restrict__ rowBase,
+                                                    const u64* __restrict__ runBase, u32* parent) {
+  const u64 nwords = g.words(), stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) {
+    const u64 row = i / g.W;
+    const u32 w = (u32)(i - row * g.W);
+    const u32 z = (u32)(row / g.sy), y = (u32)(row - (u64)z * g.sy);
+    if (y == 0) continue;
+    const u32 valid = (w == g.W - 1 && (g.sx & 31)) ? ((1u << (g.sx & 31)) - 1u) : 0xFFFFFFFFu;
+    const u32 dv = DV[i], dvu = DV[i - g.W];
+    const u32 conn = ~DH[i] & valid;                       // pixel connected to the pixel above
+    u32 cand = conn & (dv | dvu | ~(conn << 1));           // first pixel of every (run, upper run, group) overlap
+    if (!cand) continue;
+    const u32 rb = rowBase[row] + wordPrefix[i], rbu = rowBase[row - 1] + wordPrefix[i - g.W];
+    u32* par = parent + runBase[z];
+    while (cand) {
+      const u32 b = __ffs(cand) - 1;
+      cand &= cand - 1;
+      uf_unite(par, rb + __popc(dv & mask_le(b)), rbu + __popc(dvu & mask_le(b)));
+    }
+  }
+}
+
+// per slice: rank of every root run among the slice's roots (= raster rank of the component's first pixel)
+__global__ void __launch_bounds__(256) k_root_rank(Geom g, const u32* __restrict__ parent, const u32* __restrict__ sliceRuns,
+                                                    const u64* __restrict__ runBase, u32* __restrict__ compRank,
+                                                    u32* __restrict__ nz) {
+  __shared__ u32 sm[33];
+  for (u32 z = blockIdx.x; z < g.sz; z += gridDim.x) {
+    const u32 n = sliceRuns[z];
+    const u64 gb = runBase[z];
+    u32 carry = 0;
+    for (u32 i0 = 0; i0 < n; i0 += blockDim.x) {
+      const u32 i = i0 + threadIdx.x;
+      const u32 f = (i < n && __ldcg(parent + gb + i) == i) ? 1u : 0u;
+      u32 tot;
+      const u32 ex = block_excl_scan(f, sm, tot);
+      if (f) compRank[gb + i] = carry + ex;
+      carry += tot;
+    }
+    if (threadIdx.x == 0) nz[z] = carry;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_run_resolve(Geom g, u64 total_runs, const u32* __restrict__ parent,
+                                                      const u64* __restrict__ runBase, const u32* __restrict__ compRank,
+                                                      const u32* __restrict__ runStart, const u64* __restrict__ compBase,
+                                                      u32* __restrict__ runComp, u32* __restrict__ compPix) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < total_runs; r += stride) {
+    // slice of this run: last z with runBase[z] <= r
+    u32 lo = 0, hi = g.sz;
+    while (hi - lo > 1) { const u32 m = (lo + hi) >> 1; if (runBase[m] <= r) lo = m; else hi = m; }
+    const u64 gb = runBase[lo];
+    const u32 i = (u32)(r - gb);
+    const u32 root = uf_find(parent + gb, i);
+    const u32 c = compRank[gb + root];
+    runComp[r] = c;
+    if (root == i) compPix[compBase[lo] + c] = runStart[r];
+  }
+}
+
+// CRC-32C of the virtual uint32 image cc[x,y] = runComp[run(x,y)], one thread per 32-pixel word, combined with
+// x^(32 * pixels_after) so the per-slice accumulator is the raw register of the whole image.
+__global__ void __launch_bounds__(256) k_cc_crc(Geom g, const u32* __restrict__ DV, const u32* __restrict__ wordPrefix,
+                                                 const u32* __restrict__ rowBase, const u64* __restrict__ runBase,
+                                                 const u32* __restrict__ runComp, const CrcTables* __restrict__ tabs,
+                                                 u32* sliceCrc) {
+  __shared__ u32 t[4][256];
+  __shared__ u32 pw[4][256];
+  for (u32 i = threadIdx.x; i < 1024; i += blockDim.x) {
+    (&t[0][0])[i] = (&tabs->t[0][0])[i];
+    (&pw[0][0])[i] = (&tabs->pw[0][0])[i];
+  }
+  __syncthreads();
+  const u64 nwords = g.words(), stride = (u64)gridDim.x * blockDim.x;
+  const u64 nloop = (nwords + stride - 1) / stride;
+  for (u64 k = 0; k < nloop; k++) {
+    const u64 i = k * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 crc = 0, z = 0xFFFFFFFFu;
+    if (i < nwords) {
+      const u64 row = i / g.W;
+      const u32 w = (u32)(i - row * g.W);
+      z = (u32)(row / g.sy);
+      const u32 y = (u32)(row - (u64)z * g.sy);
+      const u32 dv = DV[i];
+      const u32 npx = min(32u, g.sx - w * 32);
+      const u32* rc = runComp + runBase[z];
+      u32 rid = rowBase[row] + wordPrefix[i] + (dv & 1u);
+      u32 comp = rc[rid];
+      crc = crc_word(t, 0, comp);
+      for (u32 b = 1; b < npx; b++) {
+        if ((dv >> b) & 1u) { rid++; comp = rc[rid]; }
+        crc = crc_word(t, crc, comp);
+      }
+      const u32 after = (u32)(g.sxy - ((u64)y * g.sx + (u64)w * 32 + npx));
+      if (after) crc = gf_mul(crc, gf_xpow32(pw, after));
+    }
+    // warp aggregation when every lane is in the same slice
+    const u32 z0 = __shfl_sync(FULL_MASK, z, 0);
+    if (__all_sync(FULL_MASK, z == z0)) {
+      const u32 x = __reduce_xor_sync(FULL_MASK, crc);
+      if ((threadIdx.x & 31) == 0 && z0 != 0xFFFFFFFFu) atomicXor(sliceCrc + z0, x);
+    } else if (z != 0xFFFFFFFFu) {
+      atomicXor(sliceCrc + z, crc);
+    }
+  }
+}
+
+__global__ void k_crc_finalize(u32* crc, u32 n, u32 init_term) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) crc[i] = ~(crc[i] ^ init_term);
+}
+void launch_crc_finalize_slices(u32* sliceCrc, u32 sz, u32 init_term, cudaStream_t st) {
+  k_crc_finalize<<<(sz + 255) / 256, 256, 0, st>>>(sliceCrc, sz, init_term);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, const CrcTables* d_tables, ull* scal,
+                      cudaStream_t st) {
+  const u64 nwords = g.words();
+  B.nz.ensure((u64)g.sz * 4);
+  B.compBase.ensure(((u64)g.sz + 1) * 8);
+  B.sliceCrc.ensure((u64)g.sz * 4);
+  u32* parent = B.parent.as<u32>();
+  k_run_init<<<grid_for(nwords, 256, 16), 256, 0, st>>>(g, DV, B.wordPrefix.as<u32>(), B.rowBase.as<u32>(), B.runBase.as<u64>(),
+                                                         parent, B.runStart.as<u32>());
+  CUDA_CHECK(cudaGetLastError());
+  k_run_union<<<grid_for(nwords, 256, 16), 256, 0, st>>>(g, DV, DH, B.wordPrefix.as<u32>(), B.rowBase.as<u32>(),
+                                                          B.runBase.as<u64>(), parent);
+  CUDA_CHECK(cudaGetLastError());
+  k_root_rank<<<grid_for(g.sz, 1, 8), 256, 0, st>>>(g, parent, B.sliceRuns.as<u32>(), B.runBase.as<u64>(), B.compRank.as<u32>(),
+                                                     B.nz.as<u32>());
+  CUDA_CHECK(cudaGetLastError());
+  launch_exscan_u32_u64(B.nz.as<u32>(), g.sz, 1, B.compBase.as<u64>(), &scal[SC_COMPONENTS], 0, st);
+}
+
+// second half of the solve: needs total_runs on the host (grid sizing) -- split so the caller can interleave
+void launch_ccl_resolve(const Geom& g, const u32* DV, CclBufs& B, u64 total_runs, const CrcTables* d_tables, u32 crc_init_term,
+                        cudaStream_t st) {
+  k_run_resolve<<<grid_for(total_runs, 256, 16), 256, 0, st>>>(g, total_runs, B.parent.as<u32>(), B.runBase.as<u64>(),
+                                                                B.compRank.as<u32>(), B.runStart.as<u32>(), B.compBase.as<u64>(),
+                                                                B.runComp.as<u32>(), B.compPix.as<u32>());
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaMemsetAsync(B.sliceCrc.p, 0, (u64)g.sz * 4, st));
+  k_cc_crc<<<grid_for(g.words(), 256, 8), 256, 0, st>>>(g, DV, B.wordPrefix.as<u32>(), B.rowBase.as<u32>(), B.runBase.as<u64>(),
+                                                         B.runComp.as<u32>(), d_tables, B.sliceCrc.as<u32>());
+  CUDA_CHECK(cudaGetLastError());
+  launch_crc_finalize_slices(B.sliceCrc.as<u32>(), g.sz, crc_init_term, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// generic CRC-32C of a device byte buffer
+__global__ void __launch_bounds__(256) k_crc_bytes(const u8* __restrict__ d, u64 n, const CrcTables* __restrict__ tabs, u32* acc) {
+  __shared__ u32 t[4][256];
+  __shared__ u32 pw[4][256];
+  for (u32 i = threadIdx.x; i < 1024; i += blockDim.x) {
+    (&t[0][0])[i] = (&tabs->t[0][0])[i];
+    (&pw[0][0])[i] = (&tabs->pw[0][0])[i];
+  }
+  __syncthreads();
+  // message = head (n % 4 bytes, run from the real init state by chunk 0) || body of whole uint32 words
+  const u64 head = n & 3, nw = n >> 2;
+  const u64 CH = 16;                                   // words per chunk
+  const u64 nchunks = (nw + CH - 1) / CH;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  u32 x = 0;
+  for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < (nchunks ? nchunks : 1); c += stride) {
+    u32 crc = 0;
+    if (c == 0) {
+      crc = 0xFFFFFFFFu;                               // carries the init term for the whole message
+      for (u64 i = 0; i < head; i++) crc = crc_byte(t, crc, d[i]);
+    }
+    const u64 w0 = c * CH, w1 = min(nw, w0 + CH);
+    for (u64 wi = w0; wi < w1; wi++) {
+      const u8* p = d + head + wi * 4;
+      const u32 v = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
+      crc = crc_word(t, crc, v);
+    }
+    u64 after = nw - w1;
+    while (after) {
+      const u32 part = (u32)(after > 0xFFFFFFFFull ? 0xFFFFFFFFull : after);
+      crc = gf_mul(crc, gf_xpow32(pw, part));
+      after -= part;
+    }
+    x ^= crc;
+  }
+  x = __reduce_xor_sync(FULL_MASK, x);
+  if ((threadIdx.x & 31) == 0 && x) atomicXor(acc, x);
+}
+__global__ void k_not(u32* v) { *v = ~*v; }
+
+void launch_crc_bytes(const u8* d, u64 n, const CrcTables* d_tables, const CrcTables& h_tables, u32* d_out, cudaStream_t st) {
+  (void)h_tables;
+  CUDA_CHECK(cudaMemsetAsync(d_out, 0, 4, st));
+  const u64 nchunks = ((n >> 2) + 15) / 16;
+  k_crc_bytes<<<grid_for(nchunks ? nchunks : 1, 256, 8), 256, 0, st>>>(d, n, d_tables, d_out);
+  CUDA_CHECK(cudaGetLastError());
+  k_not<<<1, 1, 0, st>>>(d_out);
+  CUDA_CHECK(cudaGetLastError());
+}

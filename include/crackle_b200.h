@@ -1,0 +1,142 @@
+/*
+ * crackle_b200.h -- C-ABI of the B200-native crackle hot path (libcrackle_b200.so).
+ *
+ * Plain pointers and sizes only; no C++ / torch types cross this boundary.  These entry points are what the
+ * reference's pybind11 boundary (src/fastcrackle.cpp) binds for the per-z-slice path:
+ *
+ *   crackle_b200_compress    replaces  fastcrackle.compress   (src/fastcrackle.cpp:131-210  ->
+ *                                      crackle::compress<LABEL> src/crackle.hpp:220-257), flat labels only
+ *   crackle_b200_decompress  replaces  fastcrackle.decompress (src/fastcrackle.cpp:41-129   ->
+ *                                      crackle::decompress<LABEL,OUT> src/crackle.hpp:503-663)
+ *   crackle_b200_free        mirrors the malloc/free contract of the reference's own C-ABI precedent
+ *                            (wasm/crackle_wasm.cc:20-67: crackle_compress / crackle_decompress)
+ *
+ * The ckl_ctx_* / ckl_* functions are the same operations on an explicit per-GPU context with device-resident
+ * buffers (what a z-sharded multi-GPU caller or a benchmark uses so volumes never leave HBM).
+ *
+ * All functions return 0 on success and a non-zero code on failure; the message text follows the reference's
+ * std::runtime_error strings ("crackle: ...") so a binding can re-raise them unchanged.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with CKL_ERR_CUDA.
+ */
+#ifndef CRACKLE_B200_H
+#define CRACKLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CKL_API __attribute__((visibility("default")))
+#else
+#define CKL_API
+#endif
+
+enum {
+  CKL_OK = 0,
+  CKL_ERR_CUDA = 1,          /* no device / CUDA runtime failure                                     */
+  CKL_ERR_ARG = 2,           /* bad argument (unsupported width, sizes, signed input, ...)           */
+  CKL_ERR_STREAM = 3,        /* invalid / corrupt .ckl stream (message matches the reference's text) */
+  CKL_ERR_UNSUPPORTED = 4,   /* valid stream outside this path (pin label formats): use the reference */
+  CKL_ERR_NOMEM = 5
+};
+
+typedef struct ckl_ctx ckl_ctx;
+
+/* Parsed .ckl header (src/header.hpp:35-308). */
+typedef struct ckl_header_info {
+  uint32_t format_version, label_format, crack_format, is_signed;
+  uint32_t data_width, stored_data_width, fortran_order, markov_model_order;
+  uint32_t sx, sy, sz, is_sorted;
+  uint64_t num_label_bytes;
+} ckl_header_info;
+
+/* ---- one-shot host API: the drop-in boundary ------------------------------------------------------------ */
+
+/* labels: HOST pointer to sx*sy*sz unsigned integers of `data_width` bytes in Fortran order (x fastest).
+ * fortran_order: header flag only (src/crackle.hpp:90).  On success *out is a malloc'ed buffer of *out_bytes
+ * (release with crackle_b200_free).  err/err_len: optional message buffer. */
+CKL_API int crackle_b200_compress(const void* labels, int data_width, uint64_t sx, uint64_t sy, uint64_t sz,
+                          int fortran_order, int markov_model_order, uint8_t** out, uint64_t* out_bytes,
+                          char* err, size_t err_len);
+
+/* Decodes slices [z_start, z_end) (clamped exactly like src/crackle.hpp:527-537; z_end < 0 means sz) into the
+ * HOST buffer `out` of out_capacity bytes: data_width-byte labels, or 1 byte per voxel (label mask) when
+ * has_label != 0.  Output memory order follows the stream's fortran_order flag (src/crackle.hpp:617-656). */
+CKL_API int crackle_b200_decompress(const uint8_t* binary, uint64_t num_bytes, int64_t z_start, int64_t z_end,
+                            int has_label, uint64_t label, void* out, uint64_t out_capacity,
+                            char* err, size_t err_len);
+
+CKL_API void crackle_b200_free(void* p);
+
+/* Host-only header parse (no GPU needed); validates magic, version and crc8 like src/header.hpp:98-150. */
+CKL_API int crackle_b200_header(const uint8_t* binary, uint64_t num_bytes, ckl_header_info* info, char* err, size_t err_len);
+
+/* ---- explicit context API (device-resident buffers) ------------------------------------------------------ */
+
+CKL_API int ckl_ctx_create(int device, ckl_ctx** ctx);
+CKL_API void ckl_ctx_destroy(ckl_ctx* ctx);
+CKL_API const char* ckl_ctx_error(const ckl_ctx* ctx);           /* message of the last failure on this context */
+CKL_API int ckl_device_count(void);
+
+/* Compress; `labels` is a host (labels_on_device == 0) or device pointer.  The stream is left in a
+ * context-owned device buffer; fetch it with ckl_result_copy / ckl_result_device. */
+CKL_API int ckl_compress(ckl_ctx* ctx, const void* labels, int labels_on_device, int data_width,
+                 uint64_t sx, uint64_t sy, uint64_t sz, int fortran_order, int markov_model_order,
+                 uint64_t* out_bytes);
+CKL_API int ckl_result_copy(ckl_ctx* ctx, void* dst, int dst_on_device, uint64_t capacity);
+CKL_API const void* ckl_result_device(ckl_ctx* ctx, uint64_t* bytes);
+
+/* Decompress; `binary` host or device, `out` host or device. */
+CKL_API int ckl_decompress(ckl_ctx* ctx, const void* binary, int binary_on_device, uint64_t num_bytes,
+                   int64_t z_start, int64_t z_end, int has_label, uint64_t label,
+                   void* out, int out_on_device, uint64_t out_capacity);
+
+/* ---- z-sharded multi-GPU compress (one context per GPU; the caller moves the small blobs between ranks,
+ *      e.g. with torch.distributed all_gather over NCCL).  Mirrors what operations.zstack /
+ *      _zstack_flat_labels (crackle/operations.py:258-295, 424-548) do for independently compressed slabs. --- */
+
+/* Per-shard summary exchanged between ranks (fixed size, little-endian, 64 bytes). */
+typedef struct ckl_shard_summary {
+  uint64_t max_label;        /* lib::max_label over the shard                                        */
+  uint64_t pairs;            /* lib::pixel_pairs inside the shard (excludes the pair with the previous shard) */
+  uint64_t first_voxel;      /* value of the shard's first voxel (flat index 0)                      */
+  uint64_t last_voxel;       /* value of the shard's last voxel                                      */
+  uint64_t voxels;
+  uint64_t reserved[3];
+} ckl_shard_summary;
+
+/* Stage 1: edge bit-planes + local reductions for a z-slab held on this GPU. */
+CKL_API int ckl_shard_begin(ckl_ctx* ctx, const void* labels, int labels_on_device, int data_width,
+                    uint64_t sx, uint64_t sy, uint64_t sz_local, ckl_shard_summary* summary);
+/* Stage 2 (after the summaries are all-reduced): crack codes, CCL, CRCs, sorted unique labels of the shard.
+ * permissible / stored_width are the GLOBAL decisions.  markov stats (if order > 0) are accumulated locally. */
+CKL_API int ckl_shard_encode(ckl_ctx* ctx, int permissible, int stored_width, int markov_model_order,
+                     uint64_t* n_unique_local, uint64_t* n_components_local, uint64_t* n_codepoints_local);
+/* Copies the shard's sorted unique labels (uint64 each) to dst (host or device). */
+CKL_API int ckl_shard_unique(ckl_ctx* ctx, uint64_t* dst, int dst_on_device);
+/* Markov statistics of the shard: uint32[4^order * 4] (wrap mod 2^32 like the reference's atomics). */
+CKL_API int ckl_shard_stats(ckl_ctx* ctx, uint32_t* dst, int dst_on_device);
+/* Stage 3: given the GLOBAL sorted unique table (and, for order > 0, the GLOBAL stats), produce this shard's
+ * pieces: keys (key_width bytes per component), N_z table entries, per-slice crack codes, per-slice crcs. */
+typedef struct ckl_shard_pieces {
+  uint64_t keys_bytes;         /* n_components_local * key_width                                     */
+  uint64_t codes_bytes;        /* concatenated crack codes of the shard's slices                     */
+  uint64_t sz_local;
+} ckl_shard_pieces;
+CKL_API int ckl_shard_finish(ckl_ctx* ctx, const uint64_t* global_unique, int unique_on_device, uint64_t n_unique_global,
+                     const uint32_t* global_stats, int stats_on_device, ckl_shard_pieces* pieces);
+/* Copies the pieces out (each may be NULL to skip): keys, component counts (uint64 per slice), code sizes
+ * (uint32 per slice), slice crcs (uint32 per slice), codes. */
+CKL_API int ckl_shard_fetch(ckl_ctx* ctx, uint8_t* keys, uint64_t* components_per_slice, uint32_t* code_sizes,
+                    uint32_t* slice_crcs, uint8_t* codes, int dst_on_device);
+
+/* Library / build information. */
+CKL_API const char* crackle_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRACKLE_B200_H */
