@@ -49,6 +49,12 @@ SYMBOLS = {
     "ckl_shard_stats": (cint, [vp, vp, cint]),
     "ckl_shard_finish": (cint, [vp, vp, cint, u64, vp, cint, ctypes.POINTER(ShardPieces)]),
     "ckl_shard_fetch": (cint, [vp, vp, vp, vp, vp, vp, cint]),
+    "ckl_prof_enable": (cint, [vp, cint]),
+    "ckl_prof_read": (cint, [vp, ctypes.c_char_p, ctypes.c_size_t]),
+    "ckl_launch_count": (u64, []),
+    "ckl_ctx_set_stream": (cint, [vp, vp]),
+    "ckl_crc32c": (cint, [vp, vp, cint, u64, ctypes.POINTER(u32)]),
+    "ckl_sort_unique_u64": (cint, [vp, vp, u64, cint, ctypes.POINTER(u64)]),
 }
 
 

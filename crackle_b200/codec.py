@@ -43,6 +43,26 @@ class Context:
                 raise ValueError(msg)
             raise RuntimeError(msg)
 
+    # -- instrumentation -----------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        """Run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); None restores the own one."""
+        self._check(_capi.lib().ckl_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def prof_enable(self, on=True):
+        _capi.lib().ckl_prof_enable(self._h, int(on))
+
+    def prof_read(self) -> dict:
+        """{stage: (total_ms, calls)} accumulated since prof_enable."""
+        buf = ctypes.create_string_buffer(8192)
+        _capi.lib().ckl_prof_read(self._h, buf, 8192)
+        out = {}
+        for item in buf.value.decode().split(";"):
+            if item:
+                k, v = item.split("=")
+                ms, n = v.split(":")
+                out[k] = (float(ms), int(n))
+        return out
+
     # -- compress ------------------------------------------------------------------------------------------
     def compress_ptr(self, ptr, on_device, data_width, sx, sy, sz, fortran_order=True, markov_model_order=0) -> int:
         n = ctypes.c_uint64()
@@ -88,6 +108,10 @@ class Context:
         out = np.empty(h["sx"] * h["sy"] * szr, dtype=dt)
         self.decompress_into(buf.ctypes.data, 0, buf.size, z_start, z_end, label, out.ctypes.data, 0, out.nbytes)
         return out
+
+
+def launch_count() -> int:
+    return int(_capi.lib().ckl_launch_count())
 
 
 _default: Optional[Context] = None

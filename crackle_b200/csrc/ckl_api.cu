@@ -12,6 +12,8 @@
 void launch_exscan_u32_u64(const u32* in, u32 n, u32 stride, u64* out, ull* total_out, u64 add_each, cudaStream_t st);
 void launch_ccl_resolve(const Geom& g, const u32* DV, CclBufs& B, u64 total_runs, const CrcTables* d_tables, u32 crc_init_term, cudaStream_t st);
 void launch_markov_copy(const Geom& g, TraceBufs& T, MarkovBufs& M, u8* dst, cudaStream_t st);
+void launch_trace_walk(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st);
+void launch_trace_post(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------------
 struct ShardJob {
@@ -26,9 +28,43 @@ struct ShardJob {
   bool encoded = false, finished = false;
 };
 
+unsigned long long g_ckl_launches = 0;
+
+// optional per-stage timing with CUDA events on the context's stream
+struct Prof {
+  bool on = false;
+  struct Rec { std::string name; cudaEvent_t a, b; };
+  std::vector<Rec> pending;
+  std::vector<std::pair<std::string, double>> acc;   // name -> accumulated ms
+  std::vector<u64> cnt;
+  void begin(const char* name, cudaStream_t st) {
+    if (!on) return;
+    Rec r; r.name = name;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    pending.push_back(r);
+  }
+  void end(cudaStream_t st) { if (on && !pending.empty()) cudaEventRecord(pending.back().b, st); }
+  void collect() {
+    for (auto& r : pending) {
+      cudaEventSynchronize(r.b);
+      float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+      size_t i = 0;
+      for (; i < acc.size(); i++) if (acc[i].first == r.name) break;
+      if (i == acc.size()) { acc.emplace_back(r.name, 0.0); cnt.push_back(0); }
+      acc[i].second += ms; cnt[i]++;
+      cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    pending.clear();
+  }
+};
+#define STAGE(c, name, ...) do { (c)->prof.begin(name, (c)->st); __VA_ARGS__; (c)->prof.end((c)->st); } while (0)
+
 struct ckl_ctx {
+  Prof prof;
   int device = 0;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr, own_st = nullptr;
+  bool ext_stream = false;
   std::string err;
   CrcTables htab;
   CrcTables* dtab = nullptr;
@@ -113,7 +149,8 @@ extern "C" int ckl_ctx_create(int device, ckl_ctx** out) {
   try {
     c->device = device;
     CUDA_CHECK(cudaSetDevice(device));
-    CUDA_CHECK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_st, cudaStreamNonBlocking));
+    c->st = c->own_st;
     crc_build_tables(c->htab);
     CUDA_CHECK(cudaMalloc(&c->dtab, sizeof(CrcTables)));
     CUDA_CHECK(cudaMemcpy(c->dtab, &c->htab, sizeof(CrcTables), cudaMemcpyHostToDevice));
@@ -130,7 +167,8 @@ extern "C" int ckl_ctx_create(int device, ckl_ctx** out) {
 extern "C" void ckl_ctx_destroy(ckl_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  if (c->st) { cudaStreamSynchronize(c->st); cudaStreamDestroy(c->st); }
+  if (c->st) cudaStreamSynchronize(c->st);
+  if (c->own_st) cudaStreamDestroy(c->own_st);
   if (c->dtab) cudaFree(c->dtab);
   if (c->scal) cudaFree(c->scal);
   if (c->hscal) cudaFreeHost(c->hscal);
@@ -172,8 +210,8 @@ static void shard_begin_impl(ckl_ctx* c, const void* labels, int on_device, int 
   c->DV.ensure(g.words() * 4);
   c->DH.ensure(g.words() * 4);
   CUDA_CHECK(cudaMemsetAsync(c->scal, 0, SC_COUNT * sizeof(ull), c->st));
-  launch_edges(J.labels, width, g, c->DV.as<u32>(), c->DH.as<u32>(), c->scal, c->st);
-  launch_ccl_count(g, c->DV.as<u32>(), c->ccl, c->scal, c->st);
+  STAGE(c, "edges", launch_edges(J.labels, width, g, c->DV.as<u32>(), c->DH.as<u32>(), c->scal, c->st));
+  STAGE(c, "ccl_count", launch_ccl_count(g, c->DV.as<u32>(), c->ccl, c->scal, c->st));
   // first / last voxel of the shard (for the pixel pair straddling shard boundaries)
   u64 fl[2] = {0, 0};
   CUDA_CHECK(cudaMemcpyAsync(&fl[0], J.labels, width, cudaMemcpyDeviceToHost, c->st));
@@ -199,13 +237,13 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   const Geom& g = J.g;
   cudaStream_t st = c->st;
   // capacities for the tracer, components
-  launch_trace_prepare(g, c->DV.as<u32>(), c->DH.as<u32>(), J.permissible, c->tr, c->scal, st);
+  STAGE(c, "trace_prepare", launch_trace_prepare(g, c->DV.as<u32>(), c->DH.as<u32>(), J.permissible, c->tr, c->scal, st));
   c->ccl.parent.ensure(J.runs * 4);
   c->ccl.runStart.ensure(J.runs * 4);
   c->ccl.compRank.ensure(J.runs * 4);
   c->ccl.runComp.ensure(J.runs * 4);
   c->ccl.compPix.ensure(J.runs * 4);
-  launch_ccl_solve(g, c->DV.as<u32>(), c->DH.as<u32>(), c->ccl, c->dtab, c->scal, st);
+  STAGE(c, "ccl_solve", launch_ccl_solve(g, c->DV.as<u32>(), c->DH.as<u32>(), c->ccl, c->dtab, c->scal, st));
   read_scalars(c);
   J.ncomp = c->hscal[SC_COMPONENTS];
   const u64 symCap = c->hscal[SC_SYMCAP], stackCap = c->hscal[SC_STACKCAP], chainCap = c->hscal[SC_CHAINCAP], cpCap = c->hscal[SC_CPCAP];
@@ -214,20 +252,23 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   c->tr.stack.ensure(stackCap * 8);
   c->tr.chain.ensure(chainCap * sizeof(ChainRec));
   c->tr.cp.ensure(cpCap);
-  launch_trace(g, c->tr, c->scal, st);
+  STAGE(c, "trace_walk", launch_trace_walk(g, c->tr, c->scal, st));
+  STAGE(c, "trace_post", launch_trace_post(g, c->tr, c->scal, st));
   // component ranks, crcs, component labels
   const u32 init_term = gf_mul(gf_xpow32(c->htab.pw, (u32)g.sxy), 0xFFFFFFFFu);
-  launch_ccl_resolve(g, c->DV.as<u32>(), c->ccl, J.runs, c->dtab, init_term, st);
+  STAGE(c, "ccl_resolve_crc", launch_ccl_resolve(g, c->DV.as<u32>(), c->ccl, J.runs, c->dtab, init_term, st));
   c->lb.mapping.ensure(J.ncomp * 8 + 8);
+  c->prof.begin("labels_sort_unique", st);
   launch_gather_mapping(J.labels, J.width, g, c->ccl, J.ncomp, c->lb.mapping.as<u64>(), st);
   J.nuniq_local = labels_sort_unique(c->lb, J.ncomp, stored_width, st);
+  c->prof.end(st);
   read_scalars(c);
   if (c->hscal[SC_ERROR]) throw CklError(CKL_ERR_CUDA, "crackle_b200: internal tracer capacity error " + std::to_string(c->hscal[SC_ERROR]));
   J.ncp = c->hscal[SC_CODEPOINTS];
   if (order > 0) {
     const u64 rows = 1ull << (2 * order);
     c->mk.stats.ensure(rows * 16);
-    launch_markov_stats(g, c->tr, order, c->mk.stats.as<u32>(), st);
+    STAGE(c, "markov_stats", launch_markov_stats(g, c->tr, order, c->mk.stats.as<u32>(), st));
   }
   J.encoded = true;
 }
@@ -255,7 +296,7 @@ static void shard_finish_impl(ckl_ctx* c, const u64* guniq_dev, u64 nuniq_global
     const u64 scratch_words = (3 * J.ncp) / 32 + 2ull * g.sz + 64;
     c->mk.scratch.ensure(scratch_words * 4);
     CUDA_CHECK(cudaMemsetAsync(c->mk.scratch.p, 0, scratch_words * 4, st));
-    launch_markov_encode(g, c->tr, order, c->mk.model.as<u8>(), c->mk, nullptr, st);
+    STAGE(c, "markov_encode", launch_markov_encode(g, c->tr, order, c->mk.model.as<u8>(), c->mk, nullptr, st));
   }
   launch_code_sizes_order0(g, c->tr, c->scal, st);     // scans sliceInfo[.codeBytes] (either format)
   read_scalars(c);
@@ -351,7 +392,7 @@ extern "C" int ckl_shard_fetch(ckl_ctx* c, uint8_t* keys, uint64_t* components_p
   if (code_sizes) {
     c->tmp32.ensure((u64)sz * 4);
     k_gather_stride4<<<(sz + 255) / 256, 256, 0, c->st>>>(c->tr.sliceInfo.as<u32>(), sz, 3, c->tmp32.as<u32>());
-    CUDA_CHECK(cudaGetLastError());
+    LAUNCH_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(code_sizes, c->tmp32.p, (u64)sz * 4, k, c->st));
   }
   CUDA_CHECK(cudaStreamSynchronize(c->st));
@@ -407,11 +448,12 @@ extern "C" int ckl_compress(ckl_ctx* c, const void* labels, int labels_on_device
   // z index: u32 code size per slice + crc32c of those bytes (crackle.hpp:173-185)
   c->tmp32.ensure((u64)g.sz * 4 + 16);
   k_gather_stride4<<<(g.sz + 255) / 256, 256, 0, st>>>(c->tr.sliceInfo.as<u32>(), g.sz, 3, c->tmp32.as<u32>());
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
   launch_write_le_u32(c->tmp32.as<u32>(), g.sz, 4, R + off_z, st);
   u32* crc_tmp = c->tmp32.as<u32>() + g.sz;
   launch_crc_bytes(R + off_z, 4ull * g.sz, c->dtab, c->htab, crc_tmp, st);
   k_store_bytes_u32<<<1, 1, 0, st>>>(R + off_z + 4ull * g.sz, crc_tmp);
+  LAUNCH_CHECK();
   // labels section (labels.hpp:123-152)
   u8 nub[8];
   for (int i = 0; i < 8; i++) nub[i] = (u8)(nu >> (8 * i));
@@ -424,14 +466,15 @@ extern "C" int ckl_compress(ckl_ctx* c, const void* labels, int labels_on_device
     CUDA_CHECK(cudaMemcpyAsync(R + off_model, c->mk.stored.p, model_bytes_for(order), cudaMemcpyDeviceToDevice, st));
     launch_markov_copy(g, c->tr, c->mk, R + off_codes, st);
   } else {
-    launch_pack_order0(g, c->tr, R + off_codes, st);
+    STAGE(c, "pack_order0", launch_pack_order0(g, c->tr, R + off_codes, st));
   }
   // trailing crcs (crackle.hpp:187, 211-214)
   launch_crc_bytes(R + off_lab, labels_bytes, c->dtab, c->htab, crc_tmp + 1, st);
   k_store_bytes_u32<<<1, 1, 0, st>>>(R + off_codes + J.codes_bytes, crc_tmp + 1);
   launch_write_le_u32(c->ccl.sliceCrc.as<u32>(), g.sz, 4, R + off_codes + J.codes_bytes + 4, st);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
   CUDA_CHECK(cudaStreamSynchronize(st));
+  c->prof.collect();
   c->result_bytes = total;
   if (out_bytes) *out_bytes = total;
   J.active = false;
@@ -579,10 +622,12 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   CUDA_CHECK(cudaMemsetAsync(c->scal, 0, SC_COUNT * sizeof(ull), st));
   const ull none = ~0ull;
   CUDA_CHECK(cudaMemcpyAsync(&c->scal[SC_CRC_BAD], &none, 8, cudaMemcpyHostToDevice, st));
+  c->prof.begin("decode_slices", st);
   launch_decode_slices(g, dstream, D.codeOff.as<u64>(), (int)h.crack_format, order, D.model.as<u8>(), c->DV.as<u32>(), c->DH.as<u32>(),
                        D.stack.as<u32>(), D.stackOff.as<u64>(), c->scal, st);
+  c->prof.end(st);
   launch_planes_from_cracks(g, (int)h.crack_format, c->DV.as<u32>(), c->DH.as<u32>(), st);
-  launch_ccl_count(g, c->DV.as<u32>(), c->ccl, c->scal, st);
+  STAGE(c, "ccl_count", launch_ccl_count(g, c->DV.as<u32>(), c->ccl, c->scal, st));
   read_scalars(c);
   if (c->hscal[SC_ERROR]) {
     if (h.crack_format) throw CklError(CKL_ERR_STREAM, "crackle: decode_permissible_crack_code: index out of range.");
@@ -591,12 +636,12 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   const u64 runs = c->hscal[SC_RUNS];
   c->ccl.parent.ensure(runs * 4); c->ccl.runStart.ensure(runs * 4); c->ccl.compRank.ensure(runs * 4);
   c->ccl.runComp.ensure(runs * 4); c->ccl.compPix.ensure(runs * 4);
-  launch_ccl_solve(g, c->DV.as<u32>(), c->DH.as<u32>(), c->ccl, c->dtab, c->scal, st);
+  STAGE(c, "ccl_solve", launch_ccl_solve(g, c->DV.as<u32>(), c->DH.as<u32>(), c->ccl, c->dtab, c->scal, st));
   const u32 init_term = gf_mul(gf_xpow32(c->htab.pw, (u32)g.sxy), 0xFFFFFFFFu);
-  launch_ccl_resolve(g, c->DV.as<u32>(), c->ccl, runs, c->dtab, init_term, st);
+  STAGE(c, "ccl_resolve_crc", launch_ccl_resolve(g, c->DV.as<u32>(), c->ccl, runs, c->dtab, init_term, st));
   if (h.format_version > 0) {   // crackle.hpp:599-611
     k_crc_compare<<<(g.sz + 255) / 256, 256, 0, st>>>(c->ccl.sliceCrc.as<u32>(), dstream + num_bytes - 4ull * h.sz + 4ull * (u64)z_start, g.sz, c->scal);
-    CUDA_CHECK(cudaGetLastError());
+    LAUNCH_CHECK();
     read_scalars(c);
     if (c->hscal[SC_CRC_BAD] != none) {
       const u64 zi = c->hscal[SC_CRC_BAD];
@@ -608,12 +653,76 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
     }
   }
   D.runLabel.ensure(runs * 8 + 8);
-  launch_run_labels(g, c->ccl, dstream, uniq_off, keys_off, nu, n_keys, sw, kw, D.keyBase.as<u64>(), D.runLabel.as<u64>(), st);
+  STAGE(c, "run_labels", launch_run_labels(g, c->ccl, dstream, uniq_off, keys_off, nu, n_keys, sw, kw, D.keyBase.as<u64>(), D.runLabel.as<u64>(), st));
   void* dout = out;
   if (!out_on_device) { c->out_dev.ensure(voxels * (u64)ow); dout = c->out_dev.p; }
-  launch_paint(g, c->DV.as<u32>(), c->ccl, D.runLabel.as<u64>(), ow, has_label, label, (int)h.fortran_order, dout, st);
+  STAGE(c, "paint", launch_paint(g, c->DV.as<u32>(), c->ccl, D.runLabel.as<u64>(), ow, has_label, label, (int)h.fortran_order, dout, st));
   if (!out_on_device) CUDA_CHECK(cudaMemcpyAsync(out, dout, voxels * (u64)ow, cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
+  c->prof.collect();
+  API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// instrumentation and small device utilities used by the multi-GPU host code
+extern "C" int ckl_prof_enable(ckl_ctx* c, int on) {
+  if (!c) return CKL_ERR_ARG;
+  c->prof.on = on != 0;
+  c->prof.acc.clear(); c->prof.cnt.clear();
+  return CKL_OK;
+}
+extern "C" int ckl_prof_read(ckl_ctx* c, char* buf, size_t cap) {
+  if (!c || !buf || !cap) return CKL_ERR_ARG;
+  c->prof.collect();
+  std::string s;
+  for (size_t i = 0; i < c->prof.acc.size(); i++)
+    s += c->prof.acc[i].first + "=" + std::to_string(c->prof.acc[i].second) + ":" + std::to_string(c->prof.cnt[i]) + ";";
+  strncpy(buf, s.c_str(), cap - 1);
+  buf[cap - 1] = 0;
+  return CKL_OK;
+}
+extern "C" uint64_t ckl_launch_count(void) { return g_ckl_launches; }
+// Run this context's work on a caller-owned stream (e.g. torch's current stream) so the caller's CUDA events
+// bracket the kernels.  Pass NULL to go back to the context's own stream.
+extern "C" int ckl_ctx_set_stream(ckl_ctx* c, void* stream) {
+  if (!c) return CKL_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->st);
+  if (stream) { c->st = (cudaStream_t)stream; c->ext_stream = true; }
+  else if (c->ext_stream) { c->st = c->own_st; c->ext_stream = false; }
+  return CKL_OK;
+}
+
+extern "C" int ckl_crc32c(ckl_ctx* c, const void* data, int on_device, uint64_t n, uint32_t* out) {
+  API_BEGIN(c)
+  if (!out) throw CklError(CKL_ERR_ARG, "crackle_b200: null output");
+  const u8* d = (const u8*)data;
+  if (!on_device) {
+    c->stream_dev.ensure(n + 8);
+    CUDA_CHECK(cudaMemcpyAsync(c->stream_dev.p, data, n, cudaMemcpyHostToDevice, c->st));
+    d = c->stream_dev.as<u8>();
+  }
+  c->tmp32.ensure(16);
+  launch_crc_bytes(d, n, c->dtab, c->htab, c->tmp32.as<u32>(), c->st);
+  CUDA_CHECK(cudaMemcpyAsync(out, c->tmp32.p, 4, cudaMemcpyDeviceToHost, c->st));
+  CUDA_CHECK(cudaStreamSynchronize(c->st));
+  API_END(c)
+}
+
+// in-place sort + unique of a device array of uint64 (the merge step of the global label table)
+extern "C" int ckl_sort_unique_u64(ckl_ctx* c, uint64_t* data_device, uint64_t n, int key_bytes, uint64_t* n_unique) {
+  API_BEGIN(c)
+  if (!n_unique) throw CklError(CKL_ERR_ARG, "crackle_b200: null output");
+  LabelBufs tmp;
+  tmp.mapping.p = data_device; tmp.mapping.cap = n * 8;      // borrowed, not owned
+  u64 cnt = 0;
+  try {
+    cnt = labels_sort_unique(tmp, n, key_bytes, c->st);
+    if (cnt) CUDA_CHECK(cudaMemcpyAsync(data_device, tmp.uniq.p, cnt * 8, cudaMemcpyDeviceToDevice, c->st));
+    CUDA_CHECK(cudaStreamSynchronize(c->st));
+  } catch (...) { tmp.mapping.p = nullptr; tmp.mapping.cap = 0; throw; }
+  tmp.mapping.p = nullptr; tmp.mapping.cap = 0;
+  *n_unique = cnt;
   API_END(c)
 }
 

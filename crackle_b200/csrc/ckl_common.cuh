@@ -29,6 +29,10 @@ struct CklError : std::runtime_error {
                                        " (" #x ") at " __FILE__ ":" + std::to_string(__LINE__));  \
   } while (0)
 
+// every kernel launch is followed by LAUNCH_CHECK(): error check + a process-wide launch counter (bench.py reports it)
+extern unsigned long long g_ckl_launches;
+#define LAUNCH_CHECK() do { g_ckl_launches++; CUDA_CHECK(cudaGetLastError()); } while (0)
+
 // Grow-only device buffer (the context keeps these across calls so steady-state calls do no cudaMalloc).
 struct DBuf {
   void* p = nullptr;

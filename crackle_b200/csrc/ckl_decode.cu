@@ -176,7 +176,7 @@ void launch_decode_slices(const Geom& g, const u8* stream, const u64* codeOff, i
   CUDA_CHECK(cudaMemsetAsync(EV, 0, g.words() * 4, st));
   CUDA_CHECK(cudaMemsetAsync(EH, 0, g.words() * 4, st));
   k_decode_slices<<<g.sz, 32, 0, st>>>(g, stream, codeOff, order, model, EV, EH, stack, stackOff, scal);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }
 
 // crack planes -> "differ" planes.  IMPERMISSIBLE: identical.  PERMISSIBLE: cracks mark connected neighbours.
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) k_planes_from_cracks(Geom g, u32* EV, u32
 void launch_planes_from_cracks(const Geom& g, int permissible, u32* EV, u32* EH, cudaStream_t st) {
   if (!permissible) return;
   k_planes_from_cracks<<<grid1(g.words(), 256, 148 * 16), 256, 0, st>>>(g, EV, EH);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }
 
 // label of every run: component rank -> key -> unique label (decode_flat)
@@ -224,7 +224,7 @@ void launch_run_labels(const Geom& g, const CclBufs& B, const u8* stream, u64 un
   k_run_labels<<<grid1(total_runs, 256, 148 * 16), 256, 0, st>>>(g, total_runs, B.runBase.as<u64>(), B.runComp.as<u32>(),
                                                                  stream + uniq_off, stream + keys_off, n_uniq, n_keys_total,
                                                                  stored_width, key_width, keyBase, runLabel);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }
 
 // paint: one warp per 32-pixel word, lane <-> pixel; the only full-width write of decompress.
@@ -266,5 +266,5 @@ void launch_paint(const Geom& g, const u32* DV, const CclBufs& B, const u64* run
                          case 4: PAINT(u32, false, false); break; default: PAINT(u64, false, false); break; }
   }
 #undef PAINT
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }

@@ -38,7 +38,7 @@ void launch_gather_mapping(const void* labels, int width, const Geom& g, const C
     case 4: k_gather_mapping<u32><<<grid, 256, 0, st>>>((const u32*)labels, g, ncomp, cb, px, mapping); break;
     default: k_gather_mapping<u64><<<grid, 256, 0, st>>>((const u64*)labels, g, ncomp, cb, px, mapping); break;
   }
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }
 
 u64 labels_sort_unique(LabelBufs& L, u64 n, int stored_width, cudaStream_t st) {
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) k_write_keys(const u64* __restrict__ mapp
 void launch_write_keys(const u64* mapping, u64 n, const u64* uniq, u64 n_uniq, int key_width, u8* dst, cudaStream_t st) {
   if (!n) return;
   k_write_keys<<<grid1d(n, 256), 256, 0, st>>>(mapping, n, uniq, n_uniq, key_width, dst);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }
 
 __global__ void __launch_bounds__(256) k_write_le_u64(const u64* __restrict__ src, u64 n, int w, u8* __restrict__ dst) {
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) k_write_le_u64(const u64* __restrict__ sr
 void launch_write_uniq(const u64* uniq, u64 n_uniq, int stored_width, u8* dst, cudaStream_t st) {
   if (!n_uniq) return;
   k_write_le_u64<<<grid1d(n_uniq, 256), 256, 0, st>>>(uniq, n_uniq, stored_width, dst);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }
 __global__ void __launch_bounds__(256) k_write_le_u32(const u32* __restrict__ src, u64 n, int w, u8* __restrict__ dst) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
@@ -98,5 +98,5 @@ __global__ void __launch_bounds__(256) k_write_le_u32(const u32* __restrict__ sr
 void launch_write_le_u32(const u32* src, u64 n, int width, u8* dst, cudaStream_t st) {
   if (!n) return;
   k_write_le_u32<<<grid1d(n, 256), 256, 0, st>>>(src, n, width, dst);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }

@@ -73,7 +73,7 @@ void launch_markov_stats(const Geom& g, TraceBufs& T, int order, u32* stats, cud
   CUDA_CHECK(cudaMemsetAsync(stats, 0, rows * 16, st));
   const size_t sm = order <= 5 ? rows * 16 : 0;
   k_markov_stats<<<grid_slices(g.sz, 4), 256, sm, st>>>(mk(g, T), order, stats);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }
 
 // model[row][symbol] = rank; stored model = lexicographic index of (symbol of rank 0..3), 5 bits per row
@@ -111,7 +111,7 @@ void launch_markov_model(int order, const u32* stats, u8* model, u8* stored, u64
   const u32 rows = 1u << (2 * order);
   CUDA_CHECK(cudaMemsetAsync(stored, 0, ((stored_bytes + 3) / 4 + 1) * 4, st));
   k_markov_model<<<(rows + 255) / 256, 256, 0, st>>>(rows, stats, model, (u32*)stored);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }
 
 // per-slice bitstream into word-aligned scratch: 2 raw bits for the first symbol, then unary-ish rank codes
@@ -165,7 +165,7 @@ void launch_markov_sizes(const Geom& g, TraceBufs& T, int order, const u8* model
   M.scratchOff.ensure(((u64)g.sz + 1) * 8);
   u32* caps = (u32*)(M.bitlen.as<u64>() + g.sz);
   k_markov_caps<<<(g.sz + 255) / 256, 256, 0, st>>>(g.sz, T.sliceInfo.as<u32>(), caps);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
   launch_exscan_u32_u64(caps, g.sz, 1, M.scratchOff.as<u64>(), &scal[SC_CPCAP], 0, st);
   // worst case: 3 bits per codepoint -> the codepoint buffer capacity bounds the scratch size
   (void)order; (void)model;
@@ -176,7 +176,7 @@ void launch_markov_encode(const Geom& g, TraceBufs& T, int order, const u8* mode
   if (!dst) {
     k_markov_encode<<<grid_slices(g.sz, 8), 256, 0, st>>>(mk(g, T), order, model, M.scratchOff.as<u64>(), M.scratch.as<u32>(),
                                                           M.bitlen.as<u64>(), T.sliceInfo.as<u32>());
-    CUDA_CHECK(cudaGetLastError());
+    LAUNCH_CHECK();
     return;
   }
 }
@@ -195,5 +195,5 @@ void launch_markov_copy(const Geom& g, TraceBufs& T, MarkovBufs& M, u8* dst, cud
   launch_write_boc_only(g, T, dst, st);
   k_markov_copy<<<grid_slices(g.sz, 8), 256, 0, st>>>(g, T.sliceInfo.as<u32>(), T.codeOff.as<u64>(), M.scratchOff.as<u64>(),
                                                       M.scratch.as<u32>(), dst);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }

@@ -117,7 +117,7 @@ void launch_edges(const void* labels, int width, const Geom& g, u32* DV, u32* DH
     case 4: k_edges<u32, RS><<<grid, 256, 0, st>>>((const u32*)labels, g, DV, DH, scal); break;
     default: k_edges<u64, RS><<<grid, 256, 0, st>>>((const u64*)labels, g, DV, DH, scal); break;
   }
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(1024) k_exscan_u32_u64(const u32* __restrict__
 }
 void launch_exscan_u32_u64(const u32* in, u32 n, u32 stride, u64* out, ull* total_out, u64 add_each, cudaStream_t st) {
   k_exscan_u32_u64<<<1, 1024, 0, st>>>(in, n, stride, out, total_out, add_each);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }
 
 void launch_ccl_count(const Geom& g, const u32* DV, CclBufs& B, ull* scal, cudaStream_t st) {
@@ -209,9 +209,9 @@ void launch_ccl_count(const Geom& g, const u32* DV, CclBufs& B, ull* scal, cudaS
   B.sliceRuns.ensure((u64)g.sz * 4);
   B.runBase.ensure(((u64)g.sz + 1) * 8);
   k_row_prefix<<<grid_for(g.rows(), 8, 8), 256, 0, st>>>(g, DV, B.wordPrefix.as<u32>(), B.rowRuns.as<u32>());
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
   k_slice_scan<<<grid_for(g.sz, 1, 8), 256, 0, st>>>(g, B.rowRuns.as<u32>(), B.rowBase.as<u32>(), B.sliceRuns.as<u32>());
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
   launch_exscan_u32_u64(B.sliceRuns.as<u32>(), g.sz, 1, B.runBase.as<u64>(), &scal[SC_RUNS], 0, st);
 }
 
@@ -355,7 +355,7 @@ __global__ void k_crc_finalize(u32* crc, u32 n, u32 init_term) {
 }
 void launch_crc_finalize_slices(u32* sliceCrc, u32 sz, u32 init_term, cudaStream_t st) {
   k_crc_finalize<<<(sz + 255) / 256, 256, 0, st>>>(sliceCrc, sz, init_term);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }
 
 void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, const CrcTables* d_tables, ull* scal,
@@ -367,13 +367,13 @@ void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, c
   u32* parent = B.parent.as<u32>();
   k_run_init<<<grid_for(nwords, 256, 16), 256, 0, st>>>(g, DV, B.wordPrefix.as<u32>(), B.rowBase.as<u32>(), B.runBase.as<u64>(),
                                                          parent, B.runStart.as<u32>());
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
   k_run_union<<<grid_for(nwords, 256, 16), 256, 0, st>>>(g, DV, DH, B.wordPrefix.as<u32>(), B.rowBase.as<u32>(),
                                                           B.runBase.as<u64>(), parent);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
   k_root_rank<<<grid_for(g.sz, 1, 8), 256, 0, st>>>(g, parent, B.sliceRuns.as<u32>(), B.runBase.as<u64>(), B.compRank.as<u32>(),
                                                      B.nz.as<u32>());
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
   launch_exscan_u32_u64(B.nz.as<u32>(), g.sz, 1, B.compBase.as<u64>(), &scal[SC_COMPONENTS], 0, st);
 }
 
@@ -383,11 +383,11 @@ void launch_ccl_resolve(const Geom& g, const u32* DV, CclBufs& B, u64 total_runs
   k_run_resolve<<<grid_for(total_runs, 256, 16), 256, 0, st>>>(g, total_runs, B.parent.as<u32>(), B.runBase.as<u64>(),
                                                                 B.compRank.as<u32>(), B.runStart.as<u32>(), B.compBase.as<u64>(),
                                                                 B.runComp.as<u32>(), B.compPix.as<u32>());
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
   CUDA_CHECK(cudaMemsetAsync(B.sliceCrc.p, 0, (u64)g.sz * 4, st));
   k_cc_crc<<<grid_for(g.words(), 256, 8), 256, 0, st>>>(g, DV, B.wordPrefix.as<u32>(), B.rowBase.as<u32>(), B.runBase.as<u64>(),
                                                          B.runComp.as<u32>(), d_tables, B.sliceCrc.as<u32>());
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
   launch_crc_finalize_slices(B.sliceCrc.as<u32>(), g.sz, crc_init_term, st);
 }
 
@@ -437,7 +437,7 @@ void launch_crc_bytes(const u8* d, u64 n, const CrcTables* d_tables, const CrcTa
   CUDA_CHECK(cudaMemsetAsync(d_out, 0, 4, st));
   const u64 nchunks = ((n >> 2) + 15) / 16;
   k_crc_bytes<<<grid_for(nchunks ? nchunks : 1, 256, 8), 256, 0, st>>>(d, n, d_tables, d_out);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
   k_not<<<1, 1, 0, st>>>(d_out);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }

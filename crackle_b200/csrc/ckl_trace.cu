@@ -120,9 +120,9 @@ void launch_trace_prepare(const Geom& g, const u32* DV, const u32* DH, int permi
   u32* caps = bounds + (u64)g.sz * 4;
   CUDA_CHECK(cudaMemsetAsync(bounds, 0, (u64)g.sz * 4 * 4, st));
   k_trace_prepare<<<grid_cap(nwords, 256, 16), 256, 0, st>>>(g, DV, DH, permissible, T.EV.as<u32>(), T.EH.as<u32>(), bounds);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
   k_trace_caps<<<(g.sz + 255) / 256, 256, 0, st>>>(g.sz, bounds, caps);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
   u64* offs = T.offs.as<u64>();
   const u64 n1 = (u64)g.sz + 1;
   launch_exscan_u32_u64(caps + 0, g.sz, 4, offs + 0 * n1, &scal[SC_SYMCAP], 0, st);
@@ -381,26 +381,20 @@ __global__ void __launch_bounds__(256) k_trace_post(TraceParams P) {
   }
 }
 
-void launch_trace(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st) {
-  TraceParams P;
-  P.g = g;
-  P.EV = T.EV.as<u32>();
-  P.EH = T.EH.as<u32>();
-  P.offs = T.offs.as<u64>();
-  P.caps = T.bounds.as<u32>() + (u64)g.sz * 4;
-  P.sym = T.sym.as<u8>();
-  P.stack = T.stack.as<uint2>();
-  P.chain = T.chain.as<ChainRec>();
-  P.cp = T.cp.as<u8>();
-  P.cpPrefix = T.cpPrefix.as<u32>();
-  P.sliceInfo = T.sliceInfo.as<u32>();
-  P.scal = scal;
-  k_trace_walk<<<grid_cap(g.sz, 1, 16), 128, 0, st>>>(P);
-  CUDA_CHECK(cudaGetLastError());
-  k_trace_post<<<grid_cap(g.sz, 1, 8), 256, 0, st>>>(P);
-  CUDA_CHECK(cudaGetLastError());
+static TraceParams make_params(const Geom& g, TraceBufs& T, ull* scal);
+void launch_trace_walk(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st) {
+  k_trace_walk<<<grid_cap(g.sz, 1, 16), 128, 0, st>>>(make_params(g, T, scal));
+  LAUNCH_CHECK();
+}
+void launch_trace_post(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st) {
+  k_trace_post<<<grid_cap(g.sz, 1, 8), 256, 0, st>>>(make_params(g, T, scal));
+  LAUNCH_CHECK();
   // total codepoints (for the "all slices empty" rule, crackle.hpp:107-118)
   launch_exscan_u32_u64(T.sliceInfo.as<u32>(), g.sz, 4, T.codeOff.as<u64>(), &scal[SC_CODEPOINTS], 0, st);
+}
+void launch_trace(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st) {
+  launch_trace_walk(g, T, scal, st);
+  launch_trace_post(g, T, scal, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -469,7 +463,7 @@ static TraceParams make_params(const Geom& g, TraceBufs& T, ull* scal) {
 void launch_pack_order0(const Geom& g, TraceBufs& T, u8* dst, cudaStream_t st) {
   TraceParams P = make_params(g, T, nullptr);
   k_pack_order0<<<grid_cap(g.sz, 1, 8), 256, 0, st>>>(P, T.codeOff.as<u64>(), dst);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }
 
 // exported for ckl_markov.cu
@@ -485,5 +479,5 @@ __global__ void __launch_bounds__(64) k_write_boc_only(TraceParams P, const u64*
 void launch_write_boc_only(const Geom& g, TraceBufs& T, u8* dst, cudaStream_t st) {
   TraceParams P = make_params(g, T, nullptr);
   k_write_boc_only<<<(g.sz + 63) / 64, 64, 0, st>>>(P, T.codeOff.as<u64>(), dst);
-  CUDA_CHECK(cudaGetLastError());
+  LAUNCH_CHECK();
 }

@@ -133,6 +133,19 @@ CKL_API int ckl_shard_finish(ckl_ctx* ctx, const uint64_t* global_unique, int un
 CKL_API int ckl_shard_fetch(ckl_ctx* ctx, uint8_t* keys, uint64_t* components_per_slice, uint32_t* code_sizes,
                     uint32_t* slice_crcs, uint8_t* codes, int dst_on_device);
 
+/* ---- instrumentation and small device utilities ---------------------------------------------------------- */
+/* Per-stage CUDA-event timing on the context's stream.  ckl_prof_read formats "stage=ms_total:calls;..." */
+CKL_API int ckl_prof_enable(ckl_ctx* ctx, int on);
+CKL_API int ckl_prof_read(ckl_ctx* ctx, char* buf, size_t cap);
+/* Run the context's work on a caller-owned CUDA stream (cudaStream_t as void*; NULL restores the own stream). */
+CKL_API int ckl_ctx_set_stream(ckl_ctx* ctx, void* stream);
+/* Number of kernels this library has launched in this process. */
+CKL_API uint64_t ckl_launch_count(void);
+/* CRC-32C (Castagnoli) of a host or device buffer, computed on the GPU (src/crc.hpp:39-57). */
+CKL_API int ckl_crc32c(ckl_ctx* ctx, const void* data, int on_device, uint64_t n, uint32_t* out);
+/* In-place sort + unique of a DEVICE array of uint64 (only the low key_bytes*8 bits are compared). */
+CKL_API int ckl_sort_unique_u64(ckl_ctx* ctx, uint64_t* data_device, uint64_t n, int key_bytes, uint64_t* n_unique);
+
 /* Library / build information. */
 CKL_API const char* crackle_b200_version(void);
 
