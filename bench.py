@@ -181,6 +181,7 @@ def main():
 
         def step():
             stream_t = job.compress(vol, z0=rank * sz, sz_total=sz * world, markov_model_order=args.order)
+            stream_t = job.broadcast_stream(stream_t)
             job.decompress_shard(stream_t, rank * sz, (rank + 1) * sz, out)
             return stream_t
     else:

@@ -48,6 +48,7 @@ SYMBOLS = {
     "ckl_shard_unique": (cint, [vp, vp, cint]),
     "ckl_shard_stats": (cint, [vp, vp, cint]),
     "ckl_shard_finish": (cint, [vp, vp, cint, u64, vp, cint, ctypes.POINTER(ShardPieces)]),
+    "ckl_shard_model": (cint, [vp, vp, cint, u64, ctypes.POINTER(u64)]),
     "ckl_shard_fetch": (cint, [vp, vp, vp, vp, vp, vp, cint]),
     "ckl_prof_enable": (cint, [vp, cint]),
     "ckl_prof_read": (cint, [vp, ctypes.c_char_p, ctypes.c_size_t]),

@@ -373,6 +373,19 @@ extern "C" int ckl_shard_finish(ckl_ctx* c, const uint64_t* global_unique, int u
   pieces->sz_local = c->job.g.sz;
   API_END(c)
 }
+extern "C" int ckl_shard_model(ckl_ctx* c, uint8_t* dst, int dst_on_device, uint64_t capacity, uint64_t* model_bytes) {
+  API_BEGIN(c)
+  ShardJob& J = c->job;
+  if (!J.finished) throw CklError(CKL_ERR_ARG, "crackle_b200: ckl_shard_model without ckl_shard_finish");
+  const u64 n = model_bytes_for(J.order);
+  if (model_bytes) *model_bytes = n;
+  if (dst && n) {
+    if (capacity < n) throw CklError(CKL_ERR_ARG, "crackle_b200: model buffer too small");
+    CUDA_CHECK(cudaMemcpyAsync(dst, c->mk.stored.p, n, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
+    CUDA_CHECK(cudaStreamSynchronize(c->st));
+  }
+  API_END(c)
+}
 extern "C" int ckl_shard_fetch(ckl_ctx* c, uint8_t* keys, uint64_t* components_per_slice, uint32_t* code_sizes, uint32_t* slice_crcs,
                                uint8_t* codes, int dst_on_device) {
   API_BEGIN(c)

@@ -128,6 +128,8 @@ typedef struct ckl_shard_pieces {
 } ckl_shard_pieces;
 CKL_API int ckl_shard_finish(ckl_ctx* ctx, const uint64_t* global_unique, int unique_on_device, uint64_t n_unique_global,
                      const uint32_t* global_stats, int stats_on_device, ckl_shard_pieces* pieces);
+/* Stored markov model bytes built from the global statistics (src/markov.hpp:325-380); 0 bytes for order 0. */
+CKL_API int ckl_shard_model(ckl_ctx* ctx, uint8_t* dst, int dst_on_device, uint64_t capacity, uint64_t* model_bytes);
 /* Copies the pieces out (each may be NULL to skip): keys, component counts (uint64 per slice), code sizes
  * (uint32 per slice), slice crcs (uint32 per slice), codes. */
 CKL_API int ckl_shard_fetch(ckl_ctx* ctx, uint8_t* keys, uint64_t* components_per_slice, uint32_t* code_sizes,

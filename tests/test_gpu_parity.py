@@ -1,0 +1,240 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the golden vectors generated from the
+compiled reference, against the CPU oracle on seeded inputs, and -- at BASELINE.json sizes -- through
+size-independent properties.  Integer/byte work: the bar is bit-exact."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import crackle_b200 as cb
+    return cb.default_context()
+
+
+def _golden_input(g):
+    a = g["input"]
+    return np.asfortranarray(a) if bool(g["f_order"]) else np.ascontiguousarray(a)
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("order", [0, 1, 5])
+def test_compress_matches_reference_golden(ctx, name, order):
+    g = load_golden(name)
+    assert ctx.compress(_golden_input(g), order) == bytes(g[f"ckl_order{order}"])
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("order", [0, 5])
+def test_decompress_matches_reference_golden(ctx, name, order):
+    import crackle_b200 as cb
+    g = load_golden(name)
+    a = g["input"]
+    b = bytes(g[f"ckl_order{order}"])
+    d = cb.decompress(b)
+    assert d.dtype == a.dtype
+    assert np.array_equal(d.reshape(a.shape), a)
+    m = cb.decompress(b, label=int(g["label"]))
+    assert m.dtype == bool and np.array_equal(m, g["mask"].view(bool))
+    if "z1_2" in g:
+        assert np.array_equal(cb.decompress_range(b, 1, 2), g["z1_2"])
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.uint64])
+def test_random_volumes_against_oracle(ctx, dtype):
+    # mirrors automated_test.py:15-39 (test_compress_decompress_random), bytes checked against the oracle
+    from oracle import oracle as O
+    from crackle_b200 import synth
+    import crackle_b200 as cb
+    rng = np.random.default_rng(np.dtype(dtype).itemsize)
+    vols = [np.asfortranarray(rng.integers(0, 5, (4, 4, 1)).astype(dtype)),
+            np.asfortranarray(rng.integers(0, 255, (256, 255, 1)).astype(dtype)),
+            np.asfortranarray(rng.integers(0, 255, (40, 37, 9)).astype(dtype)),
+            np.asfortranarray(rng.integers(0, 2, (65, 33, 5)).astype(dtype)),
+            synth.random_blobs((61, 47, 6), 9, dtype, seed=3),
+            synth.jittered_voronoi((97, 130, 4), 13, dtype, seed=4, id_bits=8 * np.dtype(dtype).itemsize - 1)]
+    for v in vols:
+        for order in (0, 2, 5):
+            b = ctx.compress(v, order)
+            assert b == O.compress(v, order), (v.shape, order)
+            assert np.array_equal(cb.decompress(b).reshape(v.shape), v)
+
+
+def test_edge_shapes(ctx):
+    # automated_test.py:151-225, 263-271: empty, black, uniform, arange, 2D, 1D inputs
+    from oracle import oracle as O
+    import crackle_b200 as cb
+    cases = [np.zeros((0, 0, 0), np.uint32, order="F"), np.zeros((3, 0, 2), np.uint8, order="F"),
+             np.zeros((1, 1, 1), np.uint64, order="F"), np.zeros((100, 100, 3), np.uint32, order="F"),
+             np.full((31, 33, 2), 2**40 + 7, np.uint64, order="F"),
+             np.asfortranarray(np.arange(33 * 32 * 2, dtype=np.uint32).reshape((33, 32, 2), order="F")),
+             np.arange(129, dtype=np.uint16), np.asfortranarray(np.arange(64, dtype=np.uint8).reshape(8, 8)),
+             np.asfortranarray((np.indices((50, 50))[0] // 10).astype(np.uint8)),
+             np.ascontiguousarray(np.random.default_rng(0).integers(0, 4, (20, 30, 5)).astype(np.uint16))]
+    for v in cases:
+        b = ctx.compress(v, 0)
+        assert b == O.compress(v, 0), v.shape
+        if v.size:
+            d = cb.decompress(b)
+            s = list(v.shape) + [1, 1]
+            assert np.array_equal(d.reshape((s[0], s[1], s[2])), v.reshape((s[0], s[1], s[2])))
+        else:
+            assert len(b) == 29
+
+
+def test_c_order_roundtrip_layout(ctx):
+    # automated_test.py:658-675 (test_contiguous_fortran): C-order volumes keep their memory order
+    import crackle_b200 as cb
+    from crackle_b200 import synth
+    v = np.ascontiguousarray(synth.random_blobs((33, 45, 7), 8, np.uint32, seed=1))
+    b = ctx.compress(v, 0)
+    assert cb.header(b)["fortran_order"] == 0
+    d = cb.decompress(b)
+    assert d.flags.c_contiguous and np.array_equal(d, v)
+    lab = int(v[10, 10, 3])
+    assert np.array_equal(cb.decompress(b, label=lab), v == lab)
+
+
+def test_z_ranges(ctx):
+    import crackle_b200 as cb
+    from crackle_b200 import synth
+    v = synth.jittered_voronoi((64, 48, 12), 10, np.uint32, seed=2, id_bits=16)
+    b = ctx.compress(v, 5)
+    for z0, z1 in ((0, 1), (3, 9), (11, 12), (0, 12), (5, 100)):
+        assert np.array_equal(cb.decompress_range(b, z0, z1), v[:, :, z0:z1])
+    with pytest.raises(RuntimeError, match="Invalid range"):
+        cb.decompress_range(b, 5, 5)
+
+
+def test_corruption_errors_match_reference_text(ctx):
+    # automated_test.py:731-826 (test_crc_check_one_bit_error)
+    import crackle_b200 as cb
+    from crackle_b200 import synth
+    v = synth.jittered_voronoi((64, 64, 4), 12, np.uint16, seed=5, id_bits=15)
+    b = bytearray(ctx.compress(v, 0))
+    bad = bytearray(b); bad[-1] ^= 1
+    with pytest.raises(RuntimeError, match="crack code crc mismatch on z=3"):
+        cb.decompress(bytes(bad))
+    bad = bytearray(b); bad[29] ^= 1
+    with pytest.raises(RuntimeError, match="grid index crc32c did not match"):
+        cb.decompress(bytes(bad))
+    bad = bytearray(b); bad[9] ^= 1
+    with pytest.raises(RuntimeError, match="CRC8 check failed"):
+        cb.decompress(bytes(bad))
+    with pytest.raises(RuntimeError, match="Input too small"):
+        cb.decompress(bytes(b[:12]))
+    # a flipped crack-code bit must be caught by the per-slice crc
+    h = cb.header(bytes(b))
+    off = 29 + 4 * (h["sz"] + 1) + h["num_label_bytes"] + 12
+    bad = bytearray(b); bad[off] ^= 0x10
+    with pytest.raises(RuntimeError):
+        cb.decompress(bytes(bad))
+
+
+def test_one_shot_c_abi(ctx):
+    # the exact entry points a fastcrackle binding would call
+    from crackle_b200 import _capi
+    g = load_golden("voronoi_u64_96x80x5")
+    a = np.asfortranarray(g["input"])
+    L = _capi.lib()
+    out, n = ctypes.c_void_p(), ctypes.c_uint64()
+    err = ctypes.create_string_buffer(512)
+    rc = L.crackle_b200_compress(a.ctypes.data, 8, 96, 80, 5, 1, 5, ctypes.byref(out), ctypes.byref(n), err, 512)
+    assert rc == 0, err.value
+    b = ctypes.string_at(out.value, n.value)
+    L.crackle_b200_free(out)
+    assert b == bytes(g["ckl_order5"])
+    dec = np.zeros(a.size, dtype=np.uint64)
+    buf = np.frombuffer(b, dtype=np.uint8)
+    rc = L.crackle_b200_decompress(buf.ctypes.data, buf.size, 0, -1, 0, 0, dec.ctypes.data, dec.nbytes, err, 512)
+    assert rc == 0, err.value
+    assert np.array_equal(dec.reshape(a.shape, order="F"), a)
+    rc = L.crackle_b200_decompress(buf.ctypes.data, buf.size, 0, -1, 0, 0, dec.ctypes.data, 8, err, 512)
+    assert rc != 0 and b"too small" in err.value
+
+
+def test_device_resident_tensors(ctx):
+    import torch
+    from oracle import oracle as O
+    from crackle_b200 import synth
+    v = synth.jittered_voronoi((128, 96, 8), 16, np.uint64, seed=6)
+    t = synth.jittered_voronoi_torch((128, 96, 8), 16, np.uint64, seed=6)
+    assert np.array_equal(t.cpu().numpy().transpose(2, 1, 0), v)          # numpy and torch generators agree
+    want = O.compress(v, 0)
+    assert ctx.compress(t, 0) == want
+    n = ctx.compress_ptr(t.data_ptr(), 1, 8, 128, 96, 8, True, 0)
+    p, n2 = ctx.result_device()
+    assert n == n2 == len(want)
+    out = torch.empty_like(t)
+    ctx.decompress_into(p, 1, n, 0, -1, None, out.data_ptr(), 1, out.numel() * 8)
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int64), t.view(torch.int64))
+    m = torch.empty(t.shape, dtype=torch.uint8, device="cuda")
+    lab = int(v[64, 48, 4])
+    ctx.decompress_into(p, 1, n, 0, -1, lab, m.data_ptr(), 1, m.numel())
+    torch.cuda.synchronize()
+    assert np.array_equal(m.cpu().numpy().transpose(2, 1, 0).astype(bool), v == lab)
+
+
+@pytest.mark.parametrize("order", [0, 5])
+def test_config1_512x512x64_u32_bytes_vs_oracle(ctx, order):
+    # BASELINE.json configs[0]: 512x512x64 uint32 ~1k labels, byte-exact against the oracle
+    from oracle import oracle as O
+    from crackle_b200 import synth
+    t = synth.jittered_voronoi_torch((512, 512, 64), 40, np.uint32, seed=0, id_bits=16)
+    v = np.asfortranarray(t.cpu().numpy().transpose(2, 1, 0))
+    b = ctx.compress(t, order)
+    assert b == O.compress(v, order)
+    import crackle_b200 as cb
+    assert np.array_equal(cb.decompress(b), v)
+
+
+@pytest.mark.parametrize("order", [0, 5])
+def test_config2_512cube_u64_properties(ctx, order):
+    # BASELINE.json configs[1]/[3]: 512^3 uint64, ~10k labels.  Full-size checks use size-independent properties:
+    # round trip, per-slice crc agreement with the decoder, z-slab bytes == oracle, mask == (volume == label).
+    import torch
+    from oracle import oracle as O
+    from crackle_b200 import synth
+    import crackle_b200 as cb
+    t = synth.jittered_voronoi_torch((512, 512, 512), 24, np.uint64, seed=0, id_bits=40)
+    n = ctx.compress_ptr(t.data_ptr(), 1, 8, 512, 512, 512, True, order)
+    p, _ = ctx.result_device()
+    out = torch.empty_like(t)
+    ctx.decompress_into(p, 1, n, 0, -1, None, out.data_ptr(), 1, out.numel() * 8)     # verifies every slice crc
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int64), t.view(torch.int64))
+    stream = ctx.result_bytes()
+    h = cb.header(stream)
+    assert (h["sx"], h["sy"], h["sz"], h["data_width"], h["stored_data_width"], h["markov_model_order"]) == (512, 512, 512, 8, 8, order)
+    # oracle decodes a z-range of the GPU stream identically
+    ref = O.decompress(stream, 100, 104)
+    assert np.array_equal(ref, t[100:104].cpu().numpy().transpose(2, 1, 0))
+    if order == 0:
+        # order-0 crack codes are slice-local: a 12-slice slab compressed alone has the same per-slice codes and crcs
+        slab = np.asfortranarray(t[200:212].cpu().numpy().transpose(2, 1, 0))
+        so, sg = O.sections(O.compress(slab, 0)), O.sections(stream)
+        assert so["codes"] == sg["codes"][200:212]
+        assert so["slice_crcs"] == sg["slice_crcs"][4 * 200:4 * 212]
+    lab = int(t[256, 256, 256].item())
+    m = torch.empty(t.shape, dtype=torch.uint8, device="cuda")
+    ctx.decompress_into(p, 1, n, 0, -1, lab, m.data_ptr(), 1, m.numel())
+    torch.cuda.synchronize()
+    assert torch.equal(m.bool(), t.view(torch.int64) == lab)
+
+
+def test_noise_volumes_permissible_path(ctx):
+    # benchmarks/perf.py:68-76 noise cases: randint(0,2000) u32 and binary u8 -> PERMISSIBLE crack format
+    from oracle import oracle as O
+    import crackle_b200 as cb
+    rng = np.random.default_rng(9)
+    for v in (np.asfortranarray(rng.integers(0, 2000, (128, 128, 8)).astype(np.uint32)),
+              np.asfortranarray(rng.integers(0, 2, (128, 128, 8)).astype(np.uint8))):
+        b = ctx.compress(v, 0)
+        assert b == O.compress(v, 0)
+        assert np.array_equal(cb.decompress(b), v)

@@ -1,0 +1,57 @@
+"""multi-GPU parity check (run under torchrun): z-sharded compress == single-GPU compress of the whole volume,
+orders 0 and 5; every rank decodes its own z-range of the broadcast stream."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import crackle_b200 as cb  # noqa: E402
+from crackle_b200 import synth  # noqa: E402
+from crackle_b200.dist import ShardedCodec  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = cb.Context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    job = ShardedCodec(ctx, dist)
+    ok = True
+    for shape, cell, dt, bits in (((256, 192, 8 * world + 3), 20, np.uint64, 40), ((130, 97, 2 * world), 12, np.uint16, 15)):
+        sx, sy, szt = shape
+        per = szt // world
+        z0 = rank * per
+        z1 = szt if rank == world - 1 else z0 + per
+        vol = synth.jittered_voronoi_torch((sx, sy, z1 - z0), cell, dt, seed=1, id_bits=bits, z0=z0, sz_total=szt)
+        whole = synth.jittered_voronoi_torch(shape, cell, dt, seed=1, id_bits=bits) if rank == 0 else None
+        for order in (0, 5):
+            s = job.compress(vol, z0, szt, order)
+            if rank == 0:
+                want = ctx.compress(whole, order)
+                got = bytes(s.cpu().numpy().tobytes())
+                same = got == want
+                print(f"shape {shape} {np.dtype(dt).name} order {order}: sharded == monolithic: {same} ({len(got)} bytes)", flush=True)
+                ok &= same
+            s = job.broadcast_stream(s)
+            out = torch.empty_like(vol)
+            job.decompress_shard(s, z0, z1, out)
+            torch.cuda.synchronize()
+            good = torch.equal(out.view(torch.uint8), vol.view(torch.uint8))
+            if not good:
+                print(f"rank {rank}: decode mismatch shape {shape} order {order}", flush=True)
+            ok &= good
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST CHECK", "PASS" if t.item() == 1 else "FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
