@@ -45,8 +45,12 @@ class Context:
 
     # -- instrumentation -----------------------------------------------------------------------------------
     def set_stream(self, cuda_stream_ptr):
-        """Run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); None restores the own one."""
-        self._check(_capi.lib().ckl_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+        """Run on a caller-owned stream, e.g. torch.cuda.current_stream().cuda_stream (0 = legacy default stream);
+        None restores the context's own stream."""
+        if cuda_stream_ptr is None:
+            self._check(_capi.lib().ckl_ctx_own_stream(self._h))
+        else:
+            self._check(_capi.lib().ckl_ctx_set_stream(self._h, ctypes.c_void_p(int(cuda_stream_ptr))))
 
     def prof_enable(self, on=True):
         _capi.lib().ckl_prof_enable(self._h, int(on))

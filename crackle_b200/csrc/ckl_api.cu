@@ -293,7 +293,7 @@ static void shard_finish_impl(ckl_ctx* c, const u64* guniq_dev, u64 nuniq_global
     c->mk.stored.ensure(model_bytes_for(order) + 16);
     launch_markov_model(order, gstats_dev, c->mk.model.as<u8>(), c->mk.stored.as<u8>(), model_bytes_for(order), st);
     launch_markov_sizes(g, c->tr, order, c->mk.model.as<u8>(), c->mk, c->scal, st);
-    const u64 scratch_words = (3 * J.ncp) / 32 + 2ull * g.sz + 64;
+    const u64 scratch_words = (3 * J.ncp) / 32 + 3ull * g.sz + 64;
     c->mk.scratch.ensure(scratch_words * 4);
     CUDA_CHECK(cudaMemsetAsync(c->mk.scratch.p, 0, scratch_words * 4, st));
     STAGE(c, "markov_encode", launch_markov_encode(g, c->tr, order, c->mk.model.as<u8>(), c->mk, nullptr, st));
@@ -695,14 +695,22 @@ extern "C" int ckl_prof_read(ckl_ctx* c, char* buf, size_t cap) {
   return CKL_OK;
 }
 extern "C" uint64_t ckl_launch_count(void) { return g_ckl_launches; }
-// Run this context's work on a caller-owned stream (e.g. torch's current stream) so the caller's CUDA events
-// bracket the kernels.  Pass NULL to go back to the context's own stream.
+// Run this context's work on a caller-owned stream (e.g. torch's current stream) so the caller's stream order and
+// CUDA events cover the kernels.  stream == 0 is the legacy default stream (what torch uses unless told otherwise).
 extern "C" int ckl_ctx_set_stream(ckl_ctx* c, void* stream) {
   if (!c) return CKL_ERR_ARG;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
-  if (stream) { c->st = (cudaStream_t)stream; c->ext_stream = true; }
-  else if (c->ext_stream) { c->st = c->own_st; c->ext_stream = false; }
+  c->st = (cudaStream_t)stream;
+  c->ext_stream = true;
+  return CKL_OK;
+}
+extern "C" int ckl_ctx_own_stream(ckl_ctx* c) {
+  if (!c) return CKL_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->st);
+  c->st = c->own_st;
+  c->ext_stream = false;
   return CKL_OK;
 }
 

@@ -139,8 +139,10 @@ CKL_API int ckl_shard_fetch(ckl_ctx* ctx, uint8_t* keys, uint64_t* components_pe
 /* Per-stage CUDA-event timing on the context's stream.  ckl_prof_read formats "stage=ms_total:calls;..." */
 CKL_API int ckl_prof_enable(ckl_ctx* ctx, int on);
 CKL_API int ckl_prof_read(ckl_ctx* ctx, char* buf, size_t cap);
-/* Run the context's work on a caller-owned CUDA stream (cudaStream_t as void*; NULL restores the own stream). */
+/* Run the context's work on a caller-owned CUDA stream (cudaStream_t as void*; 0 = the legacy default stream, which
+ * is what torch uses by default).  ckl_ctx_own_stream goes back to the context's private non-blocking stream. */
 CKL_API int ckl_ctx_set_stream(ckl_ctx* ctx, void* stream);
+CKL_API int ckl_ctx_own_stream(ckl_ctx* ctx);
 /* Number of kernels this library has launched in this process. */
 CKL_API uint64_t ckl_launch_count(void);
 /* CRC-32C (Castagnoli) of a host or device buffer, computed on the GPU (src/crc.hpp:39-57). */

@@ -37,9 +37,24 @@ def main():
                 same = got == want
                 print(f"shape {shape} {np.dtype(dt).name} order {order}: sharded == monolithic: {same} ({len(got)} bytes)", flush=True)
                 ok &= same
+                if not same:
+                    from oracle import oracle as O
+                    sg, sw = O.sections(got), O.sections(want)
+                    for k in sw:
+                        if sg[k] != sw[k]:
+                            if k == "codes":
+                                for z, (a, b) in enumerate(zip(sg[k], sw[k])):
+                                    if a != b:
+                                        print(f"  codes[z={z}] got({len(a)}) {a.hex()[:160]}\n             want({len(b)}) {b.hex()[:160]}", flush=True)
+                            else:
+                                i = next((j for j in range(min(len(sg[k]), len(sw[k]))) if sg[k][j] != sw[k][j]), -1)
+                                print(f"  section {k}: len {len(sg[k])} vs {len(sw[k])}, first diff at {i}: {bytes(sg[k][i:i+16]).hex()} vs {bytes(sw[k][i:i+16]).hex()}", flush=True)
             s = job.broadcast_stream(s)
             out = torch.empty_like(vol)
-            job.decompress_shard(s, z0, z1, out)
+            try:
+                job.decompress_shard(s, z0, z1, out)
+            except RuntimeError as e:
+                print(f"rank {rank}: decode error {e}", flush=True)
             torch.cuda.synchronize()
             good = torch.equal(out.view(torch.uint8), vol.view(torch.uint8))
             if not good:
