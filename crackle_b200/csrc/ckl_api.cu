@@ -12,8 +12,8 @@
 void launch_exscan_u32_u64(const u32* in, u32 n, u32 stride, u64* out, ull* total_out, u64 add_each, cudaStream_t st);
 void launch_ccl_resolve(const Geom& g, const u32* DV, CclBufs& B, u64 total_runs, const CrcTables* d_tables, u32 crc_init_term, cudaStream_t st);
 void launch_markov_copy(const Geom& g, TraceBufs& T, MarkovBufs& M, u8* dst, cudaStream_t st);
-void launch_trace_walk(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st);
-void launch_trace_post(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st);
+void launch_trace_walk(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes, u32 max_nodes, cudaStream_t st);
+void launch_trace_post(const Geom& g, TraceBufs& T, ull* scal, u64 total_ev_cap, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------------
 struct ShardJob {
@@ -246,14 +246,21 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   STAGE(c, "ccl_solve", launch_ccl_solve(g, c->DV.as<u32>(), c->DH.as<u32>(), c->ccl, c->dtab, c->scal, st));
   read_scalars(c);
   J.ncomp = c->hscal[SC_COMPONENTS];
-  const u64 symCap = c->hscal[SC_SYMCAP], stackCap = c->hscal[SC_STACKCAP], chainCap = c->hscal[SC_CHAINCAP], cpCap = c->hscal[SC_CPCAP];
-  c->tr.sym.ensure(symCap);
-  c->tr.cpPrefix.ensure(symCap * 4);
+  const u64 evCap = c->hscal[SC_SYMCAP], stackCap = c->hscal[SC_STACKCAP], chainCap = c->hscal[SC_CHAINCAP], cpCap = c->hscal[SC_CPCAP];
+  const u64 nodes = c->hscal[SC_NODES];
+  const u32 maxNodes = (u32)c->hscal[SC_MAXNODES];
+  if (maxNodes >= (1u << 28)) throw CklError(CKL_ERR_ARG, "crackle_b200: slice has too many crack-graph nodes");
+  c->tr.nodeVertex.ensure(nodes * 4 + 16);
+  c->tr.nodeAdj.ensure(nodes + 16);
+  c->tr.seFar.ensure(nodes * 16 + 16);
+  c->tr.seLen.ensure(nodes * 16 + 16);
+  c->tr.ev.ensure(evCap * 4 + 16);
+  c->tr.evCp.ensure((evCap + g.sz) * 4 + 16);
   c->tr.stack.ensure(stackCap * 8);
   c->tr.chain.ensure(chainCap * sizeof(ChainRec));
   c->tr.cp.ensure(cpCap);
-  STAGE(c, "trace_walk", launch_trace_walk(g, c->tr, c->scal, st));
-  STAGE(c, "trace_post", launch_trace_post(g, c->tr, c->scal, st));
+  STAGE(c, "trace_walk", launch_trace_walk(g, c->tr, c->scal, nodes, maxNodes, st));
+  STAGE(c, "trace_post", launch_trace_post(g, c->tr, c->scal, evCap, st));
   // component ranks, crcs, component labels
   const u32 init_term = gf_mul(gf_xpow32(c->htab.pw, (u32)g.sxy), 0xFFFFFFFFu);
   STAGE(c, "ccl_resolve_crc", launch_ccl_resolve(g, c->DV.as<u32>(), c->ccl, J.runs, c->dtab, init_term, st));

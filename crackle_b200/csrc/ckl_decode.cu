@@ -37,19 +37,19 @@ __device__ __forceinline__ void mark_move(DecodeState& s, u32 m) {
   const u32 W = g.W;
   if (m == 0) {          // up: vertical crack at column x, row y-1
     if (s.y == 0) { s.bad = true; return; }
-    if (s.x > 0 && s.x < g.sx) s.EV[(u64)(s.y - 1) * W + (s.x >> 5)] |= 1u << (s.x & 31);
+    if (s.x > 0 && s.x < g.sx) atomicOr(&s.EV[(u64)(s.y - 1) * W + (s.x >> 5)], 1u << (s.x & 31));
     s.y--;
   } else if (m == 2) {   // down: vertical crack at column x, row y
     if (s.y >= g.sy) { s.bad = true; return; }
-    if (s.x > 0 && s.x < g.sx) s.EV[(u64)s.y * W + (s.x >> 5)] |= 1u << (s.x & 31);
+    if (s.x > 0 && s.x < g.sx) atomicOr(&s.EV[(u64)s.y * W + (s.x >> 5)], 1u << (s.x & 31));
     s.y++;
   } else if (m == 3) {   // left: horizontal crack above pixel (x-1, y)
     if (s.x == 0) { s.bad = true; return; }
-    if (s.y > 0 && s.y < g.sy) s.EH[(u64)s.y * W + ((s.x - 1) >> 5)] |= 1u << ((s.x - 1) & 31);
+    if (s.y > 0 && s.y < g.sy) atomicOr(&s.EH[(u64)s.y * W + ((s.x - 1) >> 5)], 1u << ((s.x - 1) & 31));
     s.x--;
   } else {               // right: horizontal crack above pixel (x, y)
     if (s.x >= g.sx) { s.bad = true; return; }
-    if (s.y > 0 && s.y < g.sy) s.EH[(u64)s.y * W + (s.x >> 5)] |= 1u << (s.x & 31);
+    if (s.y > 0 && s.y < g.sy) atomicOr(&s.EH[(u64)s.y * W + (s.x >> 5)], 1u << (s.x & 31));
     s.x++;
   }
 }
@@ -114,10 +114,51 @@ __device__ __forceinline__ bool fsm_feed(Fsm& f, DecodeState& s, BocIter& it, u3
   return !s.bad;
 }
 
+// LSB-first bit reader over a byte range: aligned 32-bit loads, one word prefetched ahead of use so the load
+// latency overlaps the decode of the previous 16+ symbols; bits past the end read as zero.
+struct BitReader {
+  const u32* q;
+  u64 nw, idx;
+  u64 cur;
+  u32 cnt, nxt, lastMask;
+  __device__ __forceinline__ u32 fetch() {
+    if (idx >= nw) return 0u;
+    u32 v = __ldg(q + idx);
+    if (idx == nw - 1) v &= lastMask;
+    return v;
+  }
+  __device__ __forceinline__ void refill() {
+    if (cnt <= 32) { cur |= (u64)nxt << cnt; cnt += 32; idx++; nxt = fetch(); }
+  }
+  __device__ void init(const u8* p, u64 nbytes) {
+    const u32 a = (u32)((u64)p & 3);
+    q = reinterpret_cast<const u32*>(p - a);
+    nw = nbytes ? (a + nbytes + 3) / 4 : 0;
+    const u32 vb = (u32)((a + nbytes - 1) & 3) + 1;             // valid bytes in the last word
+    lastMask = vb == 4 ? 0xFFFFFFFFu : ((1u << (8 * vb)) - 1u);
+    idx = 0; cur = 0; cnt = 0;
+    nxt = fetch();
+    refill();
+    cur >>= 8 * a; cnt -= 8 * a;
+    refill();
+  }
+  __device__ __forceinline__ u32 peek(u32 nb) const { return (u32)cur & ((1u << nb) - 1u); }
+  __device__ __forceinline__ void skip(u32 nb) { cur >>= nb; cnt -= nb; refill(); }
+};
+
+#define DECODE_SMEM_MODEL 4096   // markov models up to order 5 are staged in shared memory
+
 __global__ void __launch_bounds__(32) k_decode_slices(Geom g, const u8* __restrict__ stream, const u64* __restrict__ codeOff, int order,
                                                        const u8* __restrict__ model, u32* EVall, u32* EHall, u32* stackAll,
                                                        const u64* __restrict__ stackOff, ull* scal) {
+  __shared__ u8 smodel[DECODE_SMEM_MODEL];
   const u32 z = blockIdx.x;
+  const u32 mbytes = order > 0 ? (4u << (2 * order)) : 0u;
+  const bool msm = order > 0 && mbytes <= DECODE_SMEM_MODEL;
+  if (msm) {
+    for (u32 i = threadIdx.x; i < mbytes; i += blockDim.x) smodel[i] = model[i];
+    __syncwarp();
+  }
   if (threadIdx.x != 0 || z >= g.sz) return;
   const u8* code = stream + codeOff[z];
   const u64 clen = codeOff[z + 1] - codeOff[z];
@@ -135,32 +176,31 @@ __global__ void __launch_bounds__(32) k_decode_slices(Geom g, const u8* __restri
   Fsm f; f.last_move = 255; f.pend = -1; f.open = 0;
   const u8* body = code + isz;
   const u64 blen = clen - isz;
+  BitReader br;
+  br.init(body, blen);
   if (order == 0) {
     u32 last = 0;
-    bool go = true;
-    for (u64 i = 0; i < blen && go; i++) {
-      const u32 byte = body[i];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        if (!go) break;
-        last = (last + ((byte >> (2 * j)) & 3u)) & 3u;
-        go = fsm_feed(f, s, it, last);
-      }
+    const u64 nfields = blen * 4;
+    for (u64 i = 0; i < nfields; i++) {
+      last = (last + br.peek(2)) & 3u;
+      br.skip(2);
+      if (!fsm_feed(f, s, it, last)) break;
     }
   } else if (blen) {
+    const u8* mdl = msm ? smodel : model;
     const u32 top = 2 * (order - 1);
-    u32 mv = body[0] & 3u;
+    u32 mv = br.peek(2);
+    br.skip(2);
     u32 ctx = mv << top;
     bool go = fsm_feed(f, s, it, mv);
     u64 pos = 2;
     const u64 nbit = blen * 8;
     while (go && pos < nbit) {
-      u32 v = body[pos >> 3];
-      if ((pos >> 3) + 1 < blen) v |= (u32)body[(pos >> 3) + 1] << 8;
-      v = (v >> (pos & 7)) & 7u;
+      const u32 v = br.peek(3);
       u32 rank, len;
       if (!(v & 1)) { rank = 0; len = 1; } else if (!(v & 2)) { rank = 1; len = 2; } else if (!(v & 4)) { rank = 2; len = 3; } else { rank = 3; len = 3; }
-      const u32 d = model[(u64)ctx * 4 + rank];
+      const u32 d = mdl[(u64)ctx * 4 + rank];
+      br.skip(len);
       pos += len;
       mv = (mv + d) & 3u;
       ctx = (ctx >> 2) + (d << top);

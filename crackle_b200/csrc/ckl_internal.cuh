@@ -13,7 +13,7 @@ struct Geom {
 // ---- device scalars written by kernels and read back in one small copy --------------------------------
 enum {
   SC_MAX = 0, SC_PAIRS, SC_RUNS, SC_COMPONENTS, SC_EDGES, SC_SYMCAP, SC_STACKCAP, SC_CHAINCAP, SC_CPCAP,
-  SC_CODEPOINTS, SC_CODE_BYTES, SC_ERROR, SC_UNIQUE, SC_FIRST, SC_LAST, SC_CRC_BAD, SC_COUNT = 24
+  SC_CODEPOINTS, SC_CODE_BYTES, SC_ERROR, SC_UNIQUE, SC_FIRST, SC_LAST, SC_CRC_BAD, SC_NODES, SC_MAXNODES, SC_COUNT = 24
 };
 
 // ---- planes + CCL (ckl_planes.cu) ------------------------------------------------------------------------
@@ -38,17 +38,21 @@ void launch_crc_finalize_slices(u32* sliceCrc, u32 sz, u32 init_term, cudaStream
 
 // ---- tracing + packing (ckl_trace.cu) ------------------------------------------------------------------
 struct TraceBufs {
-  DBuf EV, EH;                                  // mutable crack planes
-  DBuf bounds;                                  // per slice: E, B, C  (3 x u32 x sz)
-  DBuf offs;                                    // per slice u64 offsets: sym, stack, chain, cp  (4 x (sz+1))
-  DBuf sym, stack, chain, cp, cpPrefix;         // sized from scal[SC_*CAP]
+  DBuf VW;                                      // uint4 {r,d,u,n} per 32-vertex word of the (sx+1) x (sy+1) vertex grid
+  DBuf nodePrefix, rowNodes, rowBase;           // node numbering: per vertex word / per vertex row
+  DBuf sliceNodes, nodeBase;                    // per slice: node count (u32), first global node index (u64 x (sz+1))
+  DBuf nodeVertex, nodeAdj;                     // per node: vertex index (u32), remaining-edge nibble (u8, global replay)
+  DBuf seFar, seLen;                            // per (node, direction) slot: far node << 2 | arrival dir, length
+  DBuf bounds;                                  // per slice: E, S, C + caps (2 x 4 x u32 x sz)
+  DBuf offs;                                    // per slice u64 offsets: events, stack, chain, cp  (4 x (sz+1))
+  DBuf ev, evCp, stack, chain, cp;              // sized from scal[SC_*CAP]
   DBuf sliceInfo;                               // per slice: ncp, nchains, boc_bytes, code_bytes (4 x u32 x sz)
   DBuf codeOff;                                 // u64 x (sz+1) byte offsets of each slice's crack code
 };
+// symBegin / symEnd / t2f are EVENT indices inside the slice's event list
 struct ChainRec { u32 adjStart, symBegin, symEnd, t2f; u32 ncp, outBase, sortedIdx, sortedStart; };
 
 void launch_trace_prepare(const Geom& g, const u32* DV, const u32* DH, int permissible, TraceBufs& T, ull* scal, cudaStream_t st);
-void launch_trace(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st);
 // order 0: per-slice code sizes -> codeOff (exclusive scan, total in scal[SC_CODE_BYTES]) then pack into dst
 void launch_code_sizes_order0(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st);
 void launch_pack_order0(const Geom& g, TraceBufs& T, u8* dst, cudaStream_t st);

@@ -5,16 +5,33 @@
 // Reference behaviour reproduced:
 //   create_crack_codes walk / next_cluster / erase_edge     src/crackcodes.hpp:390-450, :41-64
 //   remove_initial_branch                                   src/crackcodes.hpp:185-242
-//   remove_spurious_branches                                src/crackcodes.hpp:250-281  (done online in the walker)
+//   remove_spurious_branches                                src/crackcodes.hpp:250-281  (done online in the replay)
 //   symbols_to_codepoints                                   src/crackcodes.hpp:128-183
 //   write_boc_index / pack_codepoints                       src/crackcodes.hpp:318-372, :455-496
 //
+// The reference walk is a serial, order-dependent trail over the crack graph (one chain of ~10^5 moves per slice).
+// Here it is replayed on the CONTRACTED graph (validated against the oracle by tools/proto_trace.py):
+//   1. k_vw_build     vertex words {r,d,u,n}: right / down / up edge bits of 32 vertices and the node mask n.
+//                     node = static degree 1, 3 or 4, or an (R,D)-only corner whose horizontal run to the right
+//                     does not end at a vertex with an up edge.  Every component's minimum vertex (the chain
+//                     start of next_cluster) has only R / D edges and is such a node; a degree-2 vertex entered
+//                     through one edge never branches, so all other vertices are pure pass-through.
+//   2. node numbering in raster order (per-row popcount prefix) => next_cluster = smallest node id with edges left
+//   3. k_path_walk    one thread per (node, direction): follow degree-2 vertices to the far node -> super-edges
+//   4. k_replay       one warp per slice: the reference walk over node records held in shared memory (4 x u16 per
+//                     node), emitting an event list (E super-edge / B / T / S) -- ~6x fewer serial steps, no
+//                     global-memory latency on the dependent chain
+//   5. k_event_post   scans: codepoint offsets per event, chain order by adjusted start vertex, BOC sizes
+//   6. k_expand       one thread per event: re-walk the super-edge writing absolute codepoints at their final
+//                     position (reversed + flipped inside a removed initial branch); b/t escape pairs by lookback
+//
 // Crack graph on bit-planes (pixel-indexed, W words per row): right edge of vertex (vx,vy) = EH bit vx of row vy
 // (horizontal crack above pixel (vx,vy), vy >= 1); down edge of vertex (vx,vy) = EV bit vx of row vy (vertical
-// crack left of pixel (vx,vy), vx >= 1).  Walking an edge clears its bit.
+// crack left of pixel (vx,vy), vx >= 1).
 #include "ckl_internal.cuh"
 
 #define NONE32 0xFFFFFFFFu
+enum { EV_E = 0, EV_B = 1, EV_T = 2, EV_S = 3 };      // event type in bits 30..31, payload (local slot) below
 
 static int g_sms_t = 0;
 static int sms() {
@@ -48,70 +65,132 @@ __device__ __forceinline__ u32 crack_v(const Geom& g, const u32* DV, u64 idx, u3
   return perm ? (~d & valid_x(g, w) & ~(w == 0 ? 1u : 0u)) : d;
 }
 
-// Builds the mutable crack planes and exact per-slice capacity bounds:
-//   E = edges, B >= number of 'b' symbols (pushes), C >= number of chains.
-__global__ void __launch_bounds__(256) k_trace_prepare(Geom g, const u32* __restrict__ DV, const u32* __restrict__ DH, int perm,
-                                                        u32* __restrict__ EV, u32* __restrict__ EH, u32* bounds) {
-  const u64 nwords = g.words(), stride = (u64)gridDim.x * blockDim.x;
-  const u64 nloop = (nwords + stride - 1) / stride;
-  for (u64 k = 0; k < nloop; k++) {
-    const u64 i = k * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u32 z = NONE32, e = 0, b = 0, c = 0;
-    if (i < nwords) {
-      const u64 row = i / g.W;
-      const u32 w = (u32)(i - row * g.W);
-      z = (u32)(row / g.sy);
-      const u32 y = (u32)(row - (u64)z * g.sy);
-      const u32 r = crack_h(g, DH, i, y, w, perm);
-      const u32 d = crack_v(g, DV, i, w, perm);
-      EH[i] = r;
-      EV[i] = d;
-      const u32 rprev = w > 0 ? crack_h(g, DH, i - 1, y, w - 1, perm) : 0u;
-      const u32 l = (r << 1) | (rprev >> 31);
-      const u32 u = y > 0 ? crack_v(g, DV, i - g.W, w, perm) : 0u;
+struct VGeom {           // vertex grid of one slice
+  u32 sxe, sye, Wv;      // (sx+1), (sy+1), 32-vertex words per vertex row
+  u64 rowsAll, wordsAll; // over all slices
+};
+static VGeom vgeom(const Geom& g) {
+  VGeom v;
+  v.sxe = g.sx + 1; v.sye = g.sy + 1; v.Wv = (v.sxe + 31) / 32;
+  v.rowsAll = (u64)v.sye * g.sz; v.wordsAll = v.rowsAll * v.Wv;
+  return v;
+}
+
+// 1. vertex words + node mask + per-slice bounds: bounds[z] = {E edges, S node slots with an edge, C start-capable nodes}
+__global__ void __launch_bounds__(256) k_vw_build(Geom g, VGeom vg, const u32* __restrict__ DV, const u32* __restrict__ DH, int perm,
+                                                   uint4* __restrict__ VW, u32* __restrict__ cnt, u32* bounds) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 nloop = (vg.wordsAll + stride - 1) / stride;
+  for (u64 it = 0; it < nloop; it++) {
+    const u64 i = it * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 z = NONE32, e = 0, s = 0, c = 0;
+    if (i < vg.wordsAll) {
+      const u64 row = i / vg.Wv;
+      const u32 w = (u32)(i - row * vg.Wv);
+      z = (u32)(row / vg.sye);
+      const u32 y = (u32)(row - (u64)z * vg.sye);
+      const u64 prow = ((u64)z * g.sy + y) * g.W;           // pixel-plane row (valid when y < sy)
+      u32 r = 0, rp = 0, d = 0, u = 0;
+      if (y < g.sy) {
+        if (w < g.W) { r = crack_h(g, DH, prow + w, y, w, perm); d = crack_v(g, DV, prow + w, w, perm); }
+        if (w > 0 && w - 1 < g.W) rp = crack_h(g, DH, prow + w - 1, y, w - 1, perm);
+      }
+      if (y >= 1 && w < g.W) u = crack_v(g, DV, prow - g.W + w, w, perm);
+      const u32 l = (r << 1) | (rp >> 31);
       // bit-sliced degree of the 32 vertices of this word
       const u32 s1 = r ^ l, c1 = r & l, s2 = d ^ u, c2 = d & u;
       const u32 sum0 = s1 ^ s2, carry = s1 & s2;
       const u32 two = c1 ^ c2 ^ carry, four = c1 & c2;
-      const u32 deg3 = sum0 & two, deg2 = ~sum0 & two;
-      const u32 corner = ~u & ~l & (r | d);                 // vertices that can start a chain
+      u32 n = (sum0 & ~two) | (sum0 & two) | four;          // degree 1, 3, 4
+      // (R,D)-only corners stay nodes unless their horizontal run to the right ends (inside this word) at a vertex
+      // with an up edge (then the component reaches a higher row and the corner cannot be its minimum vertex)
+      u32 cm = r & d & ~l & ~u;
+      const u32 stop = ~r | d | u;
+      while (cm) {
+        const u32 b = __ffs(cm) - 1;
+        cm &= cm - 1;
+        const u32 sm = b == 31 ? 0u : (stop & ~((2u << b) - 1u));
+        if (sm == 0 || !((u >> (__ffs(sm) - 1)) & 1u)) n |= 1u << b;
+      }
+      VW[i] = make_uint4(r, d, u, n);
+      cnt[i] = __popc(n);
       e = __popc(r) + __popc(d);
-      b = 2 * __popc(deg3) + 3 * __popc(four) + __popc(deg2 & corner);
-      c = __popc(corner);
+      s = __popc(n & r) + __popc(n & l) + __popc(n & d) + __popc(n & u);
+      c = __popc(n & ~l & ~u);
     }
     const u32 z0 = __shfl_sync(FULL_MASK, z, 0);
     if (__all_sync(FULL_MASK, z == z0)) {
       e = __reduce_add_sync(FULL_MASK, e);
-      b = __reduce_add_sync(FULL_MASK, b);
+      s = __reduce_add_sync(FULL_MASK, s);
       c = __reduce_add_sync(FULL_MASK, c);
       if ((threadIdx.x & 31) == 0 && z0 != NONE32) {
         if (e) atomicAdd(bounds + (u64)z0 * 4 + 0, e);
-        if (b) atomicAdd(bounds + (u64)z0 * 4 + 1, b);
+        if (s) atomicAdd(bounds + (u64)z0 * 4 + 1, s);
         if (c) atomicAdd(bounds + (u64)z0 * 4 + 2, c);
       }
     } else if (z != NONE32) {
       if (e) atomicAdd(bounds + (u64)z * 4 + 0, e);
-      if (b) atomicAdd(bounds + (u64)z * 4 + 1, b);
+      if (s) atomicAdd(bounds + (u64)z * 4 + 1, s);
       if (c) atomicAdd(bounds + (u64)z * 4 + 2, c);
     }
   }
 }
 
-// caps[z] = {symCap, stackCap, chainCap, cpCap}
-__global__ void k_trace_caps(u32 sz, const u32* __restrict__ bounds, u32* __restrict__ caps) {
+// 2a. per vertex row: counts -> exclusive prefix (in place) and row totals.  One warp per row.
+__global__ void __launch_bounds__(256) k_node_prefix(VGeom vg, u32* __restrict__ cnt, u32* __restrict__ rowNodes) {
+  const u32 lane = threadIdx.x & 31;
+  const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
+  for (u64 row = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < vg.rowsAll; row += nwarps) {
+    u32 carry = 0;
+    for (u32 w0 = 0; w0 < vg.Wv; w0 += 32) {
+      const u32 w = w0 + lane;
+      const u32 c = w < vg.Wv ? cnt[row * vg.Wv + w] : 0;
+      const u32 inc = warp_incl_scan(c);
+      if (w < vg.Wv) cnt[row * vg.Wv + w] = carry + inc - c;
+      carry += __shfl_sync(FULL_MASK, inc, 31);
+    }
+    if (lane == 0) rowNodes[row] = carry;
+  }
+}
+// 2b. per slice: row totals -> row bases, slice totals
+__global__ void __launch_bounds__(256) k_node_rows(u32 sz, u32 sye, const u32* __restrict__ rowNodes, u32* __restrict__ rowBase,
+                                                    u32* __restrict__ sliceNodes) {
+  __shared__ u32 sm[33];
+  for (u32 z = blockIdx.x; z < sz; z += gridDim.x) {
+    u32 carry = 0;
+    for (u32 y0 = 0; y0 < sye; y0 += blockDim.x) {
+      const u32 y = y0 + threadIdx.x;
+      const u32 v = y < sye ? rowNodes[(u64)z * sye + y] : 0;
+      u32 tot;
+      const u32 ex = block_excl_scan(v, sm, tot);
+      if (y < sye) rowBase[(u64)z * sye + y] = carry + ex;
+      carry += tot;
+    }
+    if (threadIdx.x == 0) sliceNodes[z] = carry;
+  }
+}
+
+// caps[z] = {evCap, stackCap, chainCap, cpCap}
+__global__ void k_trace_caps(u32 sz, const u32* __restrict__ bounds, const u32* __restrict__ sliceNodes, u32* __restrict__ caps, ull* scal) {
   const u32 z = blockIdx.x * blockDim.x + threadIdx.x;
   if (z >= sz) return;
-  const u32 E = bounds[(u64)z * 4], B = bounds[(u64)z * 4 + 1], C = bounds[(u64)z * 4 + 2];
-  caps[(u64)z * 4 + 0] = E + 2 * B + C + 8;        // symbols: moves + b + t (t = b + chains)
-  caps[(u64)z * 4 + 1] = B + 4;                    // revisit stack depth
-  caps[(u64)z * 4 + 2] = C + 2;                    // chains
-  caps[(u64)z * 4 + 3] = E + 4 * B + 2 * C + 16;   // codepoints: moves + 2b + 2t
+  const u32 E = bounds[(u64)z * 4], S = bounds[(u64)z * 4 + 1], C = bounds[(u64)z * 4 + 2], N = sliceNodes[z];
+  const u32 B = S - N;                               // >= number of 'b' events: sum over nodes of (degree - 1)
+  caps[(u64)z * 4 + 0] = S / 2 + 2 * B + C + 4;      // events: super-edges + b + t (t = b + chains)
+  caps[(u64)z * 4 + 1] = B + 4;                      // revisit stack depth
+  caps[(u64)z * 4 + 2] = C + 2;                      // chains
+  caps[(u64)z * 4 + 3] = E + 4 * B + 2 * C + 16;     // codepoints: moves + 2b + 2t
+  atomicMax(&scal[SC_MAXNODES], (ull)N);
 }
 
 void launch_trace_prepare(const Geom& g, const u32* DV, const u32* DH, int permissible, TraceBufs& T, ull* scal, cudaStream_t st) {
-  const u64 nwords = g.words();
-  T.EV.ensure(nwords * 4);
-  T.EH.ensure(nwords * 4);
+  const VGeom vg = vgeom(g);
+  T.VW.ensure(vg.wordsAll * 16);
+  T.nodePrefix.ensure(vg.wordsAll * 4);
+  T.rowNodes.ensure(vg.rowsAll * 4);
+  T.rowBase.ensure(vg.rowsAll * 4);
+  T.sliceNodes.ensure((u64)g.sz * 4);
+  T.nodeBase.ensure(((u64)g.sz + 1) * 8);
   T.bounds.ensure((u64)g.sz * 4 * 4 * 2);          // bounds (4 x u32) + caps (4 x u32) per slice
   T.offs.ensure(((u64)g.sz + 1) * 8 * 4);
   T.sliceInfo.ensure((u64)g.sz * 4 * 4);
@@ -119,9 +198,14 @@ void launch_trace_prepare(const Geom& g, const u32* DV, const u32* DH, int permi
   u32* bounds = T.bounds.as<u32>();
   u32* caps = bounds + (u64)g.sz * 4;
   CUDA_CHECK(cudaMemsetAsync(bounds, 0, (u64)g.sz * 4 * 4, st));
-  k_trace_prepare<<<grid_cap(nwords, 256, 16), 256, 0, st>>>(g, DV, DH, permissible, T.EV.as<u32>(), T.EH.as<u32>(), bounds);
+  k_vw_build<<<grid_cap(vg.wordsAll, 256, 8), 256, 0, st>>>(g, vg, DV, DH, permissible, T.VW.as<uint4>(), T.nodePrefix.as<u32>(), bounds);
   LAUNCH_CHECK();
-  k_trace_caps<<<(g.sz + 255) / 256, 256, 0, st>>>(g.sz, bounds, caps);
+  k_node_prefix<<<grid_cap(vg.rowsAll, 8, 8), 256, 0, st>>>(vg, T.nodePrefix.as<u32>(), T.rowNodes.as<u32>());
+  LAUNCH_CHECK();
+  k_node_rows<<<grid_cap(g.sz, 1, 8), 256, 0, st>>>(g.sz, vg.sye, T.rowNodes.as<u32>(), T.rowBase.as<u32>(), T.sliceNodes.as<u32>());
+  LAUNCH_CHECK();
+  launch_exscan_u32_u64(T.sliceNodes.as<u32>(), g.sz, 1, T.nodeBase.as<u64>(), &scal[SC_NODES], 0, st);
+  k_trace_caps<<<(g.sz + 255) / 256, 256, 0, st>>>(g.sz, bounds, T.sliceNodes.as<u32>(), caps, scal);
   LAUNCH_CHECK();
   u64* offs = T.offs.as<u64>();
   const u64 n1 = (u64)g.sz + 1;
@@ -132,189 +216,282 @@ void launch_trace_prepare(const Geom& g, const u32* DV, const u32* DH, int permi
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// The walk.  One block per slice; the block finds the next vertex with edges cooperatively (next_cluster),
-// thread 0 walks the chain.
 struct TraceParams {
   Geom g;
-  u32 *EV, *EH;
-  const u64* offs;      // 4 arrays of (sz+1): sym, stack, chain, cp
-  const u32* caps;      // per slice 4 x u32
-  u8* sym;
+  VGeom vg;
+  const uint4* VW;
+  const u32* nodePrefix;   // exclusive node count inside the vertex row, per vertex word
+  const u32* rowBase;      // per vertex row: first (slice-local) node id
+  const u32* sliceNodes;
+  const u64* nodeBase;     // per slice: first global node index
+  u32* nodeVertex;         // per node: vx + sxe * vy
+  u32* seFar;              // per slot (4 per node): (far local node << 2) | arrival direction at the far node; NONE32 = no edge
+  u32* seLen;              // per slot: moves along the super-edge
+  u8* nodeAdj;             // per node: remaining-edge nibble (global-memory replay only)
+  const u64* offs;         // 4 arrays of (sz+1): events, stack, chain, cp
+  const u32* caps;         // per slice 4 x u32
+  u32* ev;                 // events
+  u32* evCp;               // per event: exclusive codepoint offset inside the slice (creation order); one extra slot per slice
   uint2* stack;
   ChainRec* chain;
   u8* cp;
-  u32* cpPrefix;
-  u32* sliceInfo;       // per slice: nsym|ncp, nchains, bocBytes, codeBytes
+  u32* sliceInfo;          // per slice: nev|ncp, nchains, bocBytes, codeBytes
   ull* scal;
+  u32 smemNodeCap;         // slices with at most this many nodes are replayed from shared memory
 };
 
-__device__ __forceinline__ u32 block_min_u32(u32 v, u32* sm) {
-  v = __reduce_min_sync(FULL_MASK, v);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
-  __syncthreads();
-  u32 r = NONE32;
-  for (u32 i = 0; i < (blockDim.x >> 5); i++) r = min(r, sm[i]);
-  __syncthreads();
-  return r;
+__device__ __forceinline__ u32 slice_of(const u64* __restrict__ base, u32 sz, u64 idx) {   // last z with base[z] <= idx
+  u32 lo = 0, hi = sz;
+  while (hi - lo > 1) { const u32 m = (lo + hi) >> 1; if (base[m] <= idx) lo = m; else hi = m; }
+  return lo;
 }
 
-__device__ bool walk_chain(const Geom& g, u32* __restrict__ EV, u32* __restrict__ EH, u32 vx, u32 vy, u8* sym, u32& nsym, u32 symCap,
-                           uint2* stack, u32 stackCap, ChainRec& rec, ull* scal) {
-  bool ok = true;
-  const u32 sxe = g.sx + 1, W = g.W;
-  u32 x = vx, y = vy, sp = 0, nB = 0;
-  const u32 begin = nsym;
-  bool firstT = true, t2 = false, justPopped = false;
-  u32 t2f = 0, poppedB = 0, adjStart = vx + sxe * vy;
-  for (;;) {
-    // adjacency of vertex (x,y): bit0 right, bit1 left, bit2 down, bit3 up
-    u32 adj = 0;
-    if (y < g.sy) {
-      const u32* hrow = EH + (u64)y * W;
-      if (x < g.sx) {
-        adj |= (hrow[x >> 5] >> (x & 31)) & 1u;
-        adj |= ((EV[(u64)y * W + (x >> 5)] >> (x & 31)) & 1u) << 2;
-      }
-      if (x > 0) adj |= ((hrow[(x - 1) >> 5] >> ((x - 1) & 31)) & 1u) << 1;
+// 3a. node -> vertex
+__global__ void __launch_bounds__(256) k_node_init(TraceParams P) {
+  const VGeom vg = P.vg;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < vg.wordsAll; i += stride) {
+    u32 n = P.VW[i].w;
+    if (!n) continue;
+    const u64 row = i / vg.Wv;
+    const u32 w = (u32)(i - row * vg.Wv);
+    const u32 z = (u32)(row / vg.sye), y = (u32)(row - (u64)z * vg.sye);
+    u64 id = P.nodeBase[z] + P.rowBase[row] + P.nodePrefix[i];
+    while (n) {
+      const u32 b = __ffs(n) - 1;
+      n &= n - 1;
+      P.nodeVertex[id++] = y * vg.sxe + w * 32 + b;
     }
-    if (y > 0 && x < g.sx) adj |= ((EV[(u64)(y - 1) * W + (x >> 5)] >> (x & 31)) & 1u) << 3;
-
-    if (adj == 0) {
-      // a 't': dead end after a move, or -- directly after a pop -- a spurious branch (remove_spurious_branches)
-      if (firstT) {
-        firstT = false;
-        if (nB == 1 && sym[begin] == 'b') { t2 = true; t2f = nsym - begin; adjStart = x + sxe * y; }   // remove_initial_branch applies
-      }
-      if (nsym >= symCap) { atomicExch(&scal[SC_ERROR], 1ull); ok = false; break; }
-      if (justPopped && !(t2 && poppedB == begin)) { sym[poppedB] = 's'; sym[nsym++] = 's'; }
-      else sym[nsym++] = 't';
-      if (sp == 0) break;
-      const uint2 e = stack[--sp];
-      y = e.x / sxe;
-      x = e.x - y * sxe;
-      poppedB = e.y;
-      justPopped = true;
-      continue;
-    }
-    justPopped = false;
-    if (nsym + 2 > symCap) { atomicExch(&scal[SC_ERROR], 1ull); ok = false; break; }
-    if (adj & (adj - 1)) {                                  // popcount > 1: branch point
-      if (sp >= stackCap) { atomicExch(&scal[SC_ERROR], 2ull); ok = false; break; }
-      stack[sp++] = make_uint2(x + sxe * y, nsym);
-      sym[nsym++] = 'b';
-      nB++;
-    }
-    const u32 k = __ffs(adj) - 1;                            // priority: right, left, down, up
-    if (k == 0) { EH[(u64)y * W + (x >> 5)] &= ~(1u << (x & 31)); sym[nsym++] = 'r'; x++; }
-    else if (k == 1) { EH[(u64)y * W + ((x - 1) >> 5)] &= ~(1u << ((x - 1) & 31)); sym[nsym++] = 'l'; x--; }
-    else if (k == 2) { EV[(u64)y * W + (x >> 5)] &= ~(1u << (x & 31)); sym[nsym++] = 'd'; y++; }
-    else { EV[(u64)(y - 1) * W + (x >> 5)] &= ~(1u << (x & 31)); sym[nsym++] = 'u'; y--; }
   }
-  rec.adjStart = adjStart;
-  rec.symBegin = begin;
-  rec.symEnd = nsym;
-  rec.t2f = t2 ? t2f : 0;
-  return ok;
 }
 
-__global__ void __launch_bounds__(128) k_trace_walk(TraceParams P) {
-  __shared__ u32 sm[8];
-  __shared__ u32 s_scan, s_nsym, s_nch;
-  const Geom g = P.g;
-  const u64 n1 = (u64)g.sz + 1;
-  const u32 nw = g.sy * g.W;
-  for (u32 z = blockIdx.x; z < g.sz; z += gridDim.x) {
-    u32* EV = P.EV + (u64)z * nw;
-    u32* EH = P.EH + (u64)z * nw;
-    u8* sym = P.sym + P.offs[0 * n1 + z];
-    uint2* stack = P.stack + P.offs[1 * n1 + z];
-    ChainRec* chains = P.chain + P.offs[2 * n1 + z];
-    const u32 symCap = P.caps[(u64)z * 4 + 0], stackCap = P.caps[(u64)z * 4 + 1], chainCap = P.caps[(u64)z * 4 + 2];
-    if (threadIdx.x == 0) { s_scan = 0; s_nsym = 0; s_nch = 0; }
-    __syncthreads();
-    for (;;) {
-      // next_cluster: first word at or after s_scan with any edge bit (all earlier vertices are exhausted)
-      u32 found = NONE32;
-      const u32 start = s_scan;
-      for (u32 base = start; base < nw && found == NONE32; base += blockDim.x * 8) {
-        u32 cand = NONE32;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const u32 i = base + k * blockDim.x + threadIdx.x;
-          if (cand == NONE32 && i < nw && (EH[i] | EV[i])) cand = i;
-        }
-        found = block_min_u32(cand, sm);
-      }
-      if (found == NONE32) break;
-      if (threadIdx.x == 0) {
-        const u32 vy = found / g.W, w = found - vy * g.W;
-        const u32 m = EH[found] | EV[found];
-        const u32 vx = w * 32 + (__ffs(m) - 1);
-        u32 nsym = s_nsym, nch = s_nch;
-        if (nch >= chainCap) { atomicExch(&P.scal[SC_ERROR], 3ull); s_scan = nw; }
-        else {
-          const bool ok = walk_chain(g, EV, EH, vx, vy, sym, nsym, symCap, stack, stackCap, chains[nch], P.scal);
-          s_nsym = nsym;
-          s_nch = nch + 1;
-          s_scan = ok ? found : nw;
-        }
-      }
-      __syncthreads();
+// one step along a super-edge: move in direction kk, then pick the exit of the (degree-2) vertex reached.
+// Returns true when the vertex reached is a node.  Directions: 0 right, 1 left, 2 down, 3 up (the walk priority).
+__device__ __forceinline__ bool se_step(const uint4* __restrict__ vw, u32 Wv, u32& x, u32& y, u32& kk, uint4& word) {
+  x += (kk == 0) - (kk == 1);
+  y += (kk == 2) - (kk == 3);
+  word = __ldg(vw + (u64)y * Wv + (x >> 5));
+  const u32 b = x & 31;
+  if ((word.w >> b) & 1u) return true;
+  u32 a = ((word.x >> b) & 1u) | (((word.y >> b) & 1u) << 2) | (((word.z >> b) & 1u) << 3);
+  a &= ~(1u << (kk ^ 1u));                           // not back along the edge we came by
+  kk = a ? (u32)__ffs(a) - 1 : 1u;                   // the other edge; left is the one not stored in the word
+  return false;
+}
+
+// 3b. one thread per (node, direction)
+__global__ void __launch_bounds__(256) k_path_walk(TraceParams P, u64 nslots) {
+  const VGeom vg = P.vg;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += stride) {
+    const u64 gnode = s >> 2;
+    u32 kk = (u32)(s & 3);
+    const u32 z = slice_of(P.nodeBase, P.g.sz, gnode);
+    const uint4* vw = P.VW + (u64)z * vg.sye * vg.Wv;
+    const u32 v = P.nodeVertex[gnode];
+    u32 y = v / vg.sxe, x = v - y * vg.sxe;
+    uint4 word = __ldg(vw + (u64)y * vg.Wv + (x >> 5));
+    const u32 b = x & 31;
+    u32 has;
+    if (kk == 0) has = (word.x >> b) & 1u;
+    else if (kk == 2) has = (word.y >> b) & 1u;
+    else if (kk == 3) has = (word.z >> b) & 1u;
+    else has = b ? ((word.x >> (b - 1)) & 1u) : (x ? (__ldg(vw + (u64)y * vg.Wv + (x >> 5) - 1).x >> 31) : 0u);
+    if (!has) { P.seFar[s] = NONE32; P.seLen[s] = 0; continue; }
+    u32 len = 1;
+    const u32 limit = 2u * vg.sxe * vg.sye + 8u;
+    while (!se_step(vw, vg.Wv, x, y, kk, word)) {
+      if (++len > limit) { atomicExch(&P.scal[SC_ERROR], 4ull); break; }
     }
-    if (threadIdx.x == 0) { P.sliceInfo[(u64)z * 4 + 0] = s_nsym; P.sliceInfo[(u64)z * 4 + 1] = s_nch; }
-    __syncthreads();
+    const u64 row = (u64)z * vg.sye + y;
+    const u32 far = P.rowBase[row] + P.nodePrefix[row * vg.Wv + (x >> 5)] + __popc(word.w & ((1u << (x & 31)) - 1u));
+    P.seFar[s] = (far << 2) | (kk ^ 1u);
+    P.seLen[s] = len;
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// post-passes
-__device__ __forceinline__ u8 flip_sym(u8 c) { return c == 'u' ? 'd' : c == 'd' ? 'u' : c == 'l' ? 'r' : c == 'r' ? 'l' : c; }
-// symbol i of the chain after remove_initial_branch (positions 1..f-1 reversed and flipped, 0 and f skipped)
-__device__ __forceinline__ u8 eff_sym(const u8* sym, const ChainRec& c, u32 i) {
-  if (c.t2f) {
-    const u32 j = i - c.symBegin;
-    if (j == 0 || j == c.t2f) return 's';
-    if (j < c.t2f) return flip_sym(sym[c.symBegin + c.t2f - j]);
+// 4. the replay.  Node records: SMEM mode = one u64 per node holding four u16 entries (far << 2 | arrival dir),
+// 0xFFFF = no edge left; GLOBAL mode = a remaining-edge nibble per node in global memory + the read-only seFar.
+#define REPLAY_STACK 256      // shared-memory revisit stack entries per slice; deeper levels spill to global
+
+template <bool SMEM>
+struct NodeStore {
+  u64* rec;           // SMEM
+  u8* adj;            // GLOBAL
+  const u32* far;     // GLOBAL
+  __device__ __forceinline__ u32 adjacency(u32 node, u64& w) const {
+    if (SMEM) {
+      w = rec[node];
+      const u32 lo = (u32)w, hi = (u32)(w >> 32);
+      return ((lo & 0xFFFFu) != 0xFFFFu ? 1u : 0u) | ((lo >> 16) != 0xFFFFu ? 2u : 0u) | ((hi & 0xFFFFu) != 0xFFFFu ? 4u : 0u) |
+             ((hi >> 16) != 0xFFFFu ? 8u : 0u);
+    } else {
+      w = adj[node];
+      return (u32)w;
+    }
   }
-  return sym[i];
+  // consume edge k of `node` (record word w already loaded); returns the far entry (far << 2 | arrival dir)
+  __device__ __forceinline__ u32 take(u32 node, u32 k, u64 w) {
+    if (SMEM) {
+      const u32 e = (u32)(w >> (16 * k)) & 0xFFFFu;
+      rec[node] = w | (0xFFFFull << (16 * k));
+      const u32 f = e >> 2, fk = e & 3u;
+      rec[f] |= 0xFFFFull << (16 * fk);              // after the store above: a self-loop clears both entries
+      return e;
+    } else {
+      const u32 e = far[(u64)node * 4 + k];
+      adj[node] = (u8)(w & ~(1u << k));
+      const u32 f = e >> 2, fk = e & 3u;
+      adj[f] = adj[f] & (u8)~(1u << fk);
+      return e;
+    }
+  }
+  __device__ __forceinline__ bool has_edges(u32 node) const { return SMEM ? rec[node] != ~0ull : adj[node] != 0; }
+};
+
+template <bool SMEM>
+__global__ void __launch_bounds__(32) k_replay(TraceParams P) {
+  extern __shared__ u64 smem64[];
+  const u32 z = blockIdx.x, lane = threadIdx.x;
+  const Geom g = P.g;
+  const u32 N = P.sliceNodes[z];
+  if (SMEM != (N <= P.smemNodeCap)) return;           // the other instantiation handles this slice
+  const u64 n1 = (u64)g.sz + 1;
+  const u64 nb = P.nodeBase[z];
+  uint2* sstack = reinterpret_cast<uint2*>(smem64);   // REPLAY_STACK entries
+  NodeStore<SMEM> S;
+  S.rec = smem64 + REPLAY_STACK;
+  S.adj = P.nodeAdj + nb;
+  S.far = P.seFar + nb * 4;
+  for (u32 i = lane; i < N; i += 32) {
+    const uint4 f = reinterpret_cast<const uint4*>(P.seFar + nb * 4)[i];
+    if (SMEM) {
+      const u64 e0 = f.x == NONE32 ? 0xFFFFull : (u64)(f.x & 0xFFFFu), e1 = f.y == NONE32 ? 0xFFFFull : (u64)(f.y & 0xFFFFu);
+      const u64 e2 = f.z == NONE32 ? 0xFFFFull : (u64)(f.z & 0xFFFFu), e3 = f.w == NONE32 ? 0xFFFFull : (u64)(f.w & 0xFFFFu);
+      S.rec[i] = e0 | (e1 << 16) | (e2 << 32) | (e3 << 48);
+    } else {
+      S.adj[i] = (u8)((f.x != NONE32 ? 1u : 0u) | (f.y != NONE32 ? 2u : 0u) | (f.z != NONE32 ? 4u : 0u) | (f.w != NONE32 ? 8u : 0u));
+    }
+  }
+  __syncwarp();
+  u32* ev = P.ev + P.offs[0 * n1 + z];
+  uint2* gstack = P.stack + P.offs[1 * n1 + z];
+  ChainRec* chains = P.chain + P.offs[2 * n1 + z];
+  const u32 evCap = P.caps[(u64)z * 4 + 0], stackCap = P.caps[(u64)z * 4 + 1], chainCap = P.caps[(u64)z * 4 + 2];
+  const u32* nodeVertex = P.nodeVertex + nb;
+  u32 nev = 0, nch = 0, cursor = 0;
+  bool ok = true;
+  while (ok) {
+    // next_cluster: smallest node id >= cursor with an edge left (all earlier nodes are exhausted)
+    u32 start = NONE32;
+    for (u32 base = cursor; base < N; base += 32) {
+      const u32 i = base + lane;
+      const u32 m = __ballot_sync(FULL_MASK, i < N && S.has_edges(i));
+      if (m) { start = base + (__ffs(m) - 1); break; }
+    }
+    if (start == NONE32) break;
+    if (lane == 0) {
+      if (nch >= chainCap) { atomicExch(&P.scal[SC_ERROR], 3ull); ok = false; }
+      else {
+        u32 node = start, sp = 0, nB = 0;
+        const u32 begin = nev;
+        bool firstT = true, t2 = false, justPopped = false, firstIsB = false;
+        u32 t2f = 0, poppedB = 0, adjStart = nodeVertex[start];
+        for (;;) {
+          u64 w;
+          const u32 a = S.adjacency(node, w);
+          if (a == 0) {
+            // a 't': dead end after a move, or -- directly after a pop -- a spurious branch (remove_spurious_branches)
+            if (firstT) {
+              firstT = false;
+              if (nB == 1 && firstIsB) { t2 = true; t2f = nev - begin; adjStart = nodeVertex[node]; }   // remove_initial_branch applies
+            }
+            if (nev >= evCap) { atomicExch(&P.scal[SC_ERROR], 1ull); ok = false; break; }
+            if (justPopped && !(t2 && poppedB == begin)) { ev[poppedB] = (u32)EV_S << 30; ev[nev++] = (u32)EV_S << 30; }
+            else ev[nev++] = (u32)EV_T << 30;
+            if (sp == 0) break;
+            --sp;
+            const uint2 e = sp < REPLAY_STACK ? sstack[sp] : gstack[sp - REPLAY_STACK];
+            node = e.x;
+            poppedB = e.y;
+            justPopped = true;
+            continue;
+          }
+          justPopped = false;
+          if (nev + 2 > evCap) { atomicExch(&P.scal[SC_ERROR], 1ull); ok = false; break; }
+          if (a & (a - 1)) {                                  // popcount > 1: branch point
+            if (sp >= stackCap + REPLAY_STACK) { atomicExch(&P.scal[SC_ERROR], 2ull); ok = false; break; }
+            const uint2 e = make_uint2(node, nev);
+            if (sp < REPLAY_STACK) sstack[sp] = e; else gstack[sp - REPLAY_STACK] = e;
+            sp++;
+            if (nev == begin) firstIsB = true;
+            ev[nev++] = (u32)EV_B << 30;
+            nB++;
+          }
+          const u32 k = __ffs(a) - 1;                          // priority: right, left, down, up
+          const u32 e = S.take(node, k, w);
+          ev[nev++] = ((u32)EV_E << 30) | (node * 4 + k);
+          node = e >> 2;
+        }
+        ChainRec& rec = chains[nch];
+        rec.adjStart = adjStart;
+        rec.symBegin = begin;
+        rec.symEnd = nev;
+        rec.t2f = t2 ? t2f : 0;
+        nch++;
+      }
+    }
+    nev = __shfl_sync(FULL_MASK, nev, 0);
+    nch = __shfl_sync(FULL_MASK, nch, 0);
+    ok = __shfl_sync(FULL_MASK, (u32)ok, 0) != 0;
+    cursor = start;
+  }
+  if (lane == 0) { P.sliceInfo[(u64)z * 4 + 0] = nev; P.sliceInfo[(u64)z * 4 + 1] = nch; }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// 5. post-passes over the event list
 __device__ __forceinline__ u32 chain_of(const ChainRec* chains, u32 nch, u32 i) {
   u32 lo = 0, hi = nch;
   while (hi - lo > 1) { const u32 m = (lo + hi) >> 1; if (chains[m].symBegin <= i) lo = m; else hi = m; }
   return lo;
 }
-__device__ __forceinline__ u8 move_code(u8 s) { return s == 'u' ? 0 : s == 'r' ? 1 : s == 'd' ? 2 : 3; }   // crackcodes.hpp:20-26
 
-__global__ void __launch_bounds__(256) k_trace_post(TraceParams P) {
+__global__ void __launch_bounds__(256) k_event_post(TraceParams P) {
   __shared__ u32 sm[33];
   const Geom g = P.g;
   const u64 n1 = (u64)g.sz + 1;
   const u32 sxe = g.sx + 1;
   const int xw = ckl_byte_width(g.sx + 1), yw = ckl_byte_width(g.sy + 1);
   for (u32 z = blockIdx.x; z < g.sz; z += gridDim.x) {
-    const u8* sym = P.sym + P.offs[0 * n1 + z];
+    u32* ev = P.ev + P.offs[0 * n1 + z];
+    u32* pre = P.evCp + P.offs[0 * n1 + z] + z;            // one extra slot per slice
     ChainRec* chains = P.chain + P.offs[2 * n1 + z];
-    u8* cp = P.cp + P.offs[3 * n1 + z];
-    u32* pre = P.cpPrefix + P.offs[0 * n1 + z];
-    const u32 nsym = P.sliceInfo[(u64)z * 4 + 0], nch = P.sliceInfo[(u64)z * 4 + 1];
-    // (a) codepoints per symbol -> exclusive prefix
+    const u32* seLen = P.seLen + P.nodeBase[z] * 4;
+    const u32 nev = P.sliceInfo[(u64)z * 4 + 0], nch = P.sliceInfo[(u64)z * 4 + 1];
+    // (a) remove_initial_branch: the leading 'b' and the first 't' of the chain disappear
+    for (u32 c = threadIdx.x; c < nch; c += blockDim.x)
+      if (chains[c].t2f) { ev[chains[c].symBegin] = (u32)EV_S << 30; ev[chains[c].symBegin + chains[c].t2f] = (u32)EV_S << 30; }
+    __syncthreads();
+    // (b) codepoints per event -> exclusive prefix
     u32 carry = 0;
-    for (u32 i0 = 0; i0 < nsym; i0 += blockDim.x) {
+    for (u32 i0 = 0; i0 < nev; i0 += blockDim.x) {
       const u32 i = i0 + threadIdx.x;
       u32 cnt = 0;
-      if (i < nsym) {
-        const u8 e = eff_sym(sym, chains[chain_of(chains, nch, i)], i);
-        cnt = e == 's' ? 0 : (e == 'b' || e == 't') ? 2 : 1;
+      if (i < nev) {
+        const u32 e = ev[i], t = e >> 30;
+        cnt = t == EV_E ? seLen[e & 0x3FFFFFFFu] : (t == EV_S ? 0u : 2u);
       }
       u32 tot;
       const u32 ex = block_excl_scan(cnt, sm, tot);
-      if (i < nsym) pre[i] = carry + ex;
+      if (i < nev) pre[i] = carry + ex;
       carry += tot;
     }
-    if (threadIdx.x == 0) pre[nsym] = carry;
+    if (threadIdx.x == 0) pre[nev] = carry;
     __syncthreads();
     const u32 ncp = carry;
-    // (b) per-chain codepoint counts, (c) rank by adjusted start vertex (chains of a slice are vertex-disjoint)
+    // (c) per-chain codepoint counts, rank by adjusted start vertex (chains of a slice are vertex-disjoint)
     for (u32 c = threadIdx.x; c < nch; c += blockDim.x) chains[c].ncp = pre[chains[c].symEnd] - pre[chains[c].symBegin];
     for (u32 c = threadIdx.x; c < nch; c += blockDim.x) {
       const u32 a = chains[c].adjStart;
@@ -340,37 +517,6 @@ __global__ void __launch_bounds__(256) k_trace_post(TraceParams P) {
     }
     u32 nrows;
     block_excl_scan(nrows_part, sm, nrows);
-    // (e) absolute codepoints (symbols_to_codepoints), written at their final position
-    for (u32 i = threadIdx.x; i < nsym; i += blockDim.x) {
-      const ChainRec& c = chains[chain_of(chains, nch, i)];
-      const u8 e = eff_sym(sym, c, i);
-      if (e == 's') continue;
-      u8* o = cp + c.outBase + (pre[i] - pre[c.symBegin]);
-      if (e != 'b' && e != 't') { o[0] = move_code(e); continue; }
-      // previous kept symbol(s)
-      u32 j = i;
-      u8 p = 0;
-      u32 tcount = 0;            // kept 't' symbols between the previous move and this symbol
-      while (j > c.symBegin) {
-        j--;
-        const u8 q = eff_sym(sym, c, j);
-        if (q == 's') continue;
-        if (q == 't') { tcount++; continue; }
-        p = q;
-        break;
-      }
-      if (e == 'b') {
-        // (UP,DOWN) unless first symbol of the chain or the previous codepoint is DOWN -> (LEFT,RIGHT)
-        const bool alt = (i == c.symBegin) || (tcount == 0 && p == 'd');
-        o[0] = alt ? 3 : 0;
-        o[1] = alt ? 1 : 2;
-      } else {
-        // (DOWN,UP) unless the previous codepoint is UP -> (RIGHT,LEFT); consecutive 't's alternate
-        const bool alt = ((p == 'u') ? 1u : 0u) ^ (tcount & 1u);
-        o[0] = alt ? 1 : 2;
-        o[1] = alt ? 3 : 0;
-      }
-    }
     if (threadIdx.x == 0) {
       const u32 boc = 4 + yw + nrows * (yw + xw) + nch * xw;
       P.sliceInfo[(u64)z * 4 + 0] = ncp;
@@ -381,20 +527,118 @@ __global__ void __launch_bounds__(256) k_trace_post(TraceParams P) {
   }
 }
 
-static TraceParams make_params(const Geom& g, TraceBufs& T, ull* scal);
-void launch_trace_walk(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st) {
-  k_trace_walk<<<grid_cap(g.sz, 1, 16), 128, 0, st>>>(make_params(g, T, scal));
-  LAUNCH_CHECK();
+// 6. expansion: absolute codepoints (symbols_to_codepoints), written at their final position.
+// direction index -> codepoint: right 1, left 3, down 2, up 0  (crackcodes.hpp:20-26)
+__device__ __forceinline__ u8 dir_code(u32 kk) { return (u8)((0x0231u >> (4 * kk)) & 0xFu); }
+
+__global__ void __launch_bounds__(256) k_expand(TraceParams P, u64 totalEvCap) {
+  const Geom g = P.g;
+  const VGeom vg = P.vg;
+  const u64 n1 = (u64)g.sz + 1;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 gi = (u64)blockIdx.x * blockDim.x + threadIdx.x; gi < totalEvCap; gi += stride) {
+    const u32 z = slice_of(P.offs, g.sz, gi);
+    const u32 i = (u32)(gi - P.offs[z]);
+    // sliceInfo[0] holds ncp by now; the event count of the slice is the end of its last chain
+    const u32 nch = P.sliceInfo[(u64)z * 4 + 1];
+    if (!nch) continue;
+    const ChainRec* chains = P.chain + P.offs[2 * n1 + z];
+    if (i >= chains[nch - 1].symEnd) continue;
+    const u32* ev = P.ev + P.offs[z];
+    const u32 e = ev[i], t = e >> 30;
+    if (t == EV_S) continue;
+    const u32* pre = P.evCp + P.offs[z] + z;
+    const ChainRec& c = chains[chain_of(chains, nch, i)];
+    u8* out = P.cp + P.offs[3 * n1 + z] + c.outBase;
+    const u32 rel = pre[i] - pre[c.symBegin];
+    const u64 nb = P.nodeBase[z];
+    if (t == EV_E) {
+      const u32 slot = e & 0x3FFFFFFFu;
+      u32 kk = slot & 3u;
+      const u32 len = P.seLen[nb * 4 + slot];
+      const u32 v = P.nodeVertex[nb + (slot >> 2)];
+      u32 y = v / vg.sxe, x = v - y * vg.sxe;
+      const uint4* vw = P.VW + (u64)z * vg.sye * vg.Wv;
+      uint4 word;
+      if (c.t2f && i < c.symBegin + c.t2f) {
+        // inside a removed initial branch: the move run is reversed and every move flipped
+        const u32 fcp = pre[c.symBegin + c.t2f] - pre[c.symBegin];
+        u8* o = out + (fcp - 1 - rel);
+        for (u32 q = 0; q < len; q++) { *o-- = dir_code(kk ^ 1u); if (q + 1 < len) se_step(vw, vg.Wv, x, y, kk, word); }
+      } else {
+        u8* o = out + rel;
+        for (u32 q = 0; q < len; q++) { *o++ = dir_code(kk); if (q + 1 < len) se_step(vw, vg.Wv, x, y, kk, word); }
+      }
+      continue;
+    }
+    // 'b' / 't': the pair depends on the previous kept symbol; kept 't's in between alternate
+    u32 tcount = 0, j = i;
+    int prev = -1;                                        // previous kept move (direction index), -1 = none
+    while (j > c.symBegin) {
+      j--;
+      const u32 q = ev[j], qt = q >> 30;
+      if (qt == EV_S) continue;
+      if (qt == EV_T) { tcount++; continue; }
+      if (qt == EV_B) break;                              // cannot happen (a 'b' is always followed by a move)
+      if (c.t2f && j < c.symBegin + c.t2f) prev = (int)((ev[c.symBegin + 1] & 3u) ^ 1u);    // reversed run ends with flip(first move)
+      else prev = (int)((P.seFar[nb * 4 + (q & 0x3FFFFFFFu)] & 3u) ^ 1u);                   // last move = opposite of arrival dir
+      break;
+    }
+    u8* o = out + rel;
+    if (t == EV_B) {
+      // (UP,DOWN) unless first symbol of the chain or the previous codepoint is DOWN -> (LEFT,RIGHT)
+      const bool alt = (i == c.symBegin) || (tcount == 0 && prev == 2);
+      o[0] = alt ? 3 : 0;
+      o[1] = alt ? 1 : 2;
+    } else {
+      // (DOWN,UP) unless the previous codepoint is UP -> (RIGHT,LEFT); consecutive 't's alternate
+      const bool alt = ((prev == 3) ? 1u : 0u) ^ (tcount & 1u);
+      o[0] = alt ? 1 : 2;
+      o[1] = alt ? 3 : 0;
+    }
+  }
 }
-void launch_trace_post(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st) {
-  k_trace_post<<<grid_cap(g.sz, 1, 8), 256, 0, st>>>(make_params(g, T, scal));
+
+static TraceParams make_params(const Geom& g, TraceBufs& T, ull* scal);
+
+static u32 replay_smem_cap() {
+  // node records that fit beside the revisit stack in one SM's shared memory (u16 entries: node ids <= 16382)
+  return 16382u;
+}
+void launch_trace_walk(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes, u32 max_nodes, cudaStream_t st) {
+  TraceParams P = make_params(g, T, scal);
+  const VGeom vg = P.vg;
+  k_node_init<<<grid_cap(vg.wordsAll, 256, 8), 256, 0, st>>>(P);
   LAUNCH_CHECK();
+  if (!total_nodes) {
+    CUDA_CHECK(cudaMemsetAsync(T.sliceInfo.p, 0, (u64)g.sz * 16, st));
+    return;
+  }
+  k_path_walk<<<grid_cap(total_nodes * 4, 256, 8), 256, 0, st>>>(P, total_nodes * 4);
+  LAUNCH_CHECK();
+  const u32 cap = replay_smem_cap();
+  const u32 smem_nodes = max_nodes < cap ? max_nodes : cap;
+  P.smemNodeCap = cap;
+  const size_t smem = (size_t)REPLAY_STACK * 8 + (size_t)smem_nodes * 8;
+  if (smem > 48 * 1024)   // per device, cheap: set on every launch that needs it
+    CUDA_CHECK(cudaFuncSetAttribute(k_replay<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(REPLAY_STACK * 8 + (size_t)cap * 8)));
+  k_replay<true><<<g.sz, 32, smem, st>>>(P);
+  LAUNCH_CHECK();
+  if (max_nodes > cap) {
+    k_replay<false><<<g.sz, 32, REPLAY_STACK * 8, st>>>(P);
+    LAUNCH_CHECK();
+  }
+}
+void launch_trace_post(const Geom& g, TraceBufs& T, ull* scal, u64 total_ev_cap, cudaStream_t st) {
+  TraceParams P = make_params(g, T, scal);
+  k_event_post<<<grid_cap(g.sz, 1, 8), 256, 0, st>>>(P);
+  LAUNCH_CHECK();
+  if (total_ev_cap) {
+    k_expand<<<grid_cap(total_ev_cap, 256, 8), 256, 0, st>>>(P, total_ev_cap);
+    LAUNCH_CHECK();
+  }
   // total codepoints (for the "all slices empty" rule, crackle.hpp:107-118)
   launch_exscan_u32_u64(T.sliceInfo.as<u32>(), g.sz, 4, T.codeOff.as<u64>(), &scal[SC_CODEPOINTS], 0, st);
-}
-void launch_trace(const Geom& g, TraceBufs& T, ull* scal, cudaStream_t st) {
-  launch_trace_walk(g, T, scal, st);
-  launch_trace_post(g, T, scal, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -451,12 +695,16 @@ void launch_code_sizes_order0(const Geom& g, TraceBufs& T, ull* scal, cudaStream
 static TraceParams make_params(const Geom& g, TraceBufs& T, ull* scal) {
   TraceParams P;
   P.g = g;
-  P.EV = T.EV.as<u32>(); P.EH = T.EH.as<u32>();
+  P.vg = vgeom(g);
+  P.VW = T.VW.as<uint4>(); P.nodePrefix = T.nodePrefix.as<u32>(); P.rowBase = T.rowBase.as<u32>();
+  P.sliceNodes = T.sliceNodes.as<u32>(); P.nodeBase = T.nodeBase.as<u64>(); P.nodeVertex = T.nodeVertex.as<u32>();
+  P.seFar = T.seFar.as<u32>(); P.seLen = T.seLen.as<u32>(); P.nodeAdj = T.nodeAdj.as<u8>();
   P.offs = T.offs.as<u64>();
   P.caps = T.bounds.as<u32>() + (u64)g.sz * 4;
-  P.sym = T.sym.as<u8>(); P.stack = T.stack.as<uint2>(); P.chain = T.chain.as<ChainRec>();
-  P.cp = T.cp.as<u8>(); P.cpPrefix = T.cpPrefix.as<u32>(); P.sliceInfo = T.sliceInfo.as<u32>();
+  P.ev = T.ev.as<u32>(); P.evCp = T.evCp.as<u32>(); P.stack = T.stack.as<uint2>(); P.chain = T.chain.as<ChainRec>();
+  P.cp = T.cp.as<u8>(); P.sliceInfo = T.sliceInfo.as<u32>();
   P.scal = scal;
+  P.smemNodeCap = 0;
   return P;
 }
 
