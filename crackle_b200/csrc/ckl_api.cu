@@ -531,18 +531,21 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   API_BEGIN(c)
   cudaStream_t st = c->st;
   if (num_bytes < 29) throw CklError(CKL_ERR_STREAM, "crackle: Input too small to be a valid stream. Bytes: " + std::to_string(num_bytes));
-  // the small sections are parsed on the host
-  std::vector<u8> hostcopy;
-  const u8* hb = (const u8*)binary;
-  if (binary_on_device) {
-    hostcopy.resize(num_bytes);
-    CUDA_CHECK(cudaMemcpyAsync(hostcopy.data(), binary, num_bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    hb = hostcopy.data();
-  }
+  // the small sections are parsed on the host; a device-resident stream is read back piecewise (never as a whole)
+  std::vector<u8> buf_head, buf_z, buf_lab, buf_nz, buf_model;
+  auto fetch = [&](u64 offset, u64 n, std::vector<u8>& buf) -> const u8* {
+    if (!binary_on_device) return (const u8*)binary + offset;
+    buf.resize(n ? n : 1);
+    if (n) {
+      CUDA_CHECK(cudaMemcpyAsync(buf.data(), (const u8*)binary + offset, n, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    return buf.data();
+  };
+  const u8* hhead = fetch(0, 29, buf_head);
   ckl_header_info h;
   std::string perr;
-  int rc = parse_header(hb, num_bytes, &h, perr);
+  int rc = parse_header(hhead, num_bytes, &h, perr);
   if (rc) throw CklError(rc, perr);
   if (h.label_format != 0) throw CklError(CKL_ERR_UNSUPPORTED, "crackle_b200: pin label formats are outside the flat-label hot path; use the reference decoder");
   const i64 sz = (i64)h.sz;
@@ -561,9 +564,10 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   const u64 hbytes = h.format_version == 0 ? 24 : 29;
   const u64 zbytes = 4ull * (h.sz + (h.format_version == 0 ? 0 : 1));
   if (hbytes + zbytes > num_bytes) throw CklError(CKL_ERR_STREAM, "crackle: get_crack_code_offsets: Unable to read past end of buffer.");
+  const u8* hz = fetch(hbytes, zbytes, buf_z);                  // z index
   if (h.format_version > 0) {   // crackle.hpp:276-291
-    const u32 stored = (u32)le_host(hb + hbytes + 4ull * h.sz, 4);
-    const u32 computed = crc32c_host(c->htab, hb + hbytes, 4ull * h.sz);
+    const u32 stored = (u32)le_host(hz + 4ull * h.sz, 4);
+    const u32 computed = crc32c_host(c->htab, hz, 4ull * h.sz);
     if (stored != computed)
       throw CklError(CKL_ERR_STREAM, "crackle: grid index crc32c did not match. stored: " + std::to_string(stored) + " computed: " + std::to_string(computed));
   }
@@ -571,28 +575,29 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   const u64 mbytes = model_bytes_for(order);
   std::vector<u64> off((u64)sz + 1);
   off[0] = hbytes + zbytes + h.num_label_bytes + mbytes;
-  for (i64 z = 0; z < sz; z++) off[z + 1] = off[z] + le_host(hb + hbytes + 4ull * z, 4);
+  for (i64 z = 0; z < sz; z++) off[z + 1] = off[z] + le_host(hz + 4ull * z, 4);
   if (off[sz] > num_bytes) throw CklError(CKL_ERR_STREAM, "crackle: get_crack_codes: Unable to read past end of buffer.");
   if (h.format_version > 0 && off[sz] + 4 + 4ull * h.sz > num_bytes)
     throw CklError(CKL_ERR_STREAM, "crackle: get_crack_codes: Unable to read past end of buffer.");
   // labels section (labels.hpp:453-506)
   const u64 lab_off = hbytes + zbytes;
   if (h.num_label_bytes < 8) throw CklError(CKL_ERR_STREAM, "crackle: labels section too small.");
-  const u64 nu = le_host(hb + lab_off, 8);
+  const u64 nu = le_host(fetch(lab_off, 8, buf_lab), 8);
   const int sw = (int)h.stored_data_width, kw = ckl_byte_width(nu), cw = ckl_byte_width(sxy);
   const u64 uniq_off = lab_off + 8, nz_off = uniq_off + nu * (u64)sw, keys_off = nz_off + (u64)cw * h.sz;
   if (nu > h.num_label_bytes || keys_off > lab_off + h.num_label_bytes)
     throw CklError(CKL_ERR_STREAM, "crackle: labels section is inconsistent with the header.");
   const u64 n_keys = (lab_off + h.num_label_bytes - keys_off) / (u64)kw;
+  const u8* hnz = fetch(nz_off, (u64)cw * h.sz, buf_nz);       // components per slice
   std::vector<u64> keyBase(szr), stackOff(szr + 1), codeOff(szr + 1);
   {
     u64 kb = 0;
-    for (i64 z = 0; z < z_start; z++) kb += le_host(hb + nz_off + (u64)cw * z, cw);
+    for (i64 z = 0; z < z_start; z++) kb += le_host(hnz + (u64)cw * z, cw);
     stackOff[0] = 0;
     for (u64 i = 0; i < szr; i++) {
       const u64 z = (u64)z_start + i;
       keyBase[i] = kb;
-      kb += le_host(hb + nz_off + (u64)cw * z, cw);
+      kb += le_host(hnz + (u64)cw * z, cw);
       codeOff[i] = off[z];
       stackOff[i + 1] = stackOff[i] + 2 * (off[z + 1] - off[z]) + 4;
     }
@@ -601,7 +606,6 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   // markov model: symbol of rank per context row (markov.hpp:382-420)
   std::vector<u8> model;
   if (order > 0) {
-    static const u8 perm_init = 0; (void)perm_init;
     u8 lut[24]; int k = 0;
     for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) for (int cc = 0; cc < 4; cc++) for (int d = 0; d < 4; d++) {
       if (a == b || a == cc || a == d || b == cc || b == d || cc == d) continue;
@@ -609,7 +613,7 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
     }
     const u64 rows = 1ull << (2 * order);
     model.resize(rows * 4);
-    const u8* ms = hb + lab_off + h.num_label_bytes;
+    const u8* ms = fetch(lab_off + h.num_label_bytes, mbytes, buf_model);
     for (u64 r = 0; r < rows; r++) {
       const u64 bit = r * 5;
       u32 v = ms[bit >> 3];
@@ -630,7 +634,6 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   CUDA_CHECK(cudaMemcpyAsync(D.codeOff.p, codeOff.data(), (szr + 1) * 8, cudaMemcpyHostToDevice, st));
   CUDA_CHECK(cudaMemcpyAsync(D.keyBase.p, keyBase.data(), szr * 8, cudaMemcpyHostToDevice, st));
   CUDA_CHECK(cudaMemcpyAsync(D.stackOff.p, stackOff.data(), (szr + 1) * 8, cudaMemcpyHostToDevice, st));
-  D.stack.ensure(stackOff[szr] * 4 + 16);
   if (order > 0) {
     D.model.ensure(model.size());
     CUDA_CHECK(cudaMemcpyAsync(D.model.p, model.data(), model.size(), cudaMemcpyHostToDevice, st));
@@ -642,9 +645,40 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   CUDA_CHECK(cudaMemsetAsync(c->scal, 0, SC_COUNT * sizeof(ull), st));
   const ull none = ~0ull;
   CUDA_CHECK(cudaMemcpyAsync(&c->scal[SC_CRC_BAD], &none, 8, cudaMemcpyHostToDevice, st));
+  // per-slice word capacities for the scan-parallel decoder (from the code sizes; the descriptors are built on the device)
+  std::vector<u64> wordOff(szr + 1);
+  bool parallel_ok = true;
+  {
+    u64 tw = 0;
+    for (u64 i = 0; i < szr; i++) {
+      const u64 clen = codeOff[i + 1] - codeOff[i];
+      const u64 ncp_cap = order == 0 ? clen * 4 : clen * 8;
+      if (ncp_cap >= (1ull << 30)) parallel_ok = false;
+      wordOff[i] = tw;
+      tw += (ncp_cap + 15) / 16 + 1;
+    }
+    wordOff[szr] = tw;
+  }
+  const u64 total_words = wordOff[szr];
   c->prof.begin("decode_slices", st);
-  launch_decode_slices(g, dstream, D.codeOff.as<u64>(), (int)h.crack_format, order, D.model.as<u8>(), c->DV.as<u32>(), c->DH.as<u32>(),
-                       D.stack.as<u32>(), D.stackOff.as<u64>(), c->scal, st);
+  bool decoded = false;
+  if (parallel_ok) {
+    D.slices.ensure(szr * sizeof(DecSlice));
+    D.wordOff.ensure((szr + 1) * 8);
+    CUDA_CHECK(cudaMemcpyAsync(D.wordOff.p, wordOff.data(), (szr + 1) * 8, cudaMemcpyHostToDevice, st));
+    launch_decode_slices_init(g, dstream, D.codeOff.as<u64>(), D.wordOff.as<u64>(), D.slices.as<DecSlice>(), c->scal, st);
+    launch_decode_classify(g, dstream, order, D.model.as<u8>(), D, total_words, c->scal, st);
+    read_scalars(c);
+    if (!c->hscal[SC_FIRST]) {     // no opposite-move run longer than a word (never produced by the encoder)
+      launch_decode_mark(g, dstream, order, D, c->hscal[SC_LAST], c->DV.as<u32>(), c->DH.as<u32>(), c->scal, st);
+      decoded = true;
+    }
+  }
+  if (!decoded) {
+    D.stack.ensure(stackOff[szr] * 4 + 16);
+    launch_decode_slices(g, dstream, D.codeOff.as<u64>(), (int)h.crack_format, order, D.model.as<u8>(), c->DV.as<u32>(), c->DH.as<u32>(),
+                         D.stack.as<u32>(), D.stackOff.as<u64>(), c->scal, st);
+  }
   c->prof.end(st);
   launch_planes_from_cracks(g, (int)h.crack_format, c->DV.as<u32>(), c->DH.as<u32>(), st);
   STAGE(c, "ccl_count", launch_ccl_count(g, c->DV.as<u32>(), c->ccl, c->scal, st));
@@ -667,7 +701,8 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
       const u64 zi = c->hscal[SC_CRC_BAD];
       u32 computed = 0;
       CUDA_CHECK(cudaMemcpy(&computed, c->ccl.sliceCrc.as<u32>() + zi, 4, cudaMemcpyDeviceToHost));
-      const u32 stored = (u32)le_host(hb + num_bytes - 4ull * h.sz + 4ull * ((u64)z_start + zi), 4);
+      std::vector<u8> buf_crc;
+      const u32 stored = (u32)le_host(fetch(num_bytes - 4ull * h.sz + 4ull * ((u64)z_start + zi), 4, buf_crc), 4);
       throw CklError(CKL_ERR_STREAM, "crackle: crack code crc mismatch on z=" + std::to_string((u64)z_start + zi) + " computed: " +
                                          std::to_string(computed) + " stored: " + std::to_string(stored));
     }

@@ -210,12 +210,402 @@ __global__ void __launch_bounds__(32) k_decode_slices(Geom g, const u8* __restri
   if (s.bad) atomicExch(&scal[SC_ERROR], 11ull);
 }
 
+void launch_exscan_u32_u64(const u32* in, u32 n, u32 stride, u64* out, ull* total_out, u64 add_each, cudaStream_t st);
+
 void launch_decode_slices(const Geom& g, const u8* stream, const u64* codeOff, int permissible, int order, const u8* model,
                           u32* EV, u32* EH, u32* stack, const u64* stackOff, ull* scal, cudaStream_t st) {
   (void)permissible;
   CUDA_CHECK(cudaMemsetAsync(EV, 0, g.words() * 4, st));
   CUDA_CHECK(cudaMemsetAsync(EH, 0, g.words() * 4, st));
   k_decode_slices<<<g.sz, 32, 0, st>>>(g, stream, codeOff, order, model, EV, EH, stack, stackOff, scal);
+  LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Scan-parallel decoder (validated against the oracle by tools/proto_decode.py).
+//   k_dec_markov   order > 0 only: serial bit decoder per slice -> packed 2-bit difference fields
+//   k_dec_classify per 16-field word: absolute moves (prefix sum mod 4) and the second-of-escape-pair mask S
+//                  (S[i] = opp[i] & ~S[i-1], solved per 32-field window with an add-carry trick); counts events
+//   k_dec_compact  event list: codepoint index | move << 30
+//   k_dec_segsum   per segment (plain moves between two events; the codepoint before an event is the dropped
+//                  first-of-pair): displacement
+//   k_dec_chain    serial over EVENTS only (~4 % of the codepoints): BOC chain starts, revisit stack, positions
+//   k_dec_mark     per segment: walk the moves from the segment start and set the crack bits
+#define L5 0x55555555u
+__device__ __forceinline__ u32 add4(u32 a, u32 b) { return (a ^ b) ^ ((a & b & L5) << 1); }     // per 2-bit field, mod 4
+__device__ __forceinline__ u32 word_prefix4(u32 x) {
+  x = add4(x, x << 2); x = add4(x, x << 4); x = add4(x, x << 8); x = add4(x, x << 16);
+  return x;
+}
+// fields whose move is the opposite of the previous move (flag in the low bit of the field)
+__device__ __forceinline__ u32 opp_flags(u32 M, u32 prev_move) {
+  const u32 X = M ^ ((M << 2) | prev_move);
+  return (X >> 1) & ~X & L5;
+}
+
+// 32-bit word `wi` of a slice's field stream (zero past the end)
+__device__ __forceinline__ u32 dec_word(const DecSlice& d, const u8* __restrict__ stream, const u32* __restrict__ fields, int order, u64 wi) {
+  if (order > 0) return fields[d.wordOff + wi];
+  const u8* body = stream + d.body;
+  const u32 a = (u32)((u64)body & 3);
+  const u32* base = reinterpret_cast<const u32*>(body - a);
+  const u64 nb = (u64)d.blen;
+  if (wi * 4 >= nb) return 0u;
+  u32 lo = __ldg(base + wi), hi = 0;
+  if (a && (wi + 1) * 4 < a + nb) hi = __ldg(base + wi + 1);
+  u32 w = a ? __funnelshift_r(lo, hi, 8 * a) : lo;
+  const u64 rem = nb - wi * 4;
+  if (rem < 4) w &= (1u << (8 * (u32)rem)) - 1u;
+  return w;
+}
+
+// order > 0: markov::decode_codepoints (markov.hpp:268-323) -> difference fields, 16 per word
+__global__ void __launch_bounds__(32) k_dec_markov(const DecSlice* __restrict__ ds, u32 sz, const u8* __restrict__ stream, int order,
+                                                    const u8* __restrict__ model, u32* __restrict__ fields, u32* __restrict__ ncpOut) {
+  __shared__ u8 smodel[DECODE_SMEM_MODEL];
+  const u32 z = blockIdx.x;
+  const u32 mbytes = 4u << (2 * order);
+  const bool msm = mbytes <= DECODE_SMEM_MODEL;
+  if (msm) {
+    for (u32 i = threadIdx.x; i < mbytes; i += blockDim.x) smodel[i] = model[i];
+    __syncwarp();
+  }
+  if (threadIdx.x != 0 || z >= sz) return;
+  const DecSlice d = ds[z];
+  u32* out = fields + d.wordOff;
+  u64 n = 0;
+  if (d.blen) {
+    const u8* mdl = msm ? smodel : model;
+    BitReader br;
+    br.init(stream + d.body, d.blen);
+    const u32 top = 2 * (order - 1);
+    u32 acc = br.peek(2);          // first symbol: 2 raw bits (it is the absolute move; the running sum starts at 0)
+    br.skip(2);
+    u32 ctx = acc << top;
+    n = 1;
+    u64 pos = 2;
+    const u64 nbit = (u64)d.blen * 8;
+    while (pos < nbit) {
+      const u32 v = br.peek(3);
+      u32 rank, len;
+      if (!(v & 1)) { rank = 0; len = 1; } else if (!(v & 2)) { rank = 1; len = 2; } else if (!(v & 4)) { rank = 2; len = 3; } else { rank = 3; len = 3; }
+      const u32 dsym = mdl[(u64)ctx * 4 + rank];
+      br.skip(len);
+      pos += len;
+      ctx = (ctx >> 2) + (dsym << top);
+      acc |= dsym << (2 * (u32)(n & 15));
+      n++;
+      if ((n & 15) == 0) { out[(n >> 4) - 1] = acc; acc = 0; }
+    }
+    if (n & 15) out[n >> 4] = acc;
+  }
+  ncpOut[z] = (u32)n;
+}
+
+__global__ void __launch_bounds__(256) k_dec_classify(const DecSlice* __restrict__ ds, u32 sz, const u8* __restrict__ stream,
+                                                       const u32* __restrict__ fields, int order, const u32* __restrict__ ncpIn,
+                                                       u32* __restrict__ Mw, u32* __restrict__ Sw, u32* __restrict__ nevOut, ull* scal) {
+  __shared__ u32 sm[33];
+  for (u32 z = blockIdx.x; z < sz; z += gridDim.x) {
+    const DecSlice d = ds[z];
+    const u64 ncp = order > 0 ? (u64)ncpIn[z] : (u64)d.blen * 4;
+    const u64 nwords = (ncp + 15) / 16;
+    u32 carry = 0, count = 0;
+    for (u64 w0 = 0; w0 < nwords; w0 += blockDim.x) {
+      const u64 wi = w0 + threadIdx.x;
+      const bool in = wi < nwords;
+      const u32 w = in ? dec_word(d, stream, fields, order, wi) : 0u;
+      const u32 incl = word_prefix4(w);
+      u32 tot;
+      const u32 ex = block_excl_scan(incl >> 30, sm, tot);
+      const u32 e = (carry + ex) & 3u;                        // absolute move of the codepoint before this word
+      carry = (carry + tot) & 3u;
+      if (!in) continue;
+      const u32 M = add4(incl, e * L5);
+      u32 Oc = opp_flags(M, e);
+      if (wi == 0) Oc &= ~1u;                                 // the first codepoint has no predecessor
+      const u64 rem = ncp - wi * 16;
+      if (rem < 16) Oc &= (1u << (2 * (u32)rem)) - 1u;
+      u32 Op = 0;
+      if (wi > 0) {
+        const u32 inclp = word_prefix4(dec_word(d, stream, fields, order, wi - 1));
+        const u32 ep = (e - (inclp >> 30)) & 3u;
+        Op = opp_flags(add4(inclp, ep * L5), ep);
+        if (wi == 1) Op &= ~1u;
+      }
+      if (Op == L5 && (Oc & 1u)) atomicExch(&scal[SC_FIRST], 1ull);    // an opposite-run longer than a word: serial fallback
+      // second-of-pair mask: positions at even distance from the start of their run of `opp` flags
+      u64 comb = (u64)Op | ((u64)Oc << 32);
+      comb |= comb << 1;
+      const u64 st = comb & ~(comb << 2) & 0x5555555555555555ull;
+      const u64 t = comb + (st & 0x1111111111111111ull);
+      const u64 evr = comb & ~t, odr = comb & ~evr;
+      const u32 S = (u32)(((evr & 0x3333333333333333ull) | (odr & 0xCCCCCCCCCCCCCCCCull)) >> 32) & L5;
+      Mw[d.wordOff + wi] = M;
+      Sw[d.wordOff + wi] = S;
+      count += __popc(S);
+    }
+    u32 total;
+    block_excl_scan(count, sm, total);
+    if (threadIdx.x == 0) nevOut[z] = total;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_dec_compact(const DecSlice* __restrict__ ds, u32 sz, int order, const u32* __restrict__ ncpIn,
+                                                      const u32* __restrict__ Mw, const u32* __restrict__ Sw,
+                                                      const u64* __restrict__ evOff, u32* __restrict__ evIdx) {
+  __shared__ u32 sm[33];
+  for (u32 z = blockIdx.x; z < sz; z += gridDim.x) {
+    const DecSlice d = ds[z];
+    const u64 ncp = order > 0 ? (u64)ncpIn[z] : (u64)d.blen * 4;
+    const u64 nwords = (ncp + 15) / 16;
+    u32* out = evIdx + evOff[z];
+    u32 carry = 0;
+    for (u64 w0 = 0; w0 < nwords; w0 += blockDim.x) {
+      const u64 wi = w0 + threadIdx.x;
+      u32 S = wi < nwords ? Sw[d.wordOff + wi] : 0u;
+      u32 tot;
+      u32 o = carry + block_excl_scan(__popc(S), sm, tot);
+      carry += tot;
+      if (S) {
+        const u32 M = Mw[d.wordOff + wi];
+        while (S) {
+          const u32 b = __ffs(S) - 1;                         // even bit position = 2 * field
+          S &= S - 1;
+          out[o++] = (u32)(wi * 16 + (b >> 1)) | (((M >> b) & 3u) << 30);
+        }
+      }
+    }
+  }
+}
+
+// displacement of the plain moves in codepoints [lo, hi) of a slice (moves: 0 up, 1 right, 2 down, 3 left)
+__device__ __forceinline__ void seg_sum(const u32* __restrict__ Mz, u32 lo, u32 hi, int& dx, int& dy) {
+  dx = 0; dy = 0;
+  if (lo >= hi) return;
+  for (u32 w = lo >> 4; w <= (hi - 1) >> 4; w++) {
+    const u32 M = Mz[w];
+    const u32 f0 = w == (lo >> 4) ? (lo & 15) : 0, f1 = w == ((hi - 1) >> 4) ? ((hi - 1) & 15) + 1 : 16;
+    u32 rm = L5;
+    rm &= ~((1u << (2 * f0)) - 1u);
+    if (f1 < 16) rm &= (1u << (2 * f1)) - 1u;
+    const u32 b0 = M & L5, b1 = (M >> 1) & L5;
+    dx += __popc(b0 & ~b1 & rm) - __popc(b0 & b1 & rm);
+    dy += __popc(b1 & ~b0 & rm) - __popc(~b0 & ~b1 & rm);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_dec_segsum(const DecSlice* __restrict__ ds, u32 sz, const u32* __restrict__ Mw,
+                                                     const u64* __restrict__ evOff, const u32* __restrict__ evIdx, u64 totalEv,
+                                                     int2* __restrict__ evSum) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < totalEv; j += stride) {
+    u32 lo = 0, hi = sz;
+    while (hi - lo > 1) { const u32 m = (lo + hi) >> 1; if (evOff[m] <= j) lo = m; else hi = m; }
+    const u32 z = lo;
+    const u32 first = j == evOff[z] ? 0u : (evIdx[j - 1] & 0x3FFFFFFFu) + 1;
+    const u32 ei = evIdx[j] & 0x3FFFFFFFu;
+    int dx, dy;
+    seg_sum(Mw + ds[z].wordOff, first, ei ? ei - 1 : 0, dx, dy);
+    evSum[j] = make_int2(dx, dy);
+  }
+}
+
+#define DEC_STACK 512
+__global__ void __launch_bounds__(32) k_dec_chain(Geom g, const DecSlice* __restrict__ ds, const u8* __restrict__ stream,
+                                                   const u64* __restrict__ evOff, const u32* __restrict__ evIdx,
+                                                   const int2* __restrict__ evSum, int2* __restrict__ segStart, int2* __restrict__ gstack,
+                                                   u32* __restrict__ nevUsed, ull* scal) {
+  __shared__ int2 sstack[DEC_STACK];
+  __shared__ u32 s_ev[32];
+  __shared__ int2 s_sum[32], s_start[32];
+  __shared__ u32 s_used;
+  const u32 z = blockIdx.x, lane = threadIdx.x;
+  const DecSlice d = ds[z];
+  const u64 e0 = evOff[z];
+  const u32 nev = (u32)(evOff[z + 1] - e0);
+  const int xw = ckl_byte_width((u64)g.sx + 1), yw = ckl_byte_width((u64)g.sy + 1);
+  // lane 0 state
+  BocIter it;
+  int x = 0, y = 0;
+  u32 open = 0, sp = 0, used = nev;
+  bool stop = false;
+  if (lane == 0) {
+    const u8* code = stream + d.code;
+    it.p = code; it.idx = 4; it.end = d.isz; it.xw = xw; it.yw = yw; it.sxe = g.sx + 1;
+    it.ny = d.isz >= (u32)(4 + yw) ? (u32)ld_le(code + 4, yw) : 0u; it.idx += yw; it.yi = 0; it.nx = 0; it.y = 0; it.x = 0;
+    s_used = nev;
+  }
+  int2* gst = gstack + e0;
+  for (u32 base = 0; base < nev; base += 32) {
+    const u32 j = base + lane;
+    if (j < nev) { s_ev[lane] = evIdx[e0 + j]; s_sum[lane] = evSum[e0 + j]; }
+    __syncwarp();
+    if (lane == 0 && !stop) {
+      const u32 n = min(32u, nev - base);
+      for (u32 k = 0; k < n; k++) {
+        if (open == 0) {                                 // next chain: start vertex from the BOC index
+          u32 vx, vy;
+          if (!it.next(vx, vy)) { used = base + k; stop = true; break; }
+          if (vx > g.sx || vy > g.sy) { atomicExch(&scal[SC_ERROR], 11ull); used = base + k; stop = true; break; }
+          x = (int)vx; y = (int)vy; sp = 0; open = 1;
+        }
+        s_start[k] = make_int2(x, y);
+        x += s_sum[k].x; y += s_sum[k].y;
+        const u32 m = s_ev[k] >> 30;
+        if (m == 0 || m == 3) {                           // 't'
+          open--;
+          if (sp > 0) { --sp; const int2 q = sp < DEC_STACK ? sstack[sp] : gst[sp - DEC_STACK]; x = q.x; y = q.y; }
+        } else {                                          // 'b': reference quirk -- pushed as x + sx*y (crackcodes.hpp:772,850)
+          open++;
+          const int2 q = x == (int)g.sx ? make_int2(0, y + 1) : make_int2(x, y);
+          if (sp < DEC_STACK) sstack[sp] = q; else gst[sp - DEC_STACK] = q;
+          sp++;
+        }
+      }
+      if (stop) s_used = used;
+    }
+    __syncwarp();
+    if (j < nev && j < s_used) segStart[e0 + j] = s_start[lane];
+    __syncwarp();
+  }
+  if (lane == 0) nevUsed[z] = s_used;
+}
+
+__global__ void __launch_bounds__(256) k_dec_mark(Geom g, const DecSlice* __restrict__ ds, u32 sz, const u32* __restrict__ Mw,
+                                                   const u64* __restrict__ evOff, const u32* __restrict__ evIdx,
+                                                   const int2* __restrict__ segStart, const u32* __restrict__ nevUsed, u64 totalEv,
+                                                   u32* __restrict__ EVall, u32* __restrict__ EHall, ull* scal) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 nw = (u64)g.sy * g.W;
+  const int sx = (int)g.sx, sy = (int)g.sy;
+  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < totalEv; j += stride) {
+    u32 lo = 0, hi = sz;
+    while (hi - lo > 1) { const u32 m = (lo + hi) >> 1; if (evOff[m] <= j) lo = m; else hi = m; }
+    const u32 z = lo;
+    if (j - evOff[z] >= nevUsed[z]) continue;
+    const u32 first = j == evOff[z] ? 0u : (evIdx[j - 1] & 0x3FFFFFFFu) + 1;
+    const u32 ei = evIdx[j] & 0x3FFFFFFFu;
+    const u32 last = ei ? ei - 1 : 0;                       // exclusive: codepoint ei-1 is the dropped first-of-pair
+    if (first >= last) continue;
+    const u32* Mz = Mw + ds[z].wordOff;
+    u32* EV = EVall + (u64)z * nw;
+    u32* EH = EHall + (u64)z * nw;
+    int2 p = segStart[j];
+    int x = p.x, y = p.y;
+    bool bad = x < 0 || y < 0 || x > sx || y > sy;
+    u32* pend = nullptr;
+    u32 pmask = 0;
+    u32 M = Mz[first >> 4];
+    for (u32 i = first; i < last && !bad; i++) {
+      if ((i & 15) == 0) M = Mz[i >> 4];
+      const u32 m = (M >> (2 * (i & 15))) & 3u;
+      u32* a = nullptr;
+      u32 bit = 0;
+      if (m == 0) {          // up: vertical crack at column x, row y-1
+        if (y == 0) { bad = true; break; }
+        if (x > 0 && x < sx) { a = EV + (u64)(y - 1) * g.W + (x >> 5); bit = 1u << (x & 31); }
+        y--;
+      } else if (m == 2) {   // down: vertical crack at column x, row y
+        if (y >= sy) { bad = true; break; }
+        if (x > 0 && x < sx) { a = EV + (u64)y * g.W + (x >> 5); bit = 1u << (x & 31); }
+        y++;
+      } else if (m == 3) {   // left: horizontal crack above pixel (x-1, y)
+        if (x == 0) { bad = true; break; }
+        if (y > 0 && y < sy) { a = EH + (u64)y * g.W + ((x - 1) >> 5); bit = 1u << ((x - 1) & 31); }
+        x--;
+      } else {               // right: horizontal crack above pixel (x, y)
+        if (x >= sx) { bad = true; break; }
+        if (y > 0 && y < sy) { a = EH + (u64)y * g.W + (x >> 5); bit = 1u << (x & 31); }
+        x++;
+      }
+      if (a) {
+        if (a != pend) { if (pend) atomicOr(pend, pmask); pend = a; pmask = 0; }
+        pmask |= bit;
+      }
+    }
+    if (pend) atomicOr(pend, pmask);
+    if (bad) atomicExch(&scal[SC_ERROR], 11ull);
+  }
+}
+
+static u32 dec_grid(u64 n, u32 bs, u32 per_sm) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  u64 b = (n + bs - 1) / bs;
+  if (b < 1) b = 1;
+  const u64 cap = (u64)sms * per_sm;
+  return (u32)(b < cap ? b : cap);
+}
+
+// per-slice descriptors from the code offsets: index size read from the stream (crackcodes.hpp:283-316)
+__global__ void k_dec_slices_init(Geom g, const u8* __restrict__ stream, const u64* __restrict__ codeOff, const u64* __restrict__ wordOff,
+                                  DecSlice* __restrict__ out, ull* scal) {
+  const u32 z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= g.sz) return;
+  const u64 yw = (u64)ckl_byte_width((u64)g.sy + 1);
+  DecSlice d;
+  d.code = codeOff[z];
+  d.wordOff = wordOff[z];
+  const u64 clen = codeOff[z + 1] - codeOff[z];
+  d.isz = 0; d.body = d.code; d.blen = 0;
+  if (clen >= 4 + yw) {
+    const u64 isz = 4 + ld_le(stream + d.code, 4);
+    if (isz > clen) atomicExch(&scal[SC_ERROR], 10ull);
+    else { d.isz = (u32)isz; d.body = d.code + isz; d.blen = (u32)(clen - isz); }
+  }
+  out[z] = d;
+}
+void launch_decode_slices_init(const Geom& g, const u8* stream, const u64* codeOff, const u64* wordOff, DecSlice* out, ull* scal,
+                               cudaStream_t st) {
+  k_dec_slices_init<<<(g.sz + 127) / 128, 128, 0, st>>>(g, stream, codeOff, wordOff, out, scal);
+  LAUNCH_CHECK();
+}
+
+// phase 1: moves + event masks + per-slice event counts (exclusive scan into D.evOff, total in scal[SC_LAST])
+void launch_decode_classify(const Geom& g, const u8* stream, int order, const u8* model, DecodeBufs& D, u64 total_words, ull* scal,
+                            cudaStream_t st) {
+  D.Mw.ensure(total_words * 4 + 16);
+  D.Sw.ensure(total_words * 4 + 16);
+  D.nev.ensure((u64)g.sz * 4);
+  D.ncp.ensure((u64)g.sz * 4);
+  D.evOff.ensure(((u64)g.sz + 1) * 8);
+  D.nevUsed.ensure((u64)g.sz * 4);
+  const DecSlice* ds = D.slices.as<DecSlice>();
+  if (order > 0) {
+    D.fields.ensure(total_words * 4 + 16);
+    k_dec_markov<<<g.sz, 32, 0, st>>>(ds, g.sz, stream, order, model, D.fields.as<u32>(), D.ncp.as<u32>());
+    LAUNCH_CHECK();
+  }
+  k_dec_classify<<<dec_grid(g.sz, 1, 8), 256, 0, st>>>(ds, g.sz, stream, D.fields.as<u32>(), order, D.ncp.as<u32>(), D.Mw.as<u32>(),
+                                                       D.Sw.as<u32>(), D.nev.as<u32>(), scal);
+  LAUNCH_CHECK();
+  launch_exscan_u32_u64(D.nev.as<u32>(), g.sz, 1, D.evOff.as<u64>(), &scal[SC_LAST], 0, st);
+}
+
+// phase 2 (total_events known on the host): event list, segment sums, chain pass, marking
+void launch_decode_mark(const Geom& g, const u8* stream, int order, DecodeBufs& D, u64 total_events, u32* EV, u32* EH, ull* scal,
+                        cudaStream_t st) {
+  CUDA_CHECK(cudaMemsetAsync(EV, 0, g.words() * 4, st));
+  CUDA_CHECK(cudaMemsetAsync(EH, 0, g.words() * 4, st));
+  if (!total_events) return;
+  D.evIdx.ensure(total_events * 4 + 16);
+  D.evSum.ensure(total_events * 8 + 16);
+  D.segStart.ensure(total_events * 8 + 16);
+  D.gstack.ensure(total_events * 8 + 16);
+  const DecSlice* ds = D.slices.as<DecSlice>();
+  k_dec_compact<<<dec_grid(g.sz, 1, 8), 256, 0, st>>>(ds, g.sz, order, D.ncp.as<u32>(), D.Mw.as<u32>(), D.Sw.as<u32>(), D.evOff.as<u64>(),
+                                                      D.evIdx.as<u32>());
+  LAUNCH_CHECK();
+  k_dec_segsum<<<dec_grid(total_events, 256, 8), 256, 0, st>>>(ds, g.sz, D.Mw.as<u32>(), D.evOff.as<u64>(), D.evIdx.as<u32>(), total_events,
+                                                               D.evSum.as<int2>());
+  LAUNCH_CHECK();
+  k_dec_chain<<<g.sz, 32, 0, st>>>(g, ds, stream, D.evOff.as<u64>(), D.evIdx.as<u32>(), D.evSum.as<int2>(), D.segStart.as<int2>(),
+                                   D.gstack.as<int2>(), D.nevUsed.as<u32>(), scal);
+  LAUNCH_CHECK();
+  k_dec_mark<<<dec_grid(total_events, 256, 8), 256, 0, st>>>(g, ds, g.sz, D.Mw.as<u32>(), D.evOff.as<u64>(), D.evIdx.as<u32>(),
+                                                             D.segStart.as<int2>(), D.nevUsed.as<u32>(), total_events, EV, EH, scal);
   LAUNCH_CHECK();
 }
 
