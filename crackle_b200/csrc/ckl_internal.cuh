@@ -22,6 +22,7 @@ struct CclBufs {
   DBuf parent, runStart, compRank, runComp;                // per run (allocated once the run total is known)
   DBuf nz, compBase, compPix;                              // per slice / per component
   DBuf sliceCrc;                                           // raw CRC accumulators, per slice
+  DBuf crcH, crcHl; u64 crcHn = 0;                         // H[m] = sum_{j=1..m} x^(32j) mod P for m <= sxy (built once)
 };
 
 void launch_edges(const void* labels, int width, const Geom& g, u32* DV, u32* DH, ull* scal, cudaStream_t st);

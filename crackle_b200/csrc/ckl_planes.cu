@@ -219,7 +219,7 @@ __device__ __forceinline__ u32 mask_le(u32 b) { return (2u << b) - 1u; }   // bi
 
 __global__ void __launch_bounds__(256) k_run_init(Geom g, const u32* __restrict__ DV, const u32* __restrict__ wordPrefix,
                                                    const u32* __restrict__ rowBase, const u64* __restrict__ runBase,
-                                                   u32* __restrict__ parent, u32* __restrict__ runStart) {
+                                                   u32* __restrict__ runStart) {
   const u64 nwords = g.words(), stride = (u64)gridDim.x * blockDim.x;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) {
     const u64 row = i / g.W;
@@ -233,33 +233,100 @@ __global__ void __launch_bounds__(256) k_run_init(Geom g, const u32* __restrict_
       const u32 b = __ffs(starts) - 1;
       starts &= starts - 1;
       const u32 rid = rb + __popc(dv & mask_le(b));
-      parent[gb + rid] = rid;
       runStart[gb + rid] = y * g.sx + w * 32 + b;
     }
   }
 }
 
-__global__ void __launch_bounds__(256) k_run_union(Geom g, const u32* __restrict__ DV, const u32* __restrict__ DH,
-                                                    const u32* __restrict__ wordPrefix, const u32* __restrict__ rowBase,
-                                                    const u64* __restrict__ runBase, u32* parent) {
-  const u64 nwords = g.words(), stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) {
-    const u64 row = i / g.W;
-    const u32 w = (u32)(i - row * g.W);
-    const u32 z = (u32)(row / g.sy), y = (u32)(row - (u64)z * g.sy);
-    if (y == 0) continue;
-    const u32 valid = (w == g.W - 1 && (g.sx & 31)) ? ((1u << (g.sx & 31)) - 1u) : 0xFFFFFFFFu;
-    const u32 dv = DV[i], dvu = DV[i - g.W];
-    const u32 conn = ~DH[i] & valid;                       // pixel connected to the pixel above
-    u32 cand = conn & (dv | dvu | ~(conn << 1));           // first pixel of every (run, upper run, group) overlap
-    if (!cand) continue;
-    const u32 rb = rowBase[row] + wordPrefix[i], rbu = rowBase[row - 1] + wordPrefix[i - g.W];
-    u32* par = parent + runBase[z];
-    while (cand) {
-      const u32 b = __ffs(cand) - 1;
-      cand &= cand - 1;
-      uf_unite(par, rb + __popc(dv & mask_le(b)), rbu + __popc(dvu & mask_le(b)));
+// union-find with "smaller id wins" on a parent array that may live in shared memory; finds compress paths
+// (atomicMin keeps parents monotonically decreasing, so concurrent compression never loses a link)
+__device__ __forceinline__ u32 ufc_find(volatile u32* par, u32 a) {
+  u32 p = par[a];
+  while (p != a) {
+    const u32 gp = par[p];
+    if (gp != p) atomicMin((u32*)par + a, gp);
+    a = p; p = gp;
+  }
+  return a;
+}
+__device__ __forceinline__ void ufc_unite(volatile u32* par, u32 a, u32 b) {
+  for (;;) {
+    a = ufc_find(par, a);
+    b = ufc_find(par, b);
+    if (a == b) return;
+    if (a < b) { const u32 t = a; a = b; b = t; }   // a > b: hang a under b
+    const u32 old = atomicMin((u32*)par + a, b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+// unions between row `y` (y >= 1) and the row above, for the 32-pixel word `i` = (row, w); run ids relative to `base`
+__device__ __forceinline__ void unite_word(const Geom& g, const u32* __restrict__ DV, const u32* __restrict__ DH,
+                                           const u32* __restrict__ wordPrefix, const u32* __restrict__ rowBase, u64 row, u32 w,
+                                           volatile u32* par, u32 base) {
+  const u64 i = row * g.W + w;
+  const u32 valid = (w == g.W - 1 && (g.sx & 31)) ? ((1u << (g.sx & 31)) - 1u) : 0xFFFFFFFFu;
+  const u32 dv = DV[i], dvu = DV[i - g.W];
+  const u32 conn = ~DH[i] & valid;                       // pixel connected to the pixel above
+  u32 cand = conn & (dv | dvu | ~(conn << 1));           // first pixel of every (run, upper run, group) overlap
+  if (!cand) return;
+  const u32 rb = rowBase[row] + wordPrefix[i] - base, rbu = rowBase[row - 1] + wordPrefix[i - g.W] - base;
+  while (cand) {
+    const u32 b = __ffs(cand) - 1;
+    cand &= cand - 1;
+    ufc_unite(par, rb + __popc(dv & mask_le(b)), rbu + __popc(dvu & mask_le(b)));
+  }
+}
+
+// Band pass: one block owns CCL_BAND rows of one slice and solves them in shared memory (global memory when the
+// band has too many runs); the band's trees are flattened and written out with slice-local run ids.
+#define CCL_BAND 64
+#define CCL_SMEM_RUNS 12288
+__global__ void __launch_bounds__(256) k_band_ccl(Geom g, u32 nbands, const u32* __restrict__ DV, const u32* __restrict__ DH,
+                                                   const u32* __restrict__ wordPrefix, const u32* __restrict__ rowBase,
+                                                   const u32* __restrict__ sliceRuns, const u64* __restrict__ runBase, u32* parent) {
+  __shared__ u32 spar[CCL_SMEM_RUNS];
+  const u64 nitems = (u64)g.sz * nbands;
+  for (u64 item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const u32 z = (u32)(item / nbands), band = (u32)(item - (u64)z * nbands);
+    const u32 y0 = band * CCL_BAND, y1 = min(g.sy, y0 + CCL_BAND);
+    const u64 row0 = (u64)z * g.sy + y0;
+    const u32 base = rowBase[row0];
+    const u32 end = y1 < g.sy ? rowBase[row0 + (y1 - y0)] : sliceRuns[z];
+    const u32 n = end - base;
+    u32* gpar = parent + runBase[z] + base;
+    const bool sm = n <= CCL_SMEM_RUNS;
+    volatile u32* par = sm ? spar : gpar;
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) par[i] = i;
+    __syncthreads();
+    const u32 nw = (y1 - y0 - 1) * g.W;                  // words of rows y0+1 .. y1-1
+    for (u32 k = threadIdx.x; k < nw; k += blockDim.x) {
+      const u32 r = k / g.W, w = k - r * g.W;
+      unite_word(g, DV, DH, wordPrefix, rowBase, row0 + 1 + r, w, par, base);
     }
+    __syncthreads();
+    if (sm) {
+      for (u32 i = threadIdx.x; i < n; i += blockDim.x) gpar[i] = base + ufc_find(par, i);
+    } else {
+      for (u32 i = threadIdx.x; i < n; i += blockDim.x) { const u32 r = ufc_find(par, i); par[i] = r; }
+      __syncthreads();
+      for (u32 i = threadIdx.x; i < n; i += blockDim.x) par[i] += base;
+    }
+    __syncthreads();
+  }
+}
+
+// Border pass: unions across band boundaries, in global memory on the flattened band trees
+__global__ void __launch_bounds__(256) k_border_union(Geom g, u32 nbands, const u32* __restrict__ DV, const u32* __restrict__ DH,
+                                                       const u32* __restrict__ wordPrefix, const u32* __restrict__ rowBase,
+                                                       const u64* __restrict__ runBase, u32* parent) {
+  const u64 nitems = (u64)g.sz * (nbands - 1) * g.W, stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nitems; i += stride) {
+    const u32 w = (u32)(i % g.W);
+    const u64 t = i / g.W;
+    const u32 band = (u32)(t % (nbands - 1)) + 1, z = (u32)(t / (nbands - 1));
+    unite_word(g, DV, DH, wordPrefix, rowBase, (u64)z * g.sy + (u64)band * CCL_BAND, w, parent + runBase[z], 0);
   }
 }
 
@@ -302,51 +369,89 @@ __global__ void __launch_bounds__(256) k_run_resolve(Geom g, u64 total_runs, con
   }
 }
 
-// CRC-32C of the virtual uint32 image cc[x,y] = runComp[run(x,y)], one thread per 32-pixel word, combined with
-// x^(32 * pixels_after) so the per-slice accumulator is the raw register of the whole image.
-__global__ void __launch_bounds__(256) k_cc_crc(Geom g, const u32* __restrict__ DV, const u32* __restrict__ wordPrefix,
-                                                 const u32* __restrict__ rowBase, const u64* __restrict__ runBase,
-                                                 const u32* __restrict__ runComp, const CrcTables* __restrict__ tabs,
-                                                 u32* sliceCrc) {
-  __shared__ u32 t[4][256];
-  __shared__ u32 pw[4][256];
-  for (u32 i = threadIdx.x; i < 1024; i += blockDim.x) {
-    (&t[0][0])[i] = (&tabs->t[0][0])[i];
-    (&pw[0][0])[i] = (&tabs->pw[0][0])[i];
-  }
-  __syncthreads();
-  const u64 nwords = g.words(), stride = (u64)gridDim.x * blockDim.x;
-  const u64 nloop = (nwords + stride - 1) / stride;
-  for (u64 k = 0; k < nloop; k++) {
-    const u64 i = k * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u32 crc = 0, z = 0xFFFFFFFFu;
-    if (i < nwords) {
-      const u64 row = i / g.W;
-      const u32 w = (u32)(i - row * g.W);
-      z = (u32)(row / g.sy);
-      const u32 y = (u32)(row - (u64)z * g.sy);
-      const u32 dv = DV[i];
-      const u32 npx = min(32u, g.sx - w * 32);
-      const u32* rc = runComp + runBase[z];
-      u32 rid = rowBase[row] + wordPrefix[i] + (dv & 1u);
-      u32 comp = rc[rid];
-      crc = crc_word(t, 0, comp);
-      for (u32 b = 1; b < npx; b++) {
-        if ((dv >> b) & 1u) { rid++; comp = rc[rid]; }
-        crc = crc_word(t, crc, comp);
-      }
-      const u32 after = (u32)(g.sxy - ((u64)y * g.sx + (u64)w * 32 + npx));
-      if (after) crc = gf_mul(crc, gf_xpow32(pw, after));
+// CRC-32C of the virtual uint32 image cc[pixel] = runComp[run(pixel)].  The image is constant along runs and runs
+// tile the slice in raster order, so with d_r = comp[r] ^ comp[r-1] placed at the run start and extending to the
+// end of the image (GF(2)-linearity of the raw CRC):  raw = XOR_r  d_r(x) * H[sxy - start_r],
+// H[m] = sum_{j=1..m} x^(32 j) mod P  (table built once per context).  One short GF(2) multiply per RUN.
+__device__ __forceinline__ u32 gf_mul_id(u32 d, u32 h, const u32* t0) {
+  if (d < 65536u) {
+    h = t0[h & 0xFF] ^ (h >> 8);                          // * x^8
+    h = t0[h & 0xFF] ^ (h >> 8);                          // * x^16: the 16 low bits of d are x^16 .. x^31
+    u32 p = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      p ^= h & (0u - ((d >> (15 - j)) & 1u));
+      h = (h >> 1) ^ (CKL_CRC_POLY & (0u - (h & 1u)));
     }
-    // warp aggregation when every lane is in the same slice
+    return p;
+  }
+  return gf_mul(d, h);
+}
+
+__global__ void __launch_bounds__(256) k_run_crc(Geom g, u64 total_runs, const u64* __restrict__ runBase, const u32* __restrict__ runComp,
+                                                  const u32* __restrict__ runStart, const u32* __restrict__ H,
+                                                  const CrcTables* __restrict__ tabs, u32* sliceCrc) {
+  __shared__ u32 t0[256];
+  for (u32 i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t[0][i];
+  __syncthreads();
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 nloop = (total_runs + stride - 1) / stride;
+  for (u64 k = 0; k < nloop; k++) {
+    const u64 r = k * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 crc = 0, z = 0xFFFFFFFFu;
+    if (r < total_runs) {
+      u32 lo = 0, hi = g.sz;
+      while (hi - lo > 1) { const u32 m = (lo + hi) >> 1; if (runBase[m] <= r) lo = m; else hi = m; }
+      z = lo;
+      const u32 prev = r == runBase[z] ? 0u : runComp[r - 1];
+      const u32 d = runComp[r] ^ prev;
+      if (d) crc = gf_mul_id(d, H[(u32)g.sxy - runStart[r]], t0);
+    }
     const u32 z0 = __shfl_sync(FULL_MASK, z, 0);
     if (__all_sync(FULL_MASK, z == z0)) {
       const u32 x = __reduce_xor_sync(FULL_MASK, crc);
-      if ((threadIdx.x & 31) == 0 && z0 != 0xFFFFFFFFu) atomicXor(sliceCrc + z0, x);
-    } else if (z != 0xFFFFFFFFu) {
+      if ((threadIdx.x & 31) == 0 && z0 != 0xFFFFFFFFu && x) atomicXor(sliceCrc + z0, x);
+    } else if (z != 0xFFFFFFFFu && crc) {
       atomicXor(sliceCrc + z, crc);
     }
   }
+}
+
+// H table: level tables by one thread (H[0..B], H[k*B]), then a parallel fill  H[kB + j] = H[kB] * x^(32 j) ^ H[j]
+#define CRCH_B 1024u
+__global__ void k_crcH_levels(const CrcTables* __restrict__ tabs, u32 n, u32* __restrict__ Hl, u32* __restrict__ Gk) {
+  if (threadIdx.x || blockIdx.x) return;
+  u32 h = 0;
+  Hl[0] = 0;
+  for (u32 j = 1; j <= CRCH_B; j++) { h = crc_word(tabs->t, h ^ 0x80000000u, 0u); Hl[j] = h; }   // H[j] = x^32 (1 + H[j-1])
+  const u32 xB = gf_xpow32(tabs->pw, CRCH_B);
+  const u32 K = n / CRCH_B + 1;
+  u32 gk = 0;
+  Gk[0] = 0;
+  for (u32 k = 1; k <= K; k++) { gk = gf_mul(gk, xB) ^ h; Gk[k] = gk; }                           // H[(k)B] = H[(k-1)B] x^(32B) ^ H[B]
+}
+__global__ void __launch_bounds__(256) k_crcH_fill(const CrcTables* __restrict__ tabs, u32 n, const u32* __restrict__ Hl,
+                                                    const u32* __restrict__ Gk, u32* __restrict__ H) {
+  __shared__ u32 pw[4][256];
+  for (u32 i = threadIdx.x; i < 1024; i += blockDim.x) (&pw[0][0])[i] = (&tabs->pw[0][0])[i];
+  __syncthreads();
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 m = (u64)blockIdx.x * blockDim.x + threadIdx.x; m <= n; m += stride) {
+    const u32 k = (u32)(m / CRCH_B), j = (u32)(m - (u64)k * CRCH_B);
+    H[m] = k ? (gf_mul(Gk[k], gf_xpow32(pw, j)) ^ Hl[j]) : Hl[j];
+  }
+}
+static void ensure_crcH(CclBufs& B, u32 sxy, const CrcTables* d_tables, cudaStream_t st) {
+  if (B.crcHn >= (u64)sxy + 1 && B.crcH.p) return;
+  B.crcH.ensure(((u64)sxy + 1) * 4);
+  B.crcHl.ensure(((u64)CRCH_B + 1) * 4 + ((u64)sxy / CRCH_B + 2) * 4);
+  u32* Hl = B.crcHl.as<u32>();
+  u32* Gk = Hl + CRCH_B + 1;
+  k_crcH_levels<<<1, 1, 0, st>>>(d_tables, sxy, Hl, Gk);
+  LAUNCH_CHECK();
+  k_crcH_fill<<<grid_for((u64)sxy + 1, 256, 8), 256, 0, st>>>(d_tables, sxy, Hl, Gk, B.crcH.as<u32>());
+  LAUNCH_CHECK();
+  B.crcHn = (u64)sxy + 1;
 }
 
 __global__ void k_crc_finalize(u32* crc, u32 n, u32 init_term) {
@@ -360,17 +465,24 @@ void launch_crc_finalize_slices(u32* sliceCrc, u32 sz, u32 init_term, cudaStream
 
 void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, const CrcTables* d_tables, ull* scal,
                       cudaStream_t st) {
+  (void)d_tables;
   const u64 nwords = g.words();
   B.nz.ensure((u64)g.sz * 4);
   B.compBase.ensure(((u64)g.sz + 1) * 8);
   B.sliceCrc.ensure((u64)g.sz * 4);
   u32* parent = B.parent.as<u32>();
   k_run_init<<<grid_for(nwords, 256, 16), 256, 0, st>>>(g, DV, B.wordPrefix.as<u32>(), B.rowBase.as<u32>(), B.runBase.as<u64>(),
-                                                         parent, B.runStart.as<u32>());
+                                                         B.runStart.as<u32>());
   LAUNCH_CHECK();
-  k_run_union<<<grid_for(nwords, 256, 16), 256, 0, st>>>(g, DV, DH, B.wordPrefix.as<u32>(), B.rowBase.as<u32>(),
-                                                          B.runBase.as<u64>(), parent);
+  const u32 nbands = (g.sy + CCL_BAND - 1) / CCL_BAND;
+  k_band_ccl<<<grid_for((u64)g.sz * nbands, 1, 4), 256, 0, st>>>(g, nbands, DV, DH, B.wordPrefix.as<u32>(), B.rowBase.as<u32>(),
+                                                                  B.sliceRuns.as<u32>(), B.runBase.as<u64>(), parent);
   LAUNCH_CHECK();
+  if (nbands > 1) {
+    k_border_union<<<grid_for((u64)g.sz * (nbands - 1) * g.W, 256, 8), 256, 0, st>>>(g, nbands, DV, DH, B.wordPrefix.as<u32>(),
+                                                                                       B.rowBase.as<u32>(), B.runBase.as<u64>(), parent);
+    LAUNCH_CHECK();
+  }
   k_root_rank<<<grid_for(g.sz, 1, 8), 256, 0, st>>>(g, parent, B.sliceRuns.as<u32>(), B.runBase.as<u64>(), B.compRank.as<u32>(),
                                                      B.nz.as<u32>());
   LAUNCH_CHECK();
@@ -380,13 +492,15 @@ void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, c
 // second half of the solve: needs total_runs on the host (grid sizing) -- split so the caller can interleave
 void launch_ccl_resolve(const Geom& g, const u32* DV, CclBufs& B, u64 total_runs, const CrcTables* d_tables, u32 crc_init_term,
                         cudaStream_t st) {
+  (void)DV;
+  ensure_crcH(B, (u32)g.sxy, d_tables, st);
   k_run_resolve<<<grid_for(total_runs, 256, 16), 256, 0, st>>>(g, total_runs, B.parent.as<u32>(), B.runBase.as<u64>(),
                                                                 B.compRank.as<u32>(), B.runStart.as<u32>(), B.compBase.as<u64>(),
                                                                 B.runComp.as<u32>(), B.compPix.as<u32>());
   LAUNCH_CHECK();
   CUDA_CHECK(cudaMemsetAsync(B.sliceCrc.p, 0, (u64)g.sz * 4, st));
-  k_cc_crc<<<grid_for(g.words(), 256, 8), 256, 0, st>>>(g, DV, B.wordPrefix.as<u32>(), B.rowBase.as<u32>(), B.runBase.as<u64>(),
-                                                         B.runComp.as<u32>(), d_tables, B.sliceCrc.as<u32>());
+  k_run_crc<<<grid_for(total_runs, 256, 8), 256, 0, st>>>(g, total_runs, B.runBase.as<u64>(), B.runComp.as<u32>(), B.runStart.as<u32>(),
+                                                           B.crcH.as<u32>(), d_tables, B.sliceCrc.as<u32>());
   LAUNCH_CHECK();
   launch_crc_finalize_slices(B.sliceCrc.as<u32>(), g.sz, crc_init_term, st);
 }
