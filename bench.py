@@ -191,7 +191,7 @@ def main():
             ctx.decompress_into(p, 1, n, 0, -1, None, out.data_ptr(), 1, out.numel() * 8)
             return n
 
-    for _ in range(args.warmup):
+    for _ in range(max(1, args.warmup)):          # at least one untimed pass: it is also the round-trip check
         step()
     torch.cuda.synchronize()
     assert torch.equal(out.view(torch.int64), vol.view(torch.int64)), "round trip mismatch"

@@ -679,6 +679,38 @@ __global__ void __launch_bounds__(256) k_paint(Geom g, const u32* __restrict__ D
   }
 }
 
+// Fortran-order paint: one warp per row walks the row 32 pixels at a time; the run index inside the row is a
+// running popcount of the DV words (no per-word prefix array), plane words are loaded 32 at a time and broadcast.
+template <typename OUT, bool MASK>
+__global__ void __launch_bounds__(256) k_paint_rows(Geom g, const u32* __restrict__ DV, const u32* __restrict__ rowBase,
+                                                     const u64* __restrict__ runBase, const u64* __restrict__ runLabel, u64 label,
+                                                     OUT* __restrict__ out) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 lmask = (2u << lane) - 1u;
+  const u64 rows = g.rows();
+  const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
+  for (u64 row = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += nwarps) {
+    const u32 z = (u32)(row / g.sy);
+    const u64* rl = runLabel + runBase[z] + rowBase[row];
+    OUT* o = out + row * g.sx;
+    const u32* dvrow = DV + row * g.W;
+    u32 carry = 0;
+    for (u32 w0 = 0; w0 < g.W; w0 += 32) {
+      const u32 dvl = w0 + lane < g.W ? dvrow[w0 + lane] : 0u;
+      const u32 nk = min(32u, g.W - w0);
+      for (u32 k = 0; k < nk; k++) {
+        const u32 dv = __shfl_sync(FULL_MASK, dvl, k);
+        const u32 x = (w0 + k) * 32 + lane;
+        if (x < g.sx) {
+          const u64 v = rl[carry + __popc(dv & lmask)];
+          o[x] = MASK ? (OUT)(v == label) : (OUT)v;
+        }
+        carry += __popc(dv);
+      }
+    }
+  }
+}
+
 void launch_paint(const Geom& g, const u32* DV, const CclBufs& B, const u64* runLabel, int out_width, int has_label, u64 label,
                   int fortran_order, void* out, cudaStream_t st) {
   const u32 grid = grid1(g.words(), 8, 148 * 8);
@@ -686,15 +718,17 @@ void launch_paint(const Geom& g, const u32* DV, const CclBufs& B, const u64* run
   const u32* rb = B.rowBase.as<u32>();
   const u64* rB = B.runBase.as<u64>();
 #define PAINT(T, M, F) k_paint<T, M, F><<<grid, 256, 0, st>>>(g, DV, wp, rb, rB, runLabel, label, (T*)out)
+#define PAINTR(T, M) k_paint_rows<T, M><<<grid1(g.rows(), 8, 148 * 8), 256, 0, st>>>(g, DV, rb, rB, runLabel, label, (T*)out)
   if (has_label) {
-    if (fortran_order) PAINT(u8, true, true); else PAINT(u8, true, false);
+    if (fortran_order) PAINTR(u8, true); else PAINT(u8, true, false);
   } else if (fortran_order) {
-    switch (out_width) { case 1: PAINT(u8, false, true); break; case 2: PAINT(u16, false, true); break;
-                         case 4: PAINT(u32, false, true); break; default: PAINT(u64, false, true); break; }
+    switch (out_width) { case 1: PAINTR(u8, false); break; case 2: PAINTR(u16, false); break;
+                         case 4: PAINTR(u32, false); break; default: PAINTR(u64, false); break; }
   } else {
     switch (out_width) { case 1: PAINT(u8, false, false); break; case 2: PAINT(u16, false, false); break;
                          case 4: PAINT(u32, false, false); break; default: PAINT(u64, false, false); break; }
   }
 #undef PAINT
+#undef PAINTR
   LAUNCH_CHECK();
 }

@@ -16,76 +16,97 @@ template <typename T> __device__ __forceinline__ T shfl_up1(T v) {
   else return (T)__shfl_up_sync(FULL_MASK, (u32)v, 1);
 }
 
-// One warp owns a strip of RS rows of one 32-pixel word column: lane <-> x, rows walked in registers so the
-// up-neighbour is the previous iteration's value; the left neighbour comes from the lane below (lane 0 reads
-// it).  DV bit x of row y: label(x,y) != label(x-1,y) (x>0).  DH bit: label(x,y) != label(x,y-1) (y>0).
+// One warp owns a strip of RS rows across the whole row width and walks it 32 pixels at a time: lane <-> x, the
+// up-neighbour of a row is the previous row's register, the left neighbour comes from the lane below through one
+// rotate-shuffle (lane 31 injects its value of the previous column, so lane 0 sees the pixel left of the word).
+// Plane words are collected lane-per-word and stored 32 at a time (coalesced).
+// DV bit x of row y: label(x,y) != label(x-1,y) (x>0).  DH bit: label(x,y) != label(x,y-1) (y>0).
+// scal[SC_MAX] receives the bitwise OR of all labels: it has the same byte width as lib::max_label, which is all the
+// caller derives from it (crackle.hpp:233-235).  pixel_pairs counts equal flat-order neighbours (lib.hpp:249-256).
+template <typename T> __device__ __forceinline__ T shfl_idx(T v, u32 src) {
+  if constexpr (sizeof(T) == 8) return (T)__shfl_sync(FULL_MASK, (ull)v, src);
+  else return (T)__shfl_sync(FULL_MASK, (u32)v, src);
+}
+
 template <typename T, int RS>
 __global__ void __launch_bounds__(256) k_edges(const T* __restrict__ L, Geom g, u32* __restrict__ DV,
                                                 u32* __restrict__ DH, ull* scal) {
   const u32 lane = threadIdx.x & 31;
+  const u32 rot = (lane + 31) & 31;
   const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
   const u32 ntile = (g.sy + RS - 1) / RS;
-  const u64 items = (u64)g.sz * ntile * g.W;
-  u64 mx = 0, pairs = 0;
+  const u64 items = (u64)g.sz * ntile;
+  u64 orall = 0, pairs = 0;
   for (u64 it = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < items; it += nwarps) {
-    const u32 w = (u32)(it % g.W);
-    const u64 t = it / g.W;
-    const u32 tile = (u32)(t % ntile), z = (u32)(t / ntile);
+    const u32 z = (u32)(it / ntile), tile = (u32)(it - (u64)z * ntile);
     const u32 y0 = tile * RS;
     const u32 nr = min((u32)RS, g.sy - y0);
-    const u32 x = w * 32 + lane;
-    const bool inx = x < g.sx;
-    const T* base = L + (u64)z * g.sxy;
-    T cur[RS], lf[RS];
-    T up = 0;
-    if (inx && y0 > 0) up = base[(u64)(y0 - 1) * g.sx + x];
+    const T* base = L + (u64)z * g.sxy + (u64)y0 * g.sx;
+    T prev31[RS];
+    u32 dvacc[RS], dhacc[RS];
 #pragma unroll
     for (int r = 0; r < RS; r++) {
-      cur[r] = 0;
-      if (r < (int)nr && inx) cur[r] = base[(u64)(y0 + r) * g.sx + x];
+      prev31[r] = 0;
+      dvacc[r] = dhacc[r] = 0;
+      if (lane == 31 && r < (int)nr && (z | (y0 + r)) != 0) prev31[r] = base[(u64)r * g.sx - 1];   // previous flat voxel of (0, y)
     }
+    for (u32 w = 0; w < g.W; w++) {
+      const u32 x = w * 32 + lane;
+      const bool inx = x < g.sx;
+      T cur[RS];
 #pragma unroll
-    for (int r = 0; r < RS; r++) {
-      lf[r] = 0;
-      if (lane == 0 && r < (int)nr) {
-        const u64 flat = (u64)z * g.sxy + (u64)(y0 + r) * g.sx + x;
-        if (flat > 0) lf[r] = L[flat - 1];
+      for (int r = 0; r < RS; r++) {
+        cur[r] = 0;
+        if (r < (int)nr && inx) cur[r] = base[(u64)r * g.sx + x];
       }
-    }
+      T up = 0;
+      if (y0 > 0 && inx) up = *(base - g.sx + x);
+      const u32 valid = __ballot_sync(FULL_MASK, inx);
+      const u32 nvalid = __popc(valid);
 #pragma unroll
-    for (int r = 0; r < RS; r++) {
-      if (r < (int)nr) {
-        const u32 y = y0 + r;
-        const T v = cur[r];
-        T l = shfl_up1<T>(v);
-        if (lane == 0) l = lf[r];
-        const bool has_prev = x > 0 || y > 0 || z > 0;          // flat index > 0
-        pairs += (inx && has_prev && v == l) ? 1 : 0;
-        const bool vd = inx && x > 0 && v != l;
-        const bool hd = inx && y > 0 && v != up;
-        const u32 vb = __ballot_sync(FULL_MASK, vd), hb = __ballot_sync(FULL_MASK, hd);
-        if (lane == 0) {
-          const u64 o = ((u64)z * g.sy + y) * g.W + w;
-          DV[o] = vb;
-          DH[o] = hb;
+      for (int r = 0; r < RS; r++) {
+        if (r < (int)nr) {
+          const T v = cur[r];
+          const T t = lane == 31 ? prev31[r] : v;
+          const T l = shfl_idx<T>(t, rot);
+          prev31[r] = v;
+          u32 vb = __ballot_sync(FULL_MASK, inx && v != l);
+          u32 hb = __ballot_sync(FULL_MASK, inx && v != up);
+          if (y0 + r == 0) hb = 0;
+          pairs += nvalid - __popc(vb);
+          if (w == 0) {
+            if ((z | (y0 + r)) == 0 && !(vb & 1u)) pairs--;   // flat index 0 has no predecessor
+            vb &= ~1u;
+          }
+          if (lane == (w & 31)) { dvacc[r] = vb; dhacc[r] = hb; }
+          up = v;
+          orall |= (u64)v;
         }
-        up = v;
-        if (inx) mx = max(mx, (u64)v);
+      }
+      if ((w & 31) == 31 || w == g.W - 1) {
+        const u32 ws = (w & ~31u) + lane;
+        if (ws <= w) {
+#pragma unroll
+          for (int r = 0; r < RS; r++) {
+            if (r < (int)nr) {
+              const u64 o = ((u64)z * g.sy + y0 + r) * g.W + ws;
+              DV[o] = dvacc[r];
+              DH[o] = dhacc[r];
+            }
+          }
+        }
       }
     }
   }
-  // block reduction -> two atomics per block
-  __shared__ u64 s_mx[8], s_pr[8];
+  // block reduction -> two atomics per block (pairs is warp-uniform: lane 0 carries it)
+  __shared__ u64 s_or[8], s_pr[8];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mx = max(mx, (u64)__shfl_xor_sync(FULL_MASK, (ull)mx, o));
-    pairs += (u64)__shfl_xor_sync(FULL_MASK, (ull)pairs, o);
-  }
-  if (lane == 0) { s_mx[threadIdx.x >> 5] = mx; s_pr[threadIdx.x >> 5] = pairs; }
+  for (int o = 16; o > 0; o >>= 1) orall |= (u64)__shfl_xor_sync(FULL_MASK, (ull)orall, o);
+  if (lane == 0) { s_or[threadIdx.x >> 5] = orall; s_pr[threadIdx.x >> 5] = pairs; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (u32 i = 1; i < (blockDim.x >> 5); i++) { mx = max(mx, s_mx[i]); pairs += s_pr[i]; }
-    atomicMax(&scal[SC_MAX], (ull)mx);
+    for (u32 i = 1; i < (blockDim.x >> 5); i++) { orall |= s_or[i]; pairs += s_pr[i]; }
+    atomicOr(&scal[SC_MAX], (ull)orall);
     atomicAdd(&scal[SC_PAIRS], (ull)pairs);
   }
 }
@@ -108,9 +129,9 @@ static u32 grid_for(u64 items, u32 per_block, u32 blocks_per_sm) {
 }
 
 void launch_edges(const void* labels, int width, const Geom& g, u32* DV, u32* DH, ull* scal, cudaStream_t st) {
-  constexpr int RS = 16;
-  const u64 items = (u64)g.sz * ((g.sy + RS - 1) / RS) * g.W;
-  const u32 grid = grid_for(items, 8, 8);
+  constexpr int RS = 8;
+  const u64 items = (u64)g.sz * ((g.sy + RS - 1) / RS);
+  const u32 grid = grid_for(items, 8, 4);
   switch (width) {
     case 1: k_edges<u8, RS><<<grid, 256, 0, st>>>((const u8*)labels, g, DV, DH, scal); break;
     case 2: k_edges<u16, RS><<<grid, 256, 0, st>>>((const u16*)labels, g, DV, DH, scal); break;
