@@ -10,7 +10,6 @@
 #include "ckl_internal.cuh"
 
 void launch_exscan_u32_u64(const u32* in, u32 n, u32 stride, u64* out, ull* total_out, u64 add_each, cudaStream_t st);
-void launch_ccl_resolve(const Geom& g, const u32* DV, CclBufs& B, u64 total_runs, const CrcTables* d_tables, u32 crc_init_term, cudaStream_t st);
 void launch_markov_copy(const Geom& g, TraceBufs& T, MarkovBufs& M, u8* dst, cudaStream_t st);
 void launch_trace_walk(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes, u32 max_nodes, cudaStream_t st);
 void launch_trace_post(const Geom& g, TraceBufs& T, ull* scal, u64 total_ev_cap, cudaStream_t st);
@@ -263,7 +262,7 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   STAGE(c, "trace_post", launch_trace_post(g, c->tr, c->scal, evCap, st));
   // component ranks, crcs, component labels
   const u32 init_term = gf_mul(gf_xpow32(c->htab.pw, (u32)g.sxy), 0xFFFFFFFFu);
-  STAGE(c, "ccl_resolve_crc", launch_ccl_resolve(g, c->DV.as<u32>(), c->ccl, J.runs, c->dtab, init_term, st));
+  STAGE(c, "ccl_finish", launch_ccl_finish(g, c->ccl, J.runs, c->dtab, init_term, nullptr, st));
   c->lb.mapping.ensure(J.ncomp * 8 + 8);
   c->prof.begin("labels_sort_unique", st);
   launch_gather_mapping(J.labels, J.width, g, c->ccl, J.ncomp, c->lb.mapping.as<u64>(), st);
@@ -692,7 +691,11 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   c->ccl.runComp.ensure(runs * 4); c->ccl.compPix.ensure(runs * 4);
   STAGE(c, "ccl_solve", launch_ccl_solve(g, c->DV.as<u32>(), c->DH.as<u32>(), c->ccl, c->dtab, c->scal, st));
   const u32 init_term = gf_mul(gf_xpow32(c->htab.pw, (u32)g.sxy), 0xFFFFFFFFu);
-  STAGE(c, "ccl_resolve_crc", launch_ccl_resolve(g, c->DV.as<u32>(), c->ccl, runs, c->dtab, init_term, st));
+  D.runLabel.ensure(runs * 8 + 8);
+  CclDecodeSrc dsrc;
+  dsrc.uniq = dstream + uniq_off; dsrc.keys = dstream + keys_off; dsrc.n_uniq = nu; dsrc.n_keys = n_keys; dsrc.sw = sw; dsrc.kw = kw;
+  dsrc.keyBase = D.keyBase.as<u64>(); dsrc.runLabel = D.runLabel.as<u64>();
+  STAGE(c, "ccl_finish", launch_ccl_finish(g, c->ccl, runs, c->dtab, init_term, &dsrc, st));
   if (h.format_version > 0) {   // crackle.hpp:599-611
     k_crc_compare<<<(g.sz + 255) / 256, 256, 0, st>>>(c->ccl.sliceCrc.as<u32>(), dstream + num_bytes - 4ull * h.sz + 4ull * (u64)z_start, g.sz, c->scal);
     LAUNCH_CHECK();
@@ -707,8 +710,6 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
                                          std::to_string(computed) + " stored: " + std::to_string(stored));
     }
   }
-  D.runLabel.ensure(runs * 8 + 8);
-  STAGE(c, "run_labels", launch_run_labels(g, c->ccl, dstream, uniq_off, keys_off, nu, n_keys, sw, kw, D.keyBase.as<u64>(), D.runLabel.as<u64>(), st));
   void* dout = out;
   if (!out_on_device) { c->out_dev.ensure(voxels * (u64)ow); dout = c->out_dev.p; }
   STAGE(c, "paint", launch_paint(g, c->DV.as<u32>(), c->ccl, D.runLabel.as<u64>(), ow, has_label, label, (int)h.fortran_order, dout, st));

@@ -32,6 +32,11 @@ void launch_ccl_count(const Geom& g, const u32* DV, CclBufs& B, ull* scal, cudaS
 // writes scal[SC_COMPONENTS]
 void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, const CrcTables* d_tables,
                       ull* scal, cudaStream_t st);
+// second half: per-run component ranks, per-slice CRCs and (compress) component first pixels / (decompress, `decode`
+// non-null) the label of every run
+struct CclDecodeSrc { const u8* uniq; const u8* keys; u64 n_uniq, n_keys; int sw, kw; const u64* keyBase; u64* runLabel; };
+void launch_ccl_finish(const Geom& g, CclBufs& B, u64 total_runs, const CrcTables* d_tables, u32 crc_init_term,
+                       const CclDecodeSrc* decode, cudaStream_t st);
 // generic device CRC-32C of a byte buffer: result (finalised) written to *d_out
 void launch_crc_bytes(const u8* d, u64 n, const CrcTables* d_tables, const CrcTables& h_tables, u32* d_out, cudaStream_t st);
 // finalise per-slice raw registers into standard CRCs (in place)

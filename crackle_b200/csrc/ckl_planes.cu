@@ -300,6 +300,51 @@ __device__ __forceinline__ void unite_word(const Geom& g, const u32* __restrict_
   }
 }
 
+// Band-local linking, two sweeps over the words of rows y0+1 .. y1-1.  A candidate is the first pixel of a
+// (run, upper run) overlap group.  PHASE 1: the FIRST group of every run links the run straight to the upper run
+// (plain store, one writer per run; upper ids are smaller, so the forest is rooted at component minima-to-be).
+// PHASE 2: every further group is a real merge -> union-find.  Most runs of a segmentation touch exactly one upper
+// run, so almost all of the work is the atomic-free phase 1.
+template <int PHASE>
+__device__ __forceinline__ void link_word(const Geom& g, const u32* __restrict__ DV, const u32* __restrict__ DH,
+                                          const u32* __restrict__ wordPrefix, const u32* __restrict__ rowBase, u64 row, u32 w,
+                                          volatile u32* par, u32 base) {
+  const u64 i = row * g.W + w;
+  const u32 valid = (w == g.W - 1 && (g.sx & 31)) ? ((1u << (g.sx & 31)) - 1u) : 0xFFFFFFFFu;
+  const u32 dv = DV[i], dvu = DV[i - g.W];
+  const u32 conn = ~DH[i] & valid;                       // pixel connected to the pixel above
+  if (!conn) return;
+  const u32 connPrev = w ? ~DH[i - 1] : 0u;              // previous word of the row (all 32 pixels valid)
+  const u32 contIn = (connPrev >> 31) & ~(dv | dvu) & 1u; // bit 0 continues the group of pixel 32w-1
+  u32 cand = conn & (dv | dvu | ~((conn << 1) | contIn));
+  if (!cand) return;
+  const u32 rb = rowBase[row] + wordPrefix[i] - base, rbu = rowBase[row - 1] + wordPrefix[i - g.W] - base;
+  // does the run that enters this word from the left already have a connected pixel?
+  bool hadIn = false;
+  if (w && !(dv & 1u)) {
+    u32 j = w - 1, cj = connPrev;
+    for (;;) {
+      const u32 dvj = DV[row * g.W + j];
+      if (dvj) { hadIn = (cj & ~((1u << (31 - __clz(dvj))) - 1u)) != 0; break; }
+      if (cj) { hadIn = true; break; }
+      if (j == 0) break;
+      j--;
+      cj = ~DH[row * g.W + j];
+    }
+  }
+  while (cand) {
+    const u32 b = __ffs(cand) - 1;
+    cand &= cand - 1;
+    const u32 below = dv & mask_le(b);                   // run starts at or before b
+    const u32 s = below ? 31 - __clz(below) : 0;         // first pixel of the run inside this word
+    const u32 seg = ((1u << b) - 1u) & ~((1u << s) - 1u);
+    const bool first = !(conn & seg) && !(below == 0 && hadIn);
+    const u32 r = rb + __popc(below), u = rbu + __popc(dvu & mask_le(b));
+    if (PHASE == 1) { if (first) par[r] = u; }
+    else if (!first) ufc_unite(par, r, u);
+  }
+}
+
 // Band pass: one block owns CCL_BAND rows of one slice and solves them in shared memory (global memory when the
 // band has too many runs); the band's trees are flattened and written out with slice-local run ids.
 #define CCL_BAND 64
@@ -324,7 +369,16 @@ __global__ void __launch_bounds__(256) k_band_ccl(Geom g, u32 nbands, const u32*
     const u32 nw = (y1 - y0 - 1) * g.W;                  // words of rows y0+1 .. y1-1
     for (u32 k = threadIdx.x; k < nw; k += blockDim.x) {
       const u32 r = k / g.W, w = k - r * g.W;
-      unite_word(g, DV, DH, wordPrefix, rowBase, row0 + 1 + r, w, par, base);
+      link_word<1>(g, DV, DH, wordPrefix, rowBase, row0 + 1 + r, w, par, base);
+    }
+    __syncthreads();
+    // pointer jumping: any ancestor is a valid parent, so the rounds need no barriers in between
+    for (int round = 0; round < 3; round++)
+      for (u32 i = threadIdx.x; i < n; i += blockDim.x) { const u32 p = par[i]; const u32 pp = par[p]; if (pp != p) par[i] = pp; }
+    __syncthreads();
+    for (u32 k = threadIdx.x; k < nw; k += blockDim.x) {
+      const u32 r = k / g.W, w = k - r * g.W;
+      link_word<2>(g, DV, DH, wordPrefix, rowBase, row0 + 1 + r, w, par, base);
     }
     __syncthreads();
     if (sm) {
@@ -475,6 +529,64 @@ static void ensure_crcH(CclBufs& B, u32 sxy, const CrcTables* d_tables, cudaStre
   B.crcHn = (u64)sxy + 1;
 }
 
+// Fused per-run finish: component rank of the run (find + rank of the root), the run's CRC contribution (the rank
+// of the previous run comes from the neighbouring lane), and
+//   MODE 0 (compress):   first pixel of every component (-> label gather)
+//   MODE 1 (decompress): label of the run = uniq[key[keyBase[z] + comp]]   (labels::decode_flat, labels.hpp:453-506)
+// grid = (chunks, slices): no per-run slice search.
+struct RunLabelSrc { const u8* uniq; const u8* keys; u64 n_uniq, n_keys; int sw, kw; const u64* keyBase; u64* runLabel; };
+__device__ __forceinline__ u64 ld_le_dev(const u8* p, int w) {
+  u64 v = 0;
+  for (int i = 0; i < w; i++) v |= (u64)p[i] << (8 * i);
+  return v;
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) k_run_finish(Geom g, const u32* __restrict__ parent, const u32* __restrict__ sliceRuns,
+                                                     const u64* __restrict__ runBase, const u32* __restrict__ compRank,
+                                                     const u32* __restrict__ runStart, const u64* __restrict__ compBase,
+                                                     const u32* __restrict__ H, const CrcTables* __restrict__ tabs,
+                                                     u32* __restrict__ compPix, RunLabelSrc src, u32* sliceCrc) {
+  __shared__ u32 t0[256];
+  for (u32 i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t[0][i];
+  __syncthreads();
+  const u32 lane = threadIdx.x & 31;
+  for (u32 z = blockIdx.y; z < g.sz; z += gridDim.y) {
+    const u32 n = sliceRuns[z];
+    const u64 gb = runBase[z];
+    const u32* par = parent + gb;
+    const u32* rank = compRank + gb;
+    u32 x = 0;
+    const u32 per = gridDim.x * blockDim.x;
+    const u32 nloop = (n + per - 1) / per;
+    for (u32 k = 0; k < nloop; k++) {
+      const u32 i = k * per + blockIdx.x * blockDim.x + threadIdx.x;
+      u32 c = 0;
+      if (i < n) {
+        const u32 root = uf_find(par, i);
+        c = rank[root];
+        if (MODE == 0) { if (root == i) compPix[compBase[z] + c] = runStart[gb + i]; }
+        else {
+          const u64 ki = src.keyBase[z] + c;
+          u64 label = 0;
+          if (ki < src.n_keys) {
+            const u64 key = ld_le_dev(src.keys + ki * (u64)src.kw, src.kw);
+            if (key < src.n_uniq) label = ld_le_dev(src.uniq + key * (u64)src.sw, src.sw);
+          }
+          src.runLabel[gb + i] = label;
+        }
+      }
+      u32 cprev = __shfl_up_sync(FULL_MASK, c, 1);
+      if (lane == 0) cprev = (i > 0 && i < n) ? rank[uf_find(par, i - 1)] : 0u;
+      if (i < n) {
+        const u32 d = c ^ cprev;
+        if (d) x ^= gf_mul_id(d, H[(u32)g.sxy - runStart[gb + i]], t0);
+      }
+    }
+    x = __reduce_xor_sync(FULL_MASK, x);
+    if (lane == 0 && x) atomicXor(sliceCrc + z, x);
+  }
+}
+
 __global__ void k_crc_finalize(u32* crc, u32 n, u32 init_term) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) crc[i] = ~(crc[i] ^ init_term);
@@ -510,19 +622,31 @@ void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, c
   launch_exscan_u32_u64(B.nz.as<u32>(), g.sz, 1, B.compBase.as<u64>(), &scal[SC_COMPONENTS], 0, st);
 }
 
-// second half of the solve: needs total_runs on the host (grid sizing) -- split so the caller can interleave
-void launch_ccl_resolve(const Geom& g, const u32* DV, CclBufs& B, u64 total_runs, const CrcTables* d_tables, u32 crc_init_term,
-                        cudaStream_t st) {
-  (void)DV;
+// second half of the solve: ranks -> per-run results + per-slice CRCs.  `decode` selects MODE 1 (run labels).
+void launch_ccl_finish(const Geom& g, CclBufs& B, u64 total_runs, const CrcTables* d_tables, u32 crc_init_term,
+                       const CclDecodeSrc* decode, cudaStream_t st) {
   ensure_crcH(B, (u32)g.sxy, d_tables, st);
-  k_run_resolve<<<grid_for(total_runs, 256, 16), 256, 0, st>>>(g, total_runs, B.parent.as<u32>(), B.runBase.as<u64>(),
-                                                                B.compRank.as<u32>(), B.runStart.as<u32>(), B.compBase.as<u64>(),
-                                                                B.runComp.as<u32>(), B.compPix.as<u32>());
-  LAUNCH_CHECK();
   CUDA_CHECK(cudaMemsetAsync(B.sliceCrc.p, 0, (u64)g.sz * 4, st));
-  k_run_crc<<<grid_for(total_runs, 256, 8), 256, 0, st>>>(g, total_runs, B.runBase.as<u64>(), B.runComp.as<u32>(), B.runStart.as<u32>(),
-                                                           B.crcH.as<u32>(), d_tables, B.sliceCrc.as<u32>());
-  LAUNCH_CHECK();
+  if (total_runs) {
+    const u64 per_slice = (total_runs + g.sz - 1) / g.sz;
+    u32 gx = (u32)((per_slice + 255) / 256);
+    if (gx > 64) gx = 64;
+    if (gx < 1) gx = 1;
+    const dim3 grid(gx, g.sz < 65535u ? g.sz : 65535u);
+    RunLabelSrc src{};
+    if (decode) {
+      src.uniq = decode->uniq; src.keys = decode->keys; src.n_uniq = decode->n_uniq; src.n_keys = decode->n_keys;
+      src.sw = decode->sw; src.kw = decode->kw; src.keyBase = decode->keyBase; src.runLabel = decode->runLabel;
+      k_run_finish<1><<<grid, 256, 0, st>>>(g, B.parent.as<u32>(), B.sliceRuns.as<u32>(), B.runBase.as<u64>(), B.compRank.as<u32>(),
+                                           B.runStart.as<u32>(), B.compBase.as<u64>(), B.crcH.as<u32>(), d_tables, B.compPix.as<u32>(),
+                                           src, B.sliceCrc.as<u32>());
+    } else {
+      k_run_finish<0><<<grid, 256, 0, st>>>(g, B.parent.as<u32>(), B.sliceRuns.as<u32>(), B.runBase.as<u64>(), B.compRank.as<u32>(),
+                                           B.runStart.as<u32>(), B.compBase.as<u64>(), B.crcH.as<u32>(), d_tables, B.compPix.as<u32>(),
+                                           src, B.sliceCrc.as<u32>());
+    }
+    LAUNCH_CHECK();
+  }
   launch_crc_finalize_slices(B.sliceCrc.as<u32>(), g.sz, crc_init_term, st);
 }
 
