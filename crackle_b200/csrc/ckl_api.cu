@@ -63,6 +63,8 @@ struct ckl_ctx {
   Prof prof;
   int device = 0;
   cudaStream_t st = nullptr, own_st = nullptr;
+  cudaStream_t st2 = nullptr;            // side stream: the tracing chain runs beside the CCL / label chain
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool ext_stream = false;
   std::string err;
   CrcTables htab;
@@ -150,6 +152,9 @@ extern "C" int ckl_ctx_create(int device, ckl_ctx** out) {
     CUDA_CHECK(cudaSetDevice(device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_st, cudaStreamNonBlocking));
     c->st = c->own_st;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     crc_build_tables(c->htab);
     CUDA_CHECK(cudaMalloc(&c->dtab, sizeof(CrcTables)));
     CUDA_CHECK(cudaMemcpy(c->dtab, &c->htab, sizeof(CrcTables), cudaMemcpyHostToDevice));
@@ -167,6 +172,9 @@ extern "C" void ckl_ctx_destroy(ckl_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->st) cudaStreamSynchronize(c->st);
+  if (c->st2) { cudaStreamSynchronize(c->st2); cudaStreamDestroy(c->st2); }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->own_st) cudaStreamDestroy(c->own_st);
   if (c->dtab) cudaFree(c->dtab);
   if (c->scal) cudaFree(c->scal);
@@ -183,8 +191,8 @@ extern "C" const char* crackle_b200_version(void) { return "crackle_b200 0.1 (sm
     CUDA_CHECK(cudaSetDevice((c)->device));
 #define API_END(c)                                                                     \
   }                                                                                    \
-  catch (const CklError& e) { (c)->err = e.what(); (c)->job.active = false; cudaGetLastError(); return e.code; } \
-  catch (const std::exception& e) { (c)->err = e.what(); (c)->job.active = false; return CKL_ERR_CUDA; }      \
+  catch (const CklError& e) { (c)->err = e.what(); (c)->job.active = false; if ((c)->st2) cudaStreamSynchronize((c)->st2); cudaGetLastError(); return e.code; } \
+  catch (const std::exception& e) { (c)->err = e.what(); (c)->job.active = false; if ((c)->st2) cudaStreamSynchronize((c)->st2); return CKL_ERR_CUDA; }      \
   return CKL_OK;
 
 // ---------------------------------------------------------------------------------------------------------
@@ -235,14 +243,19 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   J.order = order;
   const Geom& g = J.g;
   cudaStream_t st = c->st;
-  // capacities for the tracer, components
-  STAGE(c, "trace_prepare", launch_trace_prepare(g, c->DV.as<u32>(), c->DH.as<u32>(), J.permissible, c->tr, c->scal, st));
+  // Two independent chains consume the planes: crack-code tracing (side stream) and CCL -> labels (main stream).
+  cudaStream_t st2 = c->st2;
+  CUDA_CHECK(cudaEventRecord(c->ev_fork, st));
+  CUDA_CHECK(cudaStreamWaitEvent(st2, c->ev_fork, 0));
+  c->prof.begin("trace_prepare", st2);
+  launch_trace_prepare(g, c->DV.as<u32>(), c->DH.as<u32>(), J.permissible, c->tr, c->scal, st2);
+  c->prof.end(st2);
   c->ccl.parent.ensure(J.runs * 4);
   c->ccl.runStart.ensure(J.runs * 4);
   c->ccl.compRank.ensure(J.runs * 4);
-  c->ccl.runComp.ensure(J.runs * 4);
   c->ccl.compPix.ensure(J.runs * 4);
   STAGE(c, "ccl_solve", launch_ccl_solve(g, c->DV.as<u32>(), c->DH.as<u32>(), c->ccl, c->dtab, c->scal, st));
+  CUDA_CHECK(cudaStreamSynchronize(st2));
   read_scalars(c);
   J.ncomp = c->hscal[SC_COMPONENTS];
   const u64 evCap = c->hscal[SC_SYMCAP], stackCap = c->hscal[SC_STACKCAP], chainCap = c->hscal[SC_CHAINCAP], cpCap = c->hscal[SC_CPCAP];
@@ -258,8 +271,13 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   c->tr.stack.ensure(stackCap * 8);
   c->tr.chain.ensure(chainCap * sizeof(ChainRec));
   c->tr.cp.ensure(cpCap);
-  STAGE(c, "trace_walk", launch_trace_walk(g, c->tr, c->scal, nodes, maxNodes, st));
-  STAGE(c, "trace_post", launch_trace_post(g, c->tr, c->scal, evCap, st));
+  c->prof.begin("trace_walk", st2);
+  launch_trace_walk(g, c->tr, c->scal, nodes, maxNodes, st2);
+  c->prof.end(st2);
+  c->prof.begin("trace_post", st2);
+  launch_trace_post(g, c->tr, c->scal, evCap, st2);
+  c->prof.end(st2);
+  CUDA_CHECK(cudaEventRecord(c->ev_join, st2));
   // component ranks, crcs, component labels
   const u32 init_term = gf_mul(gf_xpow32(c->htab.pw, (u32)g.sxy), 0xFFFFFFFFu);
   STAGE(c, "ccl_finish", launch_ccl_finish(g, c->ccl, J.runs, c->dtab, init_term, nullptr, st));
@@ -268,6 +286,7 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   launch_gather_mapping(J.labels, J.width, g, c->ccl, J.ncomp, c->lb.mapping.as<u64>(), st);
   J.nuniq_local = labels_sort_unique(c->lb, J.ncomp, stored_width, st);
   c->prof.end(st);
+  CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_join, 0));     // join: everything below sees the tracer's results
   read_scalars(c);
   if (c->hscal[SC_ERROR]) throw CklError(CKL_ERR_CUDA, "crackle_b200: internal tracer capacity error " + std::to_string(c->hscal[SC_ERROR]));
   J.ncp = c->hscal[SC_CODEPOINTS];

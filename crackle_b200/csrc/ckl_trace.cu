@@ -315,36 +315,41 @@ __global__ void __launch_bounds__(256) k_path_walk(TraceParams P, u64 nslots) {
 // 0xFFFF = no edge left; GLOBAL mode = a remaining-edge nibble per node in global memory + the read-only seFar.
 #define REPLAY_STACK 256      // shared-memory revisit stack entries per slice; deeper levels spill to global
 
+// A node record travels in a register between steps: after consuming edge k the far node's record is loaded,
+// cleared of the arrival entry and becomes the current record, so the dependent chain of one step is a single
+// shared-memory load plus a few ALU ops.
 template <bool SMEM>
 struct NodeStore {
-  u64* rec;           // SMEM
-  u8* adj;            // GLOBAL
-  const u32* far;     // GLOBAL
-  __device__ __forceinline__ u32 adjacency(u32 node, u64& w) const {
+  u64* rec;           // SMEM: 4 x u16 per node
+  u8* adj;            // GLOBAL: remaining-edge nibble per node
+  const u32* far;     // GLOBAL: read-only super-edge table
+  __device__ __forceinline__ u64 load(u32 node) const { return SMEM ? rec[node] : (u64)adj[node]; }
+  __device__ __forceinline__ u32 adjacency(u64 w) const {
     if (SMEM) {
-      w = rec[node];
       const u32 lo = (u32)w, hi = (u32)(w >> 32);
       return ((lo & 0xFFFFu) != 0xFFFFu ? 1u : 0u) | ((lo >> 16) != 0xFFFFu ? 2u : 0u) | ((hi & 0xFFFFu) != 0xFFFFu ? 4u : 0u) |
              ((hi >> 16) != 0xFFFFu ? 8u : 0u);
-    } else {
-      w = adj[node];
-      return (u32)w;
     }
+    return (u32)w;
   }
-  // consume edge k of `node` (record word w already loaded); returns the far entry (far << 2 | arrival dir)
-  __device__ __forceinline__ u32 take(u32 node, u32 k, u64 w) {
+  // consume edge k of `node` (record w); moves to the far node: node and w are updated to the far node and its record
+  __device__ __forceinline__ void take(u32& node, u32 k, u64& w) {
     if (SMEM) {
       const u32 e = (u32)(w >> (16 * k)) & 0xFFFFu;
-      rec[node] = w | (0xFFFFull << (16 * k));
+      w |= 0xFFFFull << (16 * k);
+      rec[node] = w;
       const u32 f = e >> 2, fk = e & 3u;
-      rec[f] |= 0xFFFFull << (16 * fk);              // after the store above: a self-loop clears both entries
-      return e;
+      if (f != node) w = rec[f];                        // a self-loop keeps working on the same record
+      w |= 0xFFFFull << (16 * fk);
+      rec[f] = w;
+      node = f;
     } else {
       const u32 e = far[(u64)node * 4 + k];
-      adj[node] = (u8)(w & ~(1u << k));
+      adj[node] = (u8)(w & ~(1ull << k));
       const u32 f = e >> 2, fk = e & 3u;
-      adj[f] = adj[f] & (u8)~(1u << fk);
-      return e;
+      w = (u64)(adj[f] & (u8)~(1u << fk));
+      adj[f] = (u8)w;
+      node = f;
     }
   }
   __device__ __forceinline__ bool has_edges(u32 node) const { return SMEM ? rec[node] != ~0ull : adj[node] != 0; }
@@ -398,16 +403,16 @@ __global__ void __launch_bounds__(32) k_replay(TraceParams P) {
         const u32 begin = nev;
         bool firstT = true, t2 = false, justPopped = false, firstIsB = false;
         u32 t2f = 0, poppedB = 0, adjStart = nodeVertex[start];
+        u64 w = S.load(node);
         for (;;) {
-          u64 w;
-          const u32 a = S.adjacency(node, w);
+          if (nev + 2 > evCap) { atomicExch(&P.scal[SC_ERROR], 1ull); ok = false; break; }
+          const u32 a = S.adjacency(w);
           if (a == 0) {
             // a 't': dead end after a move, or -- directly after a pop -- a spurious branch (remove_spurious_branches)
             if (firstT) {
               firstT = false;
               if (nB == 1 && firstIsB) { t2 = true; t2f = nev - begin; adjStart = nodeVertex[node]; }   // remove_initial_branch applies
             }
-            if (nev >= evCap) { atomicExch(&P.scal[SC_ERROR], 1ull); ok = false; break; }
             if (justPopped && !(t2 && poppedB == begin)) { ev[poppedB] = (u32)EV_S << 30; ev[nev++] = (u32)EV_S << 30; }
             else ev[nev++] = (u32)EV_T << 30;
             if (sp == 0) break;
@@ -416,10 +421,10 @@ __global__ void __launch_bounds__(32) k_replay(TraceParams P) {
             node = e.x;
             poppedB = e.y;
             justPopped = true;
+            w = S.load(node);
             continue;
           }
           justPopped = false;
-          if (nev + 2 > evCap) { atomicExch(&P.scal[SC_ERROR], 1ull); ok = false; break; }
           if (a & (a - 1)) {                                  // popcount > 1: branch point
             if (sp >= stackCap + REPLAY_STACK) { atomicExch(&P.scal[SC_ERROR], 2ull); ok = false; break; }
             const uint2 e = make_uint2(node, nev);
@@ -430,9 +435,8 @@ __global__ void __launch_bounds__(32) k_replay(TraceParams P) {
             nB++;
           }
           const u32 k = __ffs(a) - 1;                          // priority: right, left, down, up
-          const u32 e = S.take(node, k, w);
           ev[nev++] = ((u32)EV_E << 30) | (node * 4 + k);
-          node = e >> 2;
+          S.take(node, k, w);
         }
         ChainRec& rec = chains[nch];
         rec.adjStart = adjStart;
