@@ -237,7 +237,6 @@ struct TraceParams {
   u8* cp;
   u32* sliceInfo;          // per slice: nev|ncp, nchains, bocBytes, codeBytes
   ull* scal;
-  u32 smemNodeCap;         // slices with at most this many nodes are replayed from shared memory
 };
 
 __device__ __forceinline__ u32 slice_of(const u64* __restrict__ base, u32 sz, u64 idx) {   // last z with base[z] <= idx
@@ -315,70 +314,106 @@ __global__ void __launch_bounds__(256) k_path_walk(TraceParams P, u64 nslots) {
 // 0xFFFF = no edge left; GLOBAL mode = a remaining-edge nibble per node in global memory + the read-only seFar.
 #define REPLAY_STACK 256      // shared-memory revisit stack entries per slice; deeper levels spill to global
 
-// A node record travels in a register between steps: after consuming edge k the far node's record is loaded,
-// cleared of the arrival entry and becomes the current record, so the dependent chain of one step is a single
-// shared-memory load plus a few ALU ops.
-template <bool SMEM>
-struct NodeStore {
-  u64* rec;           // SMEM: 4 x u16 per node
-  u8* adj;            // GLOBAL: remaining-edge nibble per node
-  const u32* far;     // GLOBAL: read-only super-edge table
-  __device__ __forceinline__ u64 load(u32 node) const { return SMEM ? rec[node] : (u64)adj[node]; }
-  __device__ __forceinline__ u32 adjacency(u64 w) const {
-    if (SMEM) {
-      const u32 lo = (u32)w, hi = (u32)(w >> 32);
-      return ((lo & 0xFFFFu) != 0xFFFFu ? 1u : 0u) | ((lo >> 16) != 0xFFFFu ? 2u : 0u) | ((hi & 0xFFFFu) != 0xFFFFu ? 4u : 0u) |
-             ((hi >> 16) != 0xFFFFu ? 8u : 0u);
-    }
-    return (u32)w;
+// A node record travels in registers between steps: after consuming edge k the far node's record is loaded,
+// cleared of the arrival edge and becomes the current record, so the dependent chain of one step is a single
+// shared-memory load plus a few ALU ops.  Three stores:
+//   MODE 0  shared memory, slices with <= 8191 nodes: uint2 per node = four 15-bit entries (far << 2 | arrival dir)
+//           at bits 0/15 of each word and the remaining-edge nibble in bits 30..31 of the two words
+//   MODE 1  shared memory, <= 16382 nodes: four u16 entries, 0xFFFF = edge consumed
+//   MODE 2  global memory: remaining-edge nibble per node + the read-only super-edge table
+#define REPLAY_CAP0 8191u
+#define REPLAY_CAP1 16382u
+template <int MODE> struct NodeStore;
+
+template <> struct NodeStore<0> {
+  typedef uint2 Rec;
+  uint2* rec; u8* adj; const u32* far;
+  __device__ __forceinline__ void init(u32 i, uint4 f) {
+    const u32 p0 = f.x != NONE32, p1 = f.y != NONE32, p2 = f.z != NONE32, p3 = f.w != NONE32;
+    rec[i] = make_uint2((p0 ? (f.x & 0x7FFFu) : 0u) | ((p1 ? (f.y & 0x7FFFu) : 0u) << 15) | (p0 << 30) | (p1 << 31),
+                        (p2 ? (f.z & 0x7FFFu) : 0u) | ((p3 ? (f.w & 0x7FFFu) : 0u) << 15) | (p2 << 30) | (p3 << 31));
   }
-  // consume edge k of `node` (record w); moves to the far node: node and w are updated to the far node and its record
-  __device__ __forceinline__ void take(u32& node, u32 k, u64& w) {
-    if (SMEM) {
-      const u32 e = (u32)(w >> (16 * k)) & 0xFFFFu;
-      w |= 0xFFFFull << (16 * k);
-      rec[node] = w;
-      const u32 f = e >> 2, fk = e & 3u;
-      if (f != node) w = rec[f];                        // a self-loop keeps working on the same record
-      w |= 0xFFFFull << (16 * fk);
-      rec[f] = w;
-      node = f;
-    } else {
-      const u32 e = far[(u64)node * 4 + k];
-      adj[node] = (u8)(w & ~(1ull << k));
-      const u32 f = e >> 2, fk = e & 3u;
-      w = (u64)(adj[f] & (u8)~(1u << fk));
-      adj[f] = (u8)w;
-      node = f;
-    }
+  __device__ __forceinline__ Rec load(u32 node) const { return rec[node]; }
+  __device__ __forceinline__ u32 adjacency(Rec w) const { return (w.x >> 30) | ((w.y >> 30) << 2); }
+  __device__ __forceinline__ void take(u32& node, u32 k, Rec& w) {
+    const u32 word = (k & 2u) ? w.y : w.x;
+    const u32 e = (word >> (15u * (k & 1u))) & 0x7FFFu;
+    const u32 bit = 0x40000000u << (k & 1u);
+    if (k & 2u) w.y &= ~bit; else w.x &= ~bit;
+    rec[node] = w;
+    const u32 f = e >> 2, fk = e & 3u;
+    if (f != node) w = rec[f];                          // a self-loop keeps working on the same record
+    const u32 fbit = 0x40000000u << (fk & 1u);
+    if (fk & 2u) w.y &= ~fbit; else w.x &= ~fbit;
+    rec[f] = w;
+    node = f;
   }
-  __device__ __forceinline__ bool has_edges(u32 node) const { return SMEM ? rec[node] != ~0ull : adj[node] != 0; }
+  __device__ __forceinline__ bool has_edges(u32 node) const { const uint2 w = rec[node]; return ((w.x | w.y) >> 30) != 0; }
 };
 
-template <bool SMEM>
+template <> struct NodeStore<1> {
+  typedef u64 Rec;
+  u64* rec; u8* adj; const u32* far;
+  __device__ __forceinline__ void init(u32 i, uint4 f) {
+    const u64 e0 = f.x == NONE32 ? 0xFFFFull : (u64)(f.x & 0xFFFFu), e1 = f.y == NONE32 ? 0xFFFFull : (u64)(f.y & 0xFFFFu);
+    const u64 e2 = f.z == NONE32 ? 0xFFFFull : (u64)(f.z & 0xFFFFu), e3 = f.w == NONE32 ? 0xFFFFull : (u64)(f.w & 0xFFFFu);
+    rec[i] = e0 | (e1 << 16) | (e2 << 32) | (e3 << 48);
+  }
+  __device__ __forceinline__ Rec load(u32 node) const { return rec[node]; }
+  __device__ __forceinline__ u32 adjacency(Rec w) const {
+    const u32 lo = (u32)w, hi = (u32)(w >> 32);
+    return ((lo & 0xFFFFu) != 0xFFFFu ? 1u : 0u) | ((lo >> 16) != 0xFFFFu ? 2u : 0u) | ((hi & 0xFFFFu) != 0xFFFFu ? 4u : 0u) |
+           ((hi >> 16) != 0xFFFFu ? 8u : 0u);
+  }
+  __device__ __forceinline__ void take(u32& node, u32 k, Rec& w) {
+    const u32 e = (u32)(w >> (16 * k)) & 0xFFFFu;
+    w |= 0xFFFFull << (16 * k);
+    rec[node] = w;
+    const u32 f = e >> 2, fk = e & 3u;
+    if (f != node) w = rec[f];
+    w |= 0xFFFFull << (16 * fk);
+    rec[f] = w;
+    node = f;
+  }
+  __device__ __forceinline__ bool has_edges(u32 node) const { return rec[node] != ~0ull; }
+};
+
+template <> struct NodeStore<2> {
+  typedef u32 Rec;
+  u64* rec; u8* adj; const u32* far;
+  __device__ __forceinline__ void init(u32 i, uint4 f) {
+    adj[i] = (u8)((f.x != NONE32 ? 1u : 0u) | (f.y != NONE32 ? 2u : 0u) | (f.z != NONE32 ? 4u : 0u) | (f.w != NONE32 ? 8u : 0u));
+  }
+  __device__ __forceinline__ Rec load(u32 node) const { return adj[node]; }
+  __device__ __forceinline__ u32 adjacency(Rec w) const { return w; }
+  __device__ __forceinline__ void take(u32& node, u32 k, Rec& w) {
+    const u32 e = far[(u64)node * 4 + k];
+    adj[node] = (u8)(w & ~(1u << k));
+    const u32 f = e >> 2, fk = e & 3u;
+    w = adj[f] & ~(1u << fk) & 0xFu;
+    adj[f] = (u8)w;
+    node = f;
+  }
+  __device__ __forceinline__ bool has_edges(u32 node) const { return adj[node] != 0; }
+};
+
+__device__ __forceinline__ int replay_mode(u32 N) { return N <= REPLAY_CAP0 ? 0 : (N <= REPLAY_CAP1 ? 1 : 2); }
+
+template <int MODE>
 __global__ void __launch_bounds__(32) k_replay(TraceParams P) {
   extern __shared__ u64 smem64[];
   const u32 z = blockIdx.x, lane = threadIdx.x;
   const Geom g = P.g;
   const u32 N = P.sliceNodes[z];
-  if (SMEM != (N <= P.smemNodeCap)) return;           // the other instantiation handles this slice
+  if (replay_mode(N) != MODE) return;                 // another instantiation handles this slice
   const u64 n1 = (u64)g.sz + 1;
   const u64 nb = P.nodeBase[z];
   uint2* sstack = reinterpret_cast<uint2*>(smem64);   // REPLAY_STACK entries
-  NodeStore<SMEM> S;
-  S.rec = smem64 + REPLAY_STACK;
+  NodeStore<MODE> S;
+  S.rec = reinterpret_cast<decltype(S.rec)>(smem64 + REPLAY_STACK);
   S.adj = P.nodeAdj + nb;
   S.far = P.seFar + nb * 4;
-  for (u32 i = lane; i < N; i += 32) {
-    const uint4 f = reinterpret_cast<const uint4*>(P.seFar + nb * 4)[i];
-    if (SMEM) {
-      const u64 e0 = f.x == NONE32 ? 0xFFFFull : (u64)(f.x & 0xFFFFu), e1 = f.y == NONE32 ? 0xFFFFull : (u64)(f.y & 0xFFFFu);
-      const u64 e2 = f.z == NONE32 ? 0xFFFFull : (u64)(f.z & 0xFFFFu), e3 = f.w == NONE32 ? 0xFFFFull : (u64)(f.w & 0xFFFFu);
-      S.rec[i] = e0 | (e1 << 16) | (e2 << 32) | (e3 << 48);
-    } else {
-      S.adj[i] = (u8)((f.x != NONE32 ? 1u : 0u) | (f.y != NONE32 ? 2u : 0u) | (f.z != NONE32 ? 4u : 0u) | (f.w != NONE32 ? 8u : 0u));
-    }
-  }
+  for (u32 i = lane; i < N; i += 32) S.init(i, reinterpret_cast<const uint4*>(P.seFar + nb * 4)[i]);
   __syncwarp();
   u32* ev = P.ev + P.offs[0 * n1 + z];
   uint2* gstack = P.stack + P.offs[1 * n1 + z];
@@ -403,7 +438,7 @@ __global__ void __launch_bounds__(32) k_replay(TraceParams P) {
         const u32 begin = nev;
         bool firstT = true, t2 = false, justPopped = false, firstIsB = false;
         u32 t2f = 0, poppedB = 0, adjStart = nodeVertex[start];
-        u64 w = S.load(node);
+        typename NodeStore<MODE>::Rec w = S.load(node);
         for (;;) {
           if (nev + 2 > evCap) { atomicExch(&P.scal[SC_ERROR], 1ull); ok = false; break; }
           const u32 a = S.adjacency(w);
@@ -605,10 +640,6 @@ __global__ void __launch_bounds__(256) k_expand(TraceParams P, u64 totalEvCap) {
 
 static TraceParams make_params(const Geom& g, TraceBufs& T, ull* scal);
 
-static u32 replay_smem_cap() {
-  // node records that fit beside the revisit stack in one SM's shared memory (u16 entries: node ids <= 16382)
-  return 16382u;
-}
 void launch_trace_walk(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes, u32 max_nodes, cudaStream_t st) {
   TraceParams P = make_params(g, T, scal);
   const VGeom vg = P.vg;
@@ -620,16 +651,25 @@ void launch_trace_walk(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes, 
   }
   k_path_walk<<<grid_cap(total_nodes * 4, 256, 8), 256, 0, st>>>(P, total_nodes * 4);
   LAUNCH_CHECK();
-  const u32 cap = replay_smem_cap();
-  const u32 smem_nodes = max_nodes < cap ? max_nodes : cap;
-  P.smemNodeCap = cap;
-  const size_t smem = (size_t)REPLAY_STACK * 8 + (size_t)smem_nodes * 8;
-  if (smem > 48 * 1024)   // per device, cheap: set on every launch that needs it
-    CUDA_CHECK(cudaFuncSetAttribute(k_replay<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(REPLAY_STACK * 8 + (size_t)cap * 8)));
-  k_replay<true><<<g.sz, 32, smem, st>>>(P);
-  LAUNCH_CHECK();
-  if (max_nodes > cap) {
-    k_replay<false><<<g.sz, 32, REPLAY_STACK * 8, st>>>(P);
+  // slices are replayed by the instantiation matching their node count (the others return at once)
+  const size_t stack_bytes = (size_t)REPLAY_STACK * 8;
+  {
+    const u32 n0 = max_nodes < REPLAY_CAP0 ? max_nodes : REPLAY_CAP0;
+    const size_t smem = stack_bytes + (size_t)n0 * 8;
+    if (smem > 48 * 1024)   // per device, cheap: set on every launch that needs it
+      CUDA_CHECK(cudaFuncSetAttribute(k_replay<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(stack_bytes + (size_t)REPLAY_CAP0 * 8)));
+    k_replay<0><<<g.sz, 32, smem, st>>>(P);
+    LAUNCH_CHECK();
+  }
+  if (max_nodes > REPLAY_CAP0) {
+    const u32 n1 = max_nodes < REPLAY_CAP1 ? max_nodes : REPLAY_CAP1;
+    const size_t smem = stack_bytes + (size_t)n1 * 8;
+    CUDA_CHECK(cudaFuncSetAttribute(k_replay<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(stack_bytes + (size_t)REPLAY_CAP1 * 8)));
+    k_replay<1><<<g.sz, 32, smem, st>>>(P);
+    LAUNCH_CHECK();
+  }
+  if (max_nodes > REPLAY_CAP1) {
+    k_replay<2><<<g.sz, 32, stack_bytes, st>>>(P);
     LAUNCH_CHECK();
   }
 }
@@ -708,7 +748,6 @@ static TraceParams make_params(const Geom& g, TraceBufs& T, ull* scal) {
   P.ev = T.ev.as<u32>(); P.evCp = T.evCp.as<u32>(); P.stack = T.stack.as<uint2>(); P.chain = T.chain.as<ChainRec>();
   P.cp = T.cp.as<u8>(); P.sliceInfo = T.sliceInfo.as<u32>();
   P.scal = scal;
-  P.smemNodeCap = 0;
   return P;
 }
 

@@ -65,6 +65,23 @@ def test_random_volumes_against_oracle(ctx, dtype):
             assert np.array_equal(cb.decompress(b).reshape(v.shape), v)
 
 
+def test_dense_crack_graphs(ctx):
+    # noise volumes whose crack graphs have far more nodes than a segmentation's: exercises the 16-bit shared-memory and
+    # the global-memory replay stores (> 8191 / > 16382 nodes per slice) and the global-memory fallback of the band CCL
+    from oracle import oracle as O
+    import crackle_b200 as cb
+    rng = np.random.default_rng(7)
+    vols = [np.asfortranarray(rng.integers(0, 3, (110, 110, 2)).astype(np.uint8)),
+            np.asfortranarray(rng.integers(0, 3, (180, 170, 2)).astype(np.uint16)),
+            np.asfortranarray(rng.integers(0, 2, (512, 520, 1)).astype(np.uint8)),
+            np.asfortranarray(rng.integers(0, 2000, (300, 260, 2)).astype(np.uint32))]
+    for v in vols:
+        for order in (0, 3):
+            b = ctx.compress(v, order)
+            assert b == O.compress(v, order), (v.shape, order)
+            assert np.array_equal(cb.decompress(b).reshape(v.shape), v)
+
+
 def test_edge_shapes(ctx):
     # automated_test.py:151-225, 263-271: empty, black, uniform, arange, 2D, 1D inputs
     from oracle import oracle as O
