@@ -688,7 +688,7 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
     launch_decode_classify(g, dstream, order, D.model.as<u8>(), D, total_words, c->scal, st);
     read_scalars(c);
     if (!c->hscal[SC_FIRST]) {     // no opposite-move run longer than a word (never produced by the encoder)
-      launch_decode_mark(g, dstream, order, D, c->hscal[SC_LAST], c->DV.as<u32>(), c->DH.as<u32>(), c->scal, st);
+      launch_decode_mark(g, dstream, order, D, c->hscal[SC_LAST], total_words, c->DV.as<u32>(), c->DH.as<u32>(), c->scal, st);
       decoded = true;
     }
   }

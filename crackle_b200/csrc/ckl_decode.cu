@@ -227,10 +227,11 @@ void launch_decode_slices(const Geom& g, const u8* stream, const u64* codeOff, i
 //   k_dec_classify per 16-field word: absolute moves (prefix sum mod 4) and the second-of-escape-pair mask S
 //                  (S[i] = opp[i] & ~S[i-1], solved per 32-field window with an add-carry trick); counts events
 //   k_dec_compact  event list: codepoint index | move << 30
-//   k_dec_segsum   per segment (plain moves between two events; the codepoint before an event is the dropped
-//                  first-of-pair): displacement
-//   k_dec_chain    serial over EVENTS only (~4 % of the codepoints): BOC chain starts, revisit stack, positions
-//   k_dec_mark     per segment: walk the moves from the segment start and set the crack bits
+//                  and Q = running displacement of all non-event codepoints (block scan)
+//   k_dec_chain    serial over EVENTS only (~4 % of the codepoints): BOC chain starts, revisit stack, positions;
+//                  the displacement of a segment (plain moves between two events; the codepoint before an event is
+//                  the dropped first-of-pair) is a difference of two Q values
+//   k_dec_mark     one thread per 16-codepoint word: position from Q and the segment start, set the crack bits
 #define L5 0x55555555u
 __device__ __forceinline__ u32 add4(u32 a, u32 b) { return (a ^ b) ^ ((a & b & L5) << 1); }     // per 2-bit field, mod 4
 __device__ __forceinline__ u32 word_prefix4(u32 x) {
@@ -302,15 +303,31 @@ __global__ void __launch_bounds__(32) k_dec_markov(const DecSlice* __restrict__ 
   ncpOut[z] = (u32)n;
 }
 
+// displacement of the non-event fields [0, nf) of a word (moves: 0 up, 1 right, 2 down, 3 left), packed dy * 65536 + dx
+__device__ __forceinline__ int word_disp(u32 M, u32 S, u32 nf) {
+  u32 rm = L5 & ~S;
+  if (nf < 16) rm &= (1u << (2 * nf)) - 1u;
+  const u32 b0 = M & L5, b1 = (M >> 1) & L5;
+  const int dx = __popc(b0 & ~b1 & rm) - __popc(b0 & b1 & rm);
+  const int dy = __popc(b1 & ~b0 & rm) - __popc(~b0 & ~b1 & rm);
+  return dy * 65536 + dx;
+}
+__device__ __forceinline__ int2 unpack_disp(int v) {
+  const int dx = (int)(short)(v & 0xFFFF);
+  return make_int2(dx, (v - dx) >> 16);
+}
+
 __global__ void __launch_bounds__(256) k_dec_classify(const DecSlice* __restrict__ ds, u32 sz, const u8* __restrict__ stream,
                                                        const u32* __restrict__ fields, int order, const u32* __restrict__ ncpIn,
-                                                       u32* __restrict__ Mw, u32* __restrict__ Sw, u32* __restrict__ nevOut, ull* scal) {
+                                                       u32* __restrict__ Mw, u32* __restrict__ Sw, int2* __restrict__ Qw,
+                                                       u32* __restrict__ nevOut, ull* scal) {
   __shared__ u32 sm[33];
   for (u32 z = blockIdx.x; z < sz; z += gridDim.x) {
     const DecSlice d = ds[z];
     const u64 ncp = order > 0 ? (u64)ncpIn[z] : (u64)d.blen * 4;
     const u64 nwords = (ncp + 15) / 16;
     u32 carry = 0, count = 0;
+    int qx = 0, qy = 0;                                       // displacement of all non-event codepoints before the chunk
     for (u64 w0 = 0; w0 < nwords; w0 += blockDim.x) {
       const u64 wi = w0 + threadIdx.x;
       const bool in = wi < nwords;
@@ -320,30 +337,39 @@ __global__ void __launch_bounds__(256) k_dec_classify(const DecSlice* __restrict
       const u32 ex = block_excl_scan(incl >> 30, sm, tot);
       const u32 e = (carry + ex) & 3u;                        // absolute move of the codepoint before this word
       carry = (carry + tot) & 3u;
-      if (!in) continue;
-      const u32 M = add4(incl, e * L5);
-      u32 Oc = opp_flags(M, e);
-      if (wi == 0) Oc &= ~1u;                                 // the first codepoint has no predecessor
-      const u64 rem = ncp - wi * 16;
-      if (rem < 16) Oc &= (1u << (2 * (u32)rem)) - 1u;
-      u32 Op = 0;
-      if (wi > 0) {
-        const u32 inclp = word_prefix4(dec_word(d, stream, fields, order, wi - 1));
-        const u32 ep = (e - (inclp >> 30)) & 3u;
-        Op = opp_flags(add4(inclp, ep * L5), ep);
-        if (wi == 1) Op &= ~1u;
+      u32 M = 0, S = 0;
+      int disp = 0;
+      if (in) {
+        M = add4(incl, e * L5);
+        u32 Oc = opp_flags(M, e);
+        if (wi == 0) Oc &= ~1u;                               // the first codepoint has no predecessor
+        const u64 rem = ncp - wi * 16;
+        if (rem < 16) Oc &= (1u << (2 * (u32)rem)) - 1u;
+        u32 Op = 0;
+        if (wi > 0) {
+          const u32 inclp = word_prefix4(dec_word(d, stream, fields, order, wi - 1));
+          const u32 ep = (e - (inclp >> 30)) & 3u;
+          Op = opp_flags(add4(inclp, ep * L5), ep);
+          if (wi == 1) Op &= ~1u;
+        }
+        if (Op == L5 && (Oc & 1u)) atomicExch(&scal[SC_FIRST], 1ull);    // an opposite-run longer than a word: serial fallback
+        // second-of-pair mask: positions at even distance from the start of their run of `opp` flags
+        u64 comb = (u64)Op | ((u64)Oc << 32);
+        comb |= comb << 1;
+        const u64 st = comb & ~(comb << 2) & 0x5555555555555555ull;
+        const u64 t = comb + (st & 0x1111111111111111ull);
+        const u64 evr = comb & ~t, odr = comb & ~evr;
+        S = (u32)(((evr & 0x3333333333333333ull) | (odr & 0xCCCCCCCCCCCCCCCCull)) >> 32) & L5;
+        Mw[d.wordOff + wi] = M;
+        Sw[d.wordOff + wi] = S;
+        count += __popc(S);
+        disp = word_disp(M, S, rem < 16 ? (u32)rem : 16u);
       }
-      if (Op == L5 && (Oc & 1u)) atomicExch(&scal[SC_FIRST], 1ull);    // an opposite-run longer than a word: serial fallback
-      // second-of-pair mask: positions at even distance from the start of their run of `opp` flags
-      u64 comb = (u64)Op | ((u64)Oc << 32);
-      comb |= comb << 1;
-      const u64 st = comb & ~(comb << 2) & 0x5555555555555555ull;
-      const u64 t = comb + (st & 0x1111111111111111ull);
-      const u64 evr = comb & ~t, odr = comb & ~evr;
-      const u32 S = (u32)(((evr & 0x3333333333333333ull) | (odr & 0xCCCCCCCCCCCCCCCCull)) >> 32) & L5;
-      Mw[d.wordOff + wi] = M;
-      Sw[d.wordOff + wi] = S;
-      count += __popc(S);
+      u32 dtot;
+      const int2 dex = unpack_disp((int)block_excl_scan((u32)disp, sm, dtot));
+      if (in) Qw[d.wordOff + wi] = make_int2(qx + dex.x, qy + dex.y);
+      const int2 dt = unpack_disp((int)dtot);
+      qx += dt.x; qy += dt.y;
     }
     u32 total;
     block_excl_scan(count, sm, total);
@@ -351,9 +377,10 @@ __global__ void __launch_bounds__(256) k_dec_classify(const DecSlice* __restrict
   }
 }
 
+// event list (codepoint index | move << 30) and, per word, the number of events before it
 __global__ void __launch_bounds__(256) k_dec_compact(const DecSlice* __restrict__ ds, u32 sz, int order, const u32* __restrict__ ncpIn,
                                                       const u32* __restrict__ Mw, const u32* __restrict__ Sw,
-                                                      const u64* __restrict__ evOff, u32* __restrict__ evIdx) {
+                                                      const u64* __restrict__ evOff, u32* __restrict__ evIdx, u32* __restrict__ evBaseW) {
   __shared__ u32 sm[33];
   for (u32 z = blockIdx.x; z < sz; z += gridDim.x) {
     const DecSlice d = ds[z];
@@ -367,6 +394,7 @@ __global__ void __launch_bounds__(256) k_dec_compact(const DecSlice* __restrict_
       u32 tot;
       u32 o = carry + block_excl_scan(__popc(S), sm, tot);
       carry += tot;
+      if (wi < nwords) evBaseW[d.wordOff + wi] = o;
       if (S) {
         const u32 M = Mw[d.wordOff + wi];
         while (S) {
@@ -379,42 +407,21 @@ __global__ void __launch_bounds__(256) k_dec_compact(const DecSlice* __restrict_
   }
 }
 
-// displacement of the plain moves in codepoints [lo, hi) of a slice (moves: 0 up, 1 right, 2 down, 3 left)
-__device__ __forceinline__ void seg_sum(const u32* __restrict__ Mz, u32 lo, u32 hi, int& dx, int& dy) {
-  dx = 0; dy = 0;
-  if (lo >= hi) return;
-  for (u32 w = lo >> 4; w <= (hi - 1) >> 4; w++) {
-    const u32 M = Mz[w];
-    const u32 f0 = w == (lo >> 4) ? (lo & 15) : 0, f1 = w == ((hi - 1) >> 4) ? ((hi - 1) & 15) + 1 : 16;
-    u32 rm = L5;
-    rm &= ~((1u << (2 * f0)) - 1u);
-    if (f1 < 16) rm &= (1u << (2 * f1)) - 1u;
-    const u32 b0 = M & L5, b1 = (M >> 1) & L5;
-    dx += __popc(b0 & ~b1 & rm) - __popc(b0 & b1 & rm);
-    dy += __popc(b1 & ~b0 & rm) - __popc(~b0 & ~b1 & rm);
-  }
+// Q(i): displacement of all non-event codepoints before codepoint i of a slice
+__device__ __forceinline__ int2 disp_before(const u32* __restrict__ Mz, const u32* __restrict__ Sz, const int2* __restrict__ Qz, u32 i) {
+  const u32 w = i >> 4, k = i & 15;
+  int2 q = Qz[w];
+  if (k) { const int2 p = unpack_disp(word_disp(Mz[w], Sz[w], k)); q.x += p.x; q.y += p.y; }
+  return q;
 }
 
-__global__ void __launch_bounds__(256) k_dec_segsum(const DecSlice* __restrict__ ds, u32 sz, const u32* __restrict__ Mw,
-                                                     const u64* __restrict__ evOff, const u32* __restrict__ evIdx, u64 totalEv,
-                                                     int2* __restrict__ evSum) {
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < totalEv; j += stride) {
-    u32 lo = 0, hi = sz;
-    while (hi - lo > 1) { const u32 m = (lo + hi) >> 1; if (evOff[m] <= j) lo = m; else hi = m; }
-    const u32 z = lo;
-    const u32 first = j == evOff[z] ? 0u : (evIdx[j - 1] & 0x3FFFFFFFu) + 1;
-    const u32 ei = evIdx[j] & 0x3FFFFFFFu;
-    int dx, dy;
-    seg_sum(Mw + ds[z].wordOff, first, ei ? ei - 1 : 0, dx, dy);
-    evSum[j] = make_int2(dx, dy);
-  }
-}
-
+// serial over the events of a slice: lanes load 32 events and their segment displacements, lane 0 runs the chain /
+// revisit-stack logic.  Outputs per event: start position of its segment and Q at the segment's first codepoint.
 #define DEC_STACK 512
 __global__ void __launch_bounds__(32) k_dec_chain(Geom g, const DecSlice* __restrict__ ds, const u8* __restrict__ stream,
+                                                   const u32* __restrict__ Mw, const u32* __restrict__ Sw, const int2* __restrict__ Qw,
                                                    const u64* __restrict__ evOff, const u32* __restrict__ evIdx,
-                                                   const int2* __restrict__ evSum, int2* __restrict__ segStart, int2* __restrict__ gstack,
+                                                   int2* __restrict__ segStart, int2* __restrict__ segQ, int2* __restrict__ gstack,
                                                    u32* __restrict__ nevUsed, ull* scal) {
   __shared__ int2 sstack[DEC_STACK];
   __shared__ u32 s_ev[32];
@@ -424,6 +431,9 @@ __global__ void __launch_bounds__(32) k_dec_chain(Geom g, const DecSlice* __rest
   const DecSlice d = ds[z];
   const u64 e0 = evOff[z];
   const u32 nev = (u32)(evOff[z + 1] - e0);
+  const u32* Mz = Mw + d.wordOff;
+  const u32* Sz = Sw + d.wordOff;
+  const int2* Qz = Qw + d.wordOff;
   const int xw = ckl_byte_width((u64)g.sx + 1), yw = ckl_byte_width((u64)g.sy + 1);
   // lane 0 state
   BocIter it;
@@ -439,7 +449,16 @@ __global__ void __launch_bounds__(32) k_dec_chain(Geom g, const DecSlice* __rest
   int2* gst = gstack + e0;
   for (u32 base = 0; base < nev; base += 32) {
     const u32 j = base + lane;
-    if (j < nev) { s_ev[lane] = evIdx[e0 + j]; s_sum[lane] = evSum[e0 + j]; }
+    if (j < nev) {
+      const u32 ev = evIdx[e0 + j];
+      const u32 ei = ev & 0x3FFFFFFFu;
+      const u32 first = j ? (evIdx[e0 + j - 1] & 0x3FFFFFFFu) + 1 : 0u;
+      const int2 qf = disp_before(Mz, Sz, Qz, first);
+      const int2 ql = disp_before(Mz, Sz, Qz, ei - 1);       // the codepoint before an event is the dropped first-of-pair
+      s_ev[lane] = ev;
+      s_sum[lane] = make_int2(ql.x - qf.x, ql.y - qf.y);
+      segQ[e0 + j] = qf;
+    }
     __syncwarp();
     if (lane == 0 && !stop) {
       const u32 n = min(32u, nev - base);
@@ -472,60 +491,73 @@ __global__ void __launch_bounds__(32) k_dec_chain(Geom g, const DecSlice* __rest
   if (lane == 0) nevUsed[z] = s_used;
 }
 
-__global__ void __launch_bounds__(256) k_dec_mark(Geom g, const DecSlice* __restrict__ ds, u32 sz, const u32* __restrict__ Mw,
-                                                   const u64* __restrict__ evOff, const u32* __restrict__ evIdx,
-                                                   const int2* __restrict__ segStart, const u32* __restrict__ nevUsed, u64 totalEv,
-                                                   u32* __restrict__ EVall, u32* __restrict__ EHall, ull* scal) {
-  const u64 stride = (u64)gridDim.x * blockDim.x;
+// marking: one thread per 16-codepoint word (uniform work).  Position at the word start = start of the segment the
+// word begins in + (Q(word start) - Q(segment start)); an event inside the word switches to the next segment's start.
+__global__ void __launch_bounds__(256) k_dec_mark(Geom g, const DecSlice* __restrict__ ds, u32 sz, int order, const u32* __restrict__ ncpIn,
+                                                   const u32* __restrict__ Mw, const u32* __restrict__ Sw, const int2* __restrict__ Qw,
+                                                   const u32* __restrict__ evBaseW, const u64* __restrict__ evOff,
+                                                   const int2* __restrict__ segStart, const int2* __restrict__ segQ,
+                                                   const u32* __restrict__ nevUsed, u32* __restrict__ EVall, u32* __restrict__ EHall,
+                                                   ull* scal) {
   const u64 nw = (u64)g.sy * g.W;
   const int sx = (int)g.sx, sy = (int)g.sy;
-  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < totalEv; j += stride) {
-    u32 lo = 0, hi = sz;
-    while (hi - lo > 1) { const u32 m = (lo + hi) >> 1; if (evOff[m] <= j) lo = m; else hi = m; }
-    const u32 z = lo;
-    if (j - evOff[z] >= nevUsed[z]) continue;
-    const u32 first = j == evOff[z] ? 0u : (evIdx[j - 1] & 0x3FFFFFFFu) + 1;
-    const u32 ei = evIdx[j] & 0x3FFFFFFFu;
-    const u32 last = ei ? ei - 1 : 0;                       // exclusive: codepoint ei-1 is the dropped first-of-pair
-    if (first >= last) continue;
-    const u32* Mz = Mw + ds[z].wordOff;
+  for (u32 z = blockIdx.y; z < sz; z += gridDim.y) {
+    const DecSlice d = ds[z];
+    const u64 ncp = order > 0 ? (u64)ncpIn[z] : (u64)d.blen * 4;
+    const u32 nwords = (u32)((ncp + 15) / 16);
+    const u32 used = nevUsed[z];
+    const u64 e0 = evOff[z];
     u32* EV = EVall + (u64)z * nw;
     u32* EH = EHall + (u64)z * nw;
-    int2 p = segStart[j];
-    int x = p.x, y = p.y;
-    bool bad = x < 0 || y < 0 || x > sx || y > sy;
-    u32* pend = nullptr;
-    u32 pmask = 0;
-    u32 M = Mz[first >> 4];
-    for (u32 i = first; i < last && !bad; i++) {
-      if ((i & 15) == 0) M = Mz[i >> 4];
-      const u32 m = (M >> (2 * (i & 15))) & 3u;
-      u32* a = nullptr;
-      u32 bit = 0;
-      if (m == 0) {          // up: vertical crack at column x, row y-1
-        if (y == 0) { bad = true; break; }
-        if (x > 0 && x < sx) { a = EV + (u64)(y - 1) * g.W + (x >> 5); bit = 1u << (x & 31); }
-        y--;
-      } else if (m == 2) {   // down: vertical crack at column x, row y
-        if (y >= sy) { bad = true; break; }
-        if (x > 0 && x < sx) { a = EV + (u64)y * g.W + (x >> 5); bit = 1u << (x & 31); }
-        y++;
-      } else if (m == 3) {   // left: horizontal crack above pixel (x-1, y)
-        if (x == 0) { bad = true; break; }
-        if (y > 0 && y < sy) { a = EH + (u64)y * g.W + ((x - 1) >> 5); bit = 1u << ((x - 1) & 31); }
-        x--;
-      } else {               // right: horizontal crack above pixel (x, y)
-        if (x >= sx) { bad = true; break; }
-        if (y > 0 && y < sy) { a = EH + (u64)y * g.W + (x >> 5); bit = 1u << (x & 31); }
-        x++;
+    for (u32 w = blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += gridDim.x * blockDim.x) {
+      u32 s = evBaseW[d.wordOff + w];
+      if (s >= used) continue;                              // codepoints after the last chain (padding)
+      const u32 M = Mw[d.wordOff + w], S = Sw[d.wordOff + w];
+      const u32 Snext = w + 1 < nwords ? Sw[d.wordOff + w + 1] : 0u;
+      const u32 drop = (S >> 2) | ((Snext & 1u) << 30);     // first-of-pair fields: the field before an event
+      const u32 nf = (u32)min((u64)16, ncp - (u64)w * 16);
+      const int2 ss = segStart[e0 + s], sq = segQ[e0 + s], q = Qw[d.wordOff + w];
+      int x = ss.x + q.x - sq.x, y = ss.y + q.y - sq.y;
+      bool bad = false;
+      u32* pend = nullptr;
+      u32 pmask = 0;
+      for (u32 k = 0; k < nf; k++) {
+        const u32 fb = 1u << (2 * k);
+        if (S & fb) {                                       // event: the next codepoint starts the next segment
+          if (++s >= used) break;
+          const int2 p = segStart[e0 + s];
+          x = p.x; y = p.y;
+          continue;
+        }
+        if (drop & fb) continue;
+        const u32 m = (M >> (2 * k)) & 3u;
+        u32* a = nullptr;
+        u32 bit = 0;
+        if (m == 0) {          // up: vertical crack at column x, row y-1
+          if (y <= 0 || x < 0 || x > sx || y > sy) { bad = true; break; }
+          if (x > 0 && x < sx) { a = EV + (u64)(y - 1) * g.W + (x >> 5); bit = 1u << (x & 31); }
+          y--;
+        } else if (m == 2) {   // down: vertical crack at column x, row y
+          if (y >= sy || y < 0 || x < 0 || x > sx) { bad = true; break; }
+          if (x > 0 && x < sx) { a = EV + (u64)y * g.W + (x >> 5); bit = 1u << (x & 31); }
+          y++;
+        } else if (m == 3) {   // left: horizontal crack above pixel (x-1, y)
+          if (x <= 0 || x > sx || y < 0 || y > sy) { bad = true; break; }
+          if (y > 0 && y < sy) { a = EH + (u64)y * g.W + ((x - 1) >> 5); bit = 1u << ((x - 1) & 31); }
+          x--;
+        } else {               // right: horizontal crack above pixel (x, y)
+          if (x >= sx || x < 0 || y < 0 || y > sy) { bad = true; break; }
+          if (y > 0 && y < sy) { a = EH + (u64)y * g.W + (x >> 5); bit = 1u << (x & 31); }
+          x++;
+        }
+        if (a) {
+          if (a != pend) { if (pend) atomicOr(pend, pmask); pend = a; pmask = 0; }
+          pmask |= bit;
+        }
       }
-      if (a) {
-        if (a != pend) { if (pend) atomicOr(pend, pmask); pend = a; pmask = 0; }
-        pmask |= bit;
-      }
+      if (pend) atomicOr(pend, pmask);
+      if (bad) atomicExch(&scal[SC_ERROR], 11ull);
     }
-    if (pend) atomicOr(pend, pmask);
-    if (bad) atomicExch(&scal[SC_ERROR], 11ull);
   }
 }
 
@@ -563,11 +595,14 @@ void launch_decode_slices_init(const Geom& g, const u8* stream, const u64* codeO
   LAUNCH_CHECK();
 }
 
-// phase 1: moves + event masks + per-slice event counts (exclusive scan into D.evOff, total in scal[SC_LAST])
+// phase 1: moves + event masks + displacement prefixes + per-slice event counts (exclusive scan into D.evOff, total
+// in scal[SC_LAST])
 void launch_decode_classify(const Geom& g, const u8* stream, int order, const u8* model, DecodeBufs& D, u64 total_words, ull* scal,
                             cudaStream_t st) {
   D.Mw.ensure(total_words * 4 + 16);
   D.Sw.ensure(total_words * 4 + 16);
+  D.Qw.ensure(total_words * 8 + 16);
+  D.evBaseW.ensure(total_words * 4 + 16);
   D.nev.ensure((u64)g.sz * 4);
   D.ncp.ensure((u64)g.sz * 4);
   D.evOff.ensure(((u64)g.sz + 1) * 8);
@@ -579,33 +614,36 @@ void launch_decode_classify(const Geom& g, const u8* stream, int order, const u8
     LAUNCH_CHECK();
   }
   k_dec_classify<<<dec_grid(g.sz, 1, 8), 256, 0, st>>>(ds, g.sz, stream, D.fields.as<u32>(), order, D.ncp.as<u32>(), D.Mw.as<u32>(),
-                                                       D.Sw.as<u32>(), D.nev.as<u32>(), scal);
+                                                       D.Sw.as<u32>(), D.Qw.as<int2>(), D.nev.as<u32>(), scal);
   LAUNCH_CHECK();
   launch_exscan_u32_u64(D.nev.as<u32>(), g.sz, 1, D.evOff.as<u64>(), &scal[SC_LAST], 0, st);
 }
 
-// phase 2 (total_events known on the host): event list, segment sums, chain pass, marking
-void launch_decode_mark(const Geom& g, const u8* stream, int order, DecodeBufs& D, u64 total_events, u32* EV, u32* EH, ull* scal,
-                        cudaStream_t st) {
+// phase 2 (total_events known on the host): event list, chain pass, marking
+void launch_decode_mark(const Geom& g, const u8* stream, int order, DecodeBufs& D, u64 total_events, u64 total_words, u32* EV, u32* EH,
+                        ull* scal, cudaStream_t st) {
   CUDA_CHECK(cudaMemsetAsync(EV, 0, g.words() * 4, st));
   CUDA_CHECK(cudaMemsetAsync(EH, 0, g.words() * 4, st));
   if (!total_events) return;
   D.evIdx.ensure(total_events * 4 + 16);
-  D.evSum.ensure(total_events * 8 + 16);
+  D.segQ.ensure(total_events * 8 + 16);
   D.segStart.ensure(total_events * 8 + 16);
   D.gstack.ensure(total_events * 8 + 16);
   const DecSlice* ds = D.slices.as<DecSlice>();
   k_dec_compact<<<dec_grid(g.sz, 1, 8), 256, 0, st>>>(ds, g.sz, order, D.ncp.as<u32>(), D.Mw.as<u32>(), D.Sw.as<u32>(), D.evOff.as<u64>(),
-                                                      D.evIdx.as<u32>());
+                                                      D.evIdx.as<u32>(), D.evBaseW.as<u32>());
   LAUNCH_CHECK();
-  k_dec_segsum<<<dec_grid(total_events, 256, 8), 256, 0, st>>>(ds, g.sz, D.Mw.as<u32>(), D.evOff.as<u64>(), D.evIdx.as<u32>(), total_events,
-                                                               D.evSum.as<int2>());
+  k_dec_chain<<<g.sz, 32, 0, st>>>(g, ds, stream, D.Mw.as<u32>(), D.Sw.as<u32>(), D.Qw.as<int2>(), D.evOff.as<u64>(), D.evIdx.as<u32>(),
+                                   D.segStart.as<int2>(), D.segQ.as<int2>(), D.gstack.as<int2>(), D.nevUsed.as<u32>(), scal);
   LAUNCH_CHECK();
-  k_dec_chain<<<g.sz, 32, 0, st>>>(g, ds, stream, D.evOff.as<u64>(), D.evIdx.as<u32>(), D.evSum.as<int2>(), D.segStart.as<int2>(),
-                                   D.gstack.as<int2>(), D.nevUsed.as<u32>(), scal);
-  LAUNCH_CHECK();
-  k_dec_mark<<<dec_grid(total_events, 256, 8), 256, 0, st>>>(g, ds, g.sz, D.Mw.as<u32>(), D.evOff.as<u64>(), D.evIdx.as<u32>(),
-                                                             D.segStart.as<int2>(), D.nevUsed.as<u32>(), total_events, EV, EH, scal);
+  const u64 per_slice = (total_words + g.sz - 1) / g.sz;
+  u32 gx = (u32)((per_slice + 255) / 256);
+  if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
+  k_dec_mark<<<dim3(gx, g.sz < 65535u ? g.sz : 65535u), 256, 0, st>>>(g, ds, g.sz, order, D.ncp.as<u32>(), D.Mw.as<u32>(), D.Sw.as<u32>(),
+                                                                       D.Qw.as<int2>(), D.evBaseW.as<u32>(), D.evOff.as<u64>(),
+                                                                       D.segStart.as<int2>(), D.segQ.as<int2>(), D.nevUsed.as<u32>(),
+                                                                       EV, EH, scal);
   LAUNCH_CHECK();
 }
 

@@ -101,9 +101,9 @@ struct DecSlice { u64 code, body, wordOff; u32 blen, isz; };
 struct DecodeBufs {
   DBuf slices, wordOff;   // DecSlice x szr, word capacity offsets u64 x (szr+1)
   DBuf fields;      // order > 0: packed 2-bit difference fields (u32 per 16)
-  DBuf Mw, Sw;      // per 16-codepoint word: absolute moves, second-of-pair mask
+  DBuf Mw, Sw, Qw, evBaseW;   // per 16-codepoint word: absolute moves, event mask, displacement prefix, events before
   DBuf nev, ncp, evOff, nevUsed;   // per slice
-  DBuf evIdx, evSum, segStart, gstack;   // per event
+  DBuf evIdx, segQ, segStart, gstack;   // per event
   DBuf codeOff;     // u64 x (szr+1): absolute offsets of each decoded slice's crack code inside the stream
   DBuf keyBase;     // u64 x szr: first key index of each decoded slice
   DBuf storedNz;    // u32 x szr
@@ -117,8 +117,8 @@ void launch_decode_slices(const Geom& g, const u8* stream, const u64* codeOff, i
 void launch_decode_slices_init(const Geom& g, const u8* stream, const u64* codeOff, const u64* wordOff, DecSlice* out, ull* scal, cudaStream_t st);
 void launch_decode_classify(const Geom& g, const u8* stream, int order, const u8* model, DecodeBufs& D, u64 total_words, ull* scal,
                             cudaStream_t st);
-void launch_decode_mark(const Geom& g, const u8* stream, int order, DecodeBufs& D, u64 total_events, u32* EV, u32* EH, ull* scal,
-                        cudaStream_t st);
+void launch_decode_mark(const Geom& g, const u8* stream, int order, DecodeBufs& D, u64 total_events, u64 total_words, u32* EV, u32* EH,
+                        ull* scal, cudaStream_t st);
 void launch_planes_from_cracks(const Geom& g, int permissible, u32* EV, u32* EH, cudaStream_t st);
 void launch_run_labels(const Geom& g, const CclBufs& B, const u8* stream, u64 uniq_off, u64 keys_off, u64 n_uniq,
                        u64 n_keys_total, int stored_width, int key_width, const u64* keyBase, u64* runLabel, cudaStream_t st);
