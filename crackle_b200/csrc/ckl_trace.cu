@@ -278,15 +278,24 @@ __device__ __forceinline__ bool se_step(const uint4* __restrict__ vw, u32 Wv, u3
   return false;
 }
 
-// 3b. one thread per (node, direction)
-__global__ void __launch_bounds__(256) k_path_walk(TraceParams P, u64 nslots) {
+// 3b. super-edges: a (node, direction) slot with an edge follows degree-2 vertices to the far node and records
+// the result at BOTH ends.  Pass 0 walks the right / down slots; pass 1 walks the left / up slots that pass 0 did
+// not already fill from the other end (most super-edges leave one node rightwards or downwards and arrive at the
+// other from the left or from above, so almost every path is walked once instead of twice).
+#define SE_UNSET 0xFEFEFEFEu
+template <int PASS>
+__global__ void __launch_bounds__(256) k_path_walk(TraceParams P, u64 nhalf) {
   const VGeom vg = P.vg;
   const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += stride) {
-    const u64 gnode = s >> 2;
-    u32 kk = (u32)(s & 3);
+  const u32 limit = 2u * vg.sxe * vg.sye + 8u;
+  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < nhalf; t += stride) {
+    const u64 gnode = t >> 1;
+    const u32 k0 = (u32)(t & 1) * 2 + PASS;              // pass 0: right, down; pass 1: left, up
+    const u64 s = gnode * 4 + k0;
+    u32 kk = k0;
     const u32 z = slice_of(P.nodeBase, P.g.sz, gnode);
-    const uint4* vw = P.VW + (u64)z * vg.sye * vg.Wv;
+    const u64 rowz = (u64)z * vg.sye;
+    const uint4* vw = P.VW + rowz * vg.Wv;
     const u32 v = P.nodeVertex[gnode];
     u32 y = v / vg.sxe, x = v - y * vg.sxe;
     uint4 word = __ldg(vw + (u64)y * vg.Wv + (x >> 5));
@@ -297,15 +306,22 @@ __global__ void __launch_bounds__(256) k_path_walk(TraceParams P, u64 nslots) {
     else if (kk == 3) has = (word.z >> b) & 1u;
     else has = b ? ((word.x >> (b - 1)) & 1u) : (x ? (__ldg(vw + (u64)y * vg.Wv + (x >> 5) - 1).x >> 31) : 0u);
     if (!has) { P.seFar[s] = NONE32; P.seLen[s] = 0; continue; }
+    if (PASS == 1 && P.seFar[s] != SE_UNSET) continue;   // filled from the other end
     u32 len = 1;
-    const u32 limit = 2u * vg.sxe * vg.sye + 8u;
+    bool ok = true;
     while (!se_step(vw, vg.Wv, x, y, kk, word)) {
-      if (++len > limit) { atomicExch(&P.scal[SC_ERROR], 4ull); break; }
+      if (++len > limit) { atomicExch(&P.scal[SC_ERROR], 4ull); ok = false; break; }
     }
-    const u64 row = (u64)z * vg.sye + y;
+    if (!ok) { P.seFar[s] = NONE32; P.seLen[s] = 0; continue; }
+    const u64 row = rowz + y;
     const u32 far = P.rowBase[row] + P.nodePrefix[row * vg.Wv + (x >> 5)] + __popc(word.w & ((1u << (x & 31)) - 1u));
-    P.seFar[s] = (far << 2) | (kk ^ 1u);
+    const u32 fk = kk ^ 1u;
+    const u64 nb = P.nodeBase[z];
+    P.seFar[s] = (far << 2) | fk;
     P.seLen[s] = len;
+    const u64 twin = (nb + far) * 4 + fk;
+    P.seFar[twin] = ((u32)(gnode - nb) << 2) | k0;
+    P.seLen[twin] = len;
   }
 }
 
@@ -436,20 +452,22 @@ __global__ void __launch_bounds__(32) k_replay(TraceParams P) {
       else {
         u32 node = start, sp = 0, nB = 0;
         const u32 begin = nev;
+        u32* evp = ev + nev;                                   // events are appended through a bumped pointer
+        u32* const evLimit = ev + evCap - 2;
         bool firstT = true, t2 = false, justPopped = false, firstIsB = false;
         u32 t2f = 0, poppedB = 0, adjStart = nodeVertex[start];
         typename NodeStore<MODE>::Rec w = S.load(node);
         for (;;) {
-          if (nev + 2 > evCap) { atomicExch(&P.scal[SC_ERROR], 1ull); ok = false; break; }
+          if (evp > evLimit) { atomicExch(&P.scal[SC_ERROR], 1ull); ok = false; break; }
           const u32 a = S.adjacency(w);
           if (a == 0) {
             // a 't': dead end after a move, or -- directly after a pop -- a spurious branch (remove_spurious_branches)
             if (firstT) {
               firstT = false;
-              if (nB == 1 && firstIsB) { t2 = true; t2f = nev - begin; adjStart = nodeVertex[node]; }   // remove_initial_branch applies
+              if (nB == 1 && firstIsB) { t2 = true; t2f = (u32)(evp - ev) - begin; adjStart = nodeVertex[node]; }   // remove_initial_branch applies
             }
-            if (justPopped && !(t2 && poppedB == begin)) { ev[poppedB] = (u32)EV_S << 30; ev[nev++] = (u32)EV_S << 30; }
-            else ev[nev++] = (u32)EV_T << 30;
+            if (justPopped && !(t2 && poppedB == begin)) { ev[poppedB] = (u32)EV_S << 30; *evp++ = (u32)EV_S << 30; }
+            else *evp++ = (u32)EV_T << 30;
             if (sp == 0) break;
             --sp;
             const uint2 e = sp < REPLAY_STACK ? sstack[sp] : gstack[sp - REPLAY_STACK];
@@ -462,17 +480,19 @@ __global__ void __launch_bounds__(32) k_replay(TraceParams P) {
           justPopped = false;
           if (a & (a - 1)) {                                  // popcount > 1: branch point
             if (sp >= stackCap + REPLAY_STACK) { atomicExch(&P.scal[SC_ERROR], 2ull); ok = false; break; }
-            const uint2 e = make_uint2(node, nev);
+            const u32 bi = (u32)(evp - ev);
+            const uint2 e = make_uint2(node, bi);
             if (sp < REPLAY_STACK) sstack[sp] = e; else gstack[sp - REPLAY_STACK] = e;
             sp++;
-            if (nev == begin) firstIsB = true;
-            ev[nev++] = (u32)EV_B << 30;
+            if (bi == begin) firstIsB = true;
+            *evp++ = (u32)EV_B << 30;
             nB++;
           }
           const u32 k = __ffs(a) - 1;                          // priority: right, left, down, up
-          ev[nev++] = ((u32)EV_E << 30) | (node * 4 + k);
+          *evp++ = ((u32)EV_E << 30) | (node * 4 + k);
           S.take(node, k, w);
         }
+        nev = (u32)(evp - ev);
         ChainRec& rec = chains[nch];
         rec.adjStart = adjStart;
         rec.symBegin = begin;
@@ -570,70 +590,98 @@ __global__ void __launch_bounds__(256) k_event_post(TraceParams P) {
 // direction index -> codepoint: right 1, left 3, down 2, up 0  (crackcodes.hpp:20-26)
 __device__ __forceinline__ u8 dir_code(u32 kk) { return (u8)((0x0231u >> (4 * kk)) & 0xFu); }
 
-__global__ void __launch_bounds__(256) k_expand(TraceParams P, u64 totalEvCap) {
+// grid = (chunks, slices); lanes fetch the next event of their warp's chunk as soon as their current super-edge
+// is written out (same lane-refill scheme as k_path_walk).
+#define EX_CHUNK 256u
+__global__ void __launch_bounds__(256) k_expand(TraceParams P) {
   const Geom g = P.g;
   const VGeom vg = P.vg;
   const u64 n1 = (u64)g.sz + 1;
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 gi = (u64)blockIdx.x * blockDim.x + threadIdx.x; gi < totalEvCap; gi += stride) {
-    const u32 z = slice_of(P.offs, g.sz, gi);
-    const u32 i = (u32)(gi - P.offs[z]);
-    // sliceInfo[0] holds ncp by now; the event count of the slice is the end of its last chain
+  const u32 lane = threadIdx.x & 31;
+  const u32 ltmask = (1u << lane) - 1u;
+  for (u32 z = blockIdx.y; z < g.sz; z += gridDim.y) {
     const u32 nch = P.sliceInfo[(u64)z * 4 + 1];
     if (!nch) continue;
     const ChainRec* chains = P.chain + P.offs[2 * n1 + z];
-    if (i >= chains[nch - 1].symEnd) continue;
+    const u32 nev = chains[nch - 1].symEnd;            // sliceInfo[0] holds ncp by now; events end with the last chain
     const u32* ev = P.ev + P.offs[z];
-    const u32 e = ev[i], t = e >> 30;
-    if (t == EV_S) continue;
     const u32* pre = P.evCp + P.offs[z] + z;
-    const ChainRec& c = chains[chain_of(chains, nch, i)];
-    u8* out = P.cp + P.offs[3 * n1 + z] + c.outBase;
-    const u32 rel = pre[i] - pre[c.symBegin];
+    u8* cpz = P.cp + P.offs[3 * n1 + z];
     const u64 nb = P.nodeBase[z];
-    if (t == EV_E) {
-      const u32 slot = e & 0x3FFFFFFFu;
-      u32 kk = slot & 3u;
-      const u32 len = P.seLen[nb * 4 + slot];
-      const u32 v = P.nodeVertex[nb + (slot >> 2)];
-      u32 y = v / vg.sxe, x = v - y * vg.sxe;
-      const uint4* vw = P.VW + (u64)z * vg.sye * vg.Wv;
+    const uint4* vw = P.VW + (u64)z * vg.sye * vg.Wv;
+    const u32 nchunks = (nev + EX_CHUNK - 1) / EX_CHUNK;
+    for (u32 chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); chunk < nchunks; chunk += gridDim.x * (blockDim.x >> 5)) {
+      u32 next = chunk * EX_CHUNK;
+      const u32 end = min(nev, next + EX_CHUNK);
+      bool active = false;
+      u32 x = 0, y = 0, kk = 0, left = 0, flip = 0;
+      int step = 1;
+      u8* o = nullptr;
       uint4 word;
-      if (c.t2f && i < c.symBegin + c.t2f) {
-        // inside a removed initial branch: the move run is reversed and every move flipped
-        const u32 fcp = pre[c.symBegin + c.t2f] - pre[c.symBegin];
-        u8* o = out + (fcp - 1 - rel);
-        for (u32 q = 0; q < len; q++) { *o-- = dir_code(kk ^ 1u); if (q + 1 < len) se_step(vw, vg.Wv, x, y, kk, word); }
-      } else {
-        u8* o = out + rel;
-        for (u32 q = 0; q < len; q++) { *o++ = dir_code(kk); if (q + 1 < len) se_step(vw, vg.Wv, x, y, kk, word); }
+      for (;;) {
+        const u32 idle = __ballot_sync(FULL_MASK, !active);
+        if (idle) {
+          const u32 i = next + __popc(idle & ltmask);
+          if (!active && i < end) {
+            const u32 e = ev[i], t = e >> 30;
+            if (t != EV_S) {
+              const ChainRec& c = chains[chain_of(chains, nch, i)];
+              u8* out = cpz + c.outBase;
+              const u32 rel = pre[i] - pre[c.symBegin];
+              if (t == EV_E) {
+                const u32 slot = e & 0x3FFFFFFFu;
+                kk = slot & 3u;
+                left = P.seLen[nb * 4 + slot];
+                const u32 v = P.nodeVertex[nb + (slot >> 2)];
+                y = v / vg.sxe; x = v - y * vg.sxe;
+                if (c.t2f && i < c.symBegin + c.t2f) {
+                  // inside a removed initial branch: the move run is reversed and every move flipped
+                  const u32 fcp = pre[c.symBegin + c.t2f] - pre[c.symBegin];
+                  o = out + (fcp - 1 - rel); step = -1; flip = 1;
+                } else { o = out + rel; step = 1; flip = 0; }
+                active = left != 0;
+              } else {
+                // 'b' / 't': the pair depends on the previous kept symbol; kept 't's in between alternate
+                u32 tcount = 0, j = i;
+                int prev = -1;                                        // previous kept move (direction index), -1 = none
+                while (j > c.symBegin) {
+                  j--;
+                  const u32 q = ev[j], qt = q >> 30;
+                  if (qt == EV_S) continue;
+                  if (qt == EV_T) { tcount++; continue; }
+                  if (qt == EV_B) break;                              // cannot happen (a 'b' is always followed by a move)
+                  if (c.t2f && j < c.symBegin + c.t2f) prev = (int)((ev[c.symBegin + 1] & 3u) ^ 1u);   // reversed run ends with flip(first move)
+                  else prev = (int)((P.seFar[nb * 4 + (q & 0x3FFFFFFFu)] & 3u) ^ 1u);                  // last move = opposite of arrival dir
+                  break;
+                }
+                u8* ob = out + rel;
+                if (t == EV_B) {
+                  // (UP,DOWN) unless first symbol of the chain or the previous codepoint is DOWN -> (LEFT,RIGHT)
+                  const bool alt = (i == c.symBegin) || (tcount == 0 && prev == 2);
+                  ob[0] = alt ? 3 : 0;
+                  ob[1] = alt ? 1 : 2;
+                } else {
+                  // (DOWN,UP) unless the previous codepoint is UP -> (RIGHT,LEFT); consecutive 't's alternate
+                  const bool alt = ((prev == 3) ? 1u : 0u) ^ (tcount & 1u);
+                  ob[0] = alt ? 1 : 2;
+                  ob[1] = alt ? 3 : 0;
+                }
+              }
+            }
+          }
+          next += __popc(idle);
+        }
+        if (!__any_sync(FULL_MASK, active)) {
+          if (next >= end) break;
+          continue;
+        }
+        if (active) {
+          *o = dir_code(kk ^ flip);
+          o += step;
+          if (--left == 0) active = false;
+          else se_step(vw, vg.Wv, x, y, kk, word);
+        }
       }
-      continue;
-    }
-    // 'b' / 't': the pair depends on the previous kept symbol; kept 't's in between alternate
-    u32 tcount = 0, j = i;
-    int prev = -1;                                        // previous kept move (direction index), -1 = none
-    while (j > c.symBegin) {
-      j--;
-      const u32 q = ev[j], qt = q >> 30;
-      if (qt == EV_S) continue;
-      if (qt == EV_T) { tcount++; continue; }
-      if (qt == EV_B) break;                              // cannot happen (a 'b' is always followed by a move)
-      if (c.t2f && j < c.symBegin + c.t2f) prev = (int)((ev[c.symBegin + 1] & 3u) ^ 1u);    // reversed run ends with flip(first move)
-      else prev = (int)((P.seFar[nb * 4 + (q & 0x3FFFFFFFu)] & 3u) ^ 1u);                   // last move = opposite of arrival dir
-      break;
-    }
-    u8* o = out + rel;
-    if (t == EV_B) {
-      // (UP,DOWN) unless first symbol of the chain or the previous codepoint is DOWN -> (LEFT,RIGHT)
-      const bool alt = (i == c.symBegin) || (tcount == 0 && prev == 2);
-      o[0] = alt ? 3 : 0;
-      o[1] = alt ? 1 : 2;
-    } else {
-      // (DOWN,UP) unless the previous codepoint is UP -> (RIGHT,LEFT); consecutive 't's alternate
-      const bool alt = ((prev == 3) ? 1u : 0u) ^ (tcount & 1u);
-      o[0] = alt ? 1 : 2;
-      o[1] = alt ? 3 : 0;
     }
   }
 }
@@ -649,7 +697,10 @@ void launch_trace_walk(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes, 
     CUDA_CHECK(cudaMemsetAsync(T.sliceInfo.p, 0, (u64)g.sz * 16, st));
     return;
   }
-  k_path_walk<<<grid_cap(total_nodes * 4, 256, 8), 256, 0, st>>>(P, total_nodes * 4);
+  CUDA_CHECK(cudaMemsetAsync(T.seFar.p, 0xFE, total_nodes * 16, st));     // SE_UNSET
+  k_path_walk<0><<<grid_cap(total_nodes * 2, 256, 8), 256, 0, st>>>(P, total_nodes * 2);
+  LAUNCH_CHECK();
+  k_path_walk<1><<<grid_cap(total_nodes * 2, 256, 8), 256, 0, st>>>(P, total_nodes * 2);
   LAUNCH_CHECK();
   // slices are replayed by the instantiation matching their node count (the others return at once)
   const size_t stack_bytes = (size_t)REPLAY_STACK * 8;
@@ -678,7 +729,11 @@ void launch_trace_post(const Geom& g, TraceBufs& T, ull* scal, u64 total_ev_cap,
   k_event_post<<<grid_cap(g.sz, 1, 8), 256, 0, st>>>(P);
   LAUNCH_CHECK();
   if (total_ev_cap) {
-    k_expand<<<grid_cap(total_ev_cap, 256, 8), 256, 0, st>>>(P, total_ev_cap);
+    const u64 per_slice = (total_ev_cap + g.sz - 1) / g.sz;
+    u32 gx = (u32)((per_slice + 8 * EX_CHUNK - 1) / (8 * EX_CHUNK));
+    if (gx > 32) gx = 32;
+    if (gx < 1) gx = 1;
+    k_expand<<<dim3(gx, g.sz < 65535u ? g.sz : 65535u), 256, 0, st>>>(P);
     LAUNCH_CHECK();
   }
   // total codepoints (for the "all slices empty" rule, crackle.hpp:107-118)
