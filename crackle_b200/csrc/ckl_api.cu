@@ -152,7 +152,13 @@ extern "C" int ckl_ctx_create(int device, ckl_ctx** out) {
     CUDA_CHECK(cudaSetDevice(device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_st, cudaStreamNonBlocking));
     c->st = c->own_st;
-    CUDA_CHECK(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
+    {
+      // the tracing chain is the critical path of compress: its side stream gets the highest priority so its blocks
+      // are scheduled ahead of the concurrent CCL / label kernels
+      int lo = 0, hi = 0;
+      CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CUDA_CHECK(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, hi));
+    }
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     crc_build_tables(c->htab);
