@@ -684,7 +684,7 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
     wordOff[szr] = tw;
   }
   const u64 total_words = wordOff[szr];
-  c->prof.begin("decode_slices", st);
+  c->prof.begin("d_decode", st);
   bool decoded = false;
   if (parallel_ok) {
     D.slices.ensure(szr * sizeof(DecSlice));
@@ -705,7 +705,7 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   }
   c->prof.end(st);
   launch_planes_from_cracks(g, (int)h.crack_format, c->DV.as<u32>(), c->DH.as<u32>(), st);
-  STAGE(c, "ccl_count", launch_ccl_count(g, c->DV.as<u32>(), c->ccl, c->scal, st));
+  STAGE(c, "d_ccl_count", launch_ccl_count(g, c->DV.as<u32>(), c->ccl, c->scal, st));
   read_scalars(c);
   if (c->hscal[SC_ERROR]) {
     if (h.crack_format) throw CklError(CKL_ERR_STREAM, "crackle: decode_permissible_crack_code: index out of range.");
@@ -714,13 +714,13 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   const u64 runs = c->hscal[SC_RUNS];
   c->ccl.parent.ensure(runs * 4); c->ccl.runStart.ensure(runs * 4); c->ccl.compRank.ensure(runs * 4);
   c->ccl.runComp.ensure(runs * 4); c->ccl.compPix.ensure(runs * 4);
-  STAGE(c, "ccl_solve", launch_ccl_solve(g, c->DV.as<u32>(), c->DH.as<u32>(), c->ccl, c->dtab, c->scal, st));
+  STAGE(c, "d_ccl_solve", launch_ccl_solve(g, c->DV.as<u32>(), c->DH.as<u32>(), c->ccl, c->dtab, c->scal, st));
   const u32 init_term = gf_mul(gf_xpow32(c->htab.pw, (u32)g.sxy), 0xFFFFFFFFu);
   D.runLabel.ensure(runs * 8 + 8);
   CclDecodeSrc dsrc;
   dsrc.uniq = dstream + uniq_off; dsrc.keys = dstream + keys_off; dsrc.n_uniq = nu; dsrc.n_keys = n_keys; dsrc.sw = sw; dsrc.kw = kw;
   dsrc.keyBase = D.keyBase.as<u64>(); dsrc.runLabel = D.runLabel.as<u64>();
-  STAGE(c, "ccl_finish", launch_ccl_finish(g, c->ccl, runs, c->dtab, init_term, &dsrc, st));
+  STAGE(c, "d_ccl_finish", launch_ccl_finish(g, c->ccl, runs, c->dtab, init_term, &dsrc, st));
   if (h.format_version > 0) {   // crackle.hpp:599-611
     k_crc_compare<<<(g.sz + 255) / 256, 256, 0, st>>>(c->ccl.sliceCrc.as<u32>(), dstream + num_bytes - 4ull * h.sz + 4ull * (u64)z_start, g.sz, c->scal);
     LAUNCH_CHECK();
@@ -737,7 +737,7 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   }
   void* dout = out;
   if (!out_on_device) { c->out_dev.ensure(voxels * (u64)ow); dout = c->out_dev.p; }
-  STAGE(c, "paint", launch_paint(g, c->DV.as<u32>(), c->ccl, D.runLabel.as<u64>(), ow, has_label, label, (int)h.fortran_order, dout, st));
+  STAGE(c, "d_paint", launch_paint(g, c->DV.as<u32>(), c->ccl, D.runLabel.as<u64>(), ow, has_label, label, (int)h.fortran_order, dout, st));
   if (!out_on_device) CUDA_CHECK(cudaMemcpyAsync(out, dout, voxels * (u64)ow, cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
   c->prof.collect();

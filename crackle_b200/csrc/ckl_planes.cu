@@ -28,11 +28,42 @@ template <typename T> __device__ __forceinline__ T shfl_idx(T v, u32 src) {
   else return (T)__shfl_sync(FULL_MASK, (u32)v, src);
 }
 
+// one 32-pixel column step of a strip: FULL = all RS rows present (no per-row bounds tests)
+template <typename T, int RS, bool FULL>
+__device__ __forceinline__ void edges_column(const T* __restrict__ rowp, u64 sx, u32 nr, bool inx, bool has_left, bool top0, bool first_col,
+                                             u32 lane, u32 wsel, T& up, u64& orall, u32& neq, u32 (&dvacc)[RS], u32 (&dhacc)[RS]) {
+  T cur[RS], lf[RS];
+#pragma unroll
+  for (int r = 0; r < RS; r++) {
+    cur[r] = 0; lf[r] = 0;
+    if ((FULL || r < (int)nr) && inx) {
+      cur[r] = rowp[(u64)r * sx];
+      if (lane == 0 && (has_left || r > 0)) lf[r] = rowp[(u64)r * sx - 1];     // flat predecessor (previous word / previous row)
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RS; r++) {
+    if (FULL || r < (int)nr) {
+      const T v = cur[r];
+      T l = shfl_up1<T>(v);
+      if (lane == 0) l = lf[r];
+      u32 vb = __ballot_sync(FULL_MASK, inx && v != l);
+      u32 hb = __ballot_sync(FULL_MASK, inx && v != up);
+      if (r == 0 && top0) hb = 0;
+      if (lane == 0 && r == 0 && !has_left) vb |= 1u;      // flat index 0 has no predecessor: not an equal pair
+      neq += __popc(vb);
+      if (first_col) vb &= ~1u;
+      if (lane == wsel) { dvacc[r] = vb; dhacc[r] = hb; }
+      up = v;
+      orall |= (u64)v;
+    }
+  }
+}
+
 template <typename T, int RS>
 __global__ void __launch_bounds__(256) k_edges(const T* __restrict__ L, Geom g, u32* __restrict__ DV,
                                                 u32* __restrict__ DH, ull* scal) {
   const u32 lane = threadIdx.x & 31;
-  const u32 rot = (lane + 31) & 31;
   const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
   const u32 ntile = (g.sy + RS - 1) / RS;
   const u64 items = (u64)g.sz * ntile;
@@ -42,47 +73,19 @@ __global__ void __launch_bounds__(256) k_edges(const T* __restrict__ L, Geom g, 
     const u32 y0 = tile * RS;
     const u32 nr = min((u32)RS, g.sy - y0);
     const T* base = L + (u64)z * g.sxy + (u64)y0 * g.sx;
-    T prev31[RS];
+    const bool top0 = y0 == 0, has_prev = (z | y0) != 0;    // has_prev: row y0 has a flat predecessor at x = 0
     u32 dvacc[RS], dhacc[RS];
 #pragma unroll
-    for (int r = 0; r < RS; r++) {
-      prev31[r] = 0;
-      dvacc[r] = dhacc[r] = 0;
-      if (lane == 31 && r < (int)nr && (z | (y0 + r)) != 0) prev31[r] = base[(u64)r * g.sx - 1];   // previous flat voxel of (0, y)
-    }
+    for (int r = 0; r < RS; r++) dvacc[r] = dhacc[r] = 0;
+    u32 neq = 0;
     for (u32 w = 0; w < g.W; w++) {
       const u32 x = w * 32 + lane;
       const bool inx = x < g.sx;
-      T cur[RS];
-#pragma unroll
-      for (int r = 0; r < RS; r++) {
-        cur[r] = 0;
-        if (r < (int)nr && inx) cur[r] = base[(u64)r * g.sx + x];
-      }
       T up = 0;
-      if (y0 > 0 && inx) up = *(base - g.sx + x);
-      const u32 valid = __ballot_sync(FULL_MASK, inx);
-      const u32 nvalid = __popc(valid);
-#pragma unroll
-      for (int r = 0; r < RS; r++) {
-        if (r < (int)nr) {
-          const T v = cur[r];
-          const T t = lane == 31 ? prev31[r] : v;
-          const T l = shfl_idx<T>(t, rot);
-          prev31[r] = v;
-          u32 vb = __ballot_sync(FULL_MASK, inx && v != l);
-          u32 hb = __ballot_sync(FULL_MASK, inx && v != up);
-          if (y0 + r == 0) hb = 0;
-          pairs += nvalid - __popc(vb);
-          if (w == 0) {
-            if ((z | (y0 + r)) == 0 && !(vb & 1u)) pairs--;   // flat index 0 has no predecessor
-            vb &= ~1u;
-          }
-          if (lane == (w & 31)) { dvacc[r] = vb; dhacc[r] = hb; }
-          up = v;
-          orall |= (u64)v;
-        }
-      }
+      if (!top0 && inx) up = *(base - g.sx + x);
+      const bool has_left = w > 0 || has_prev;
+      if (nr == RS) edges_column<T, RS, true>(base + x, g.sx, nr, inx, has_left, top0, w == 0, lane, w & 31, up, orall, neq, dvacc, dhacc);
+      else edges_column<T, RS, false>(base + x, g.sx, nr, inx, has_left, top0, w == 0, lane, w & 31, up, orall, neq, dvacc, dhacc);
       if ((w & 31) == 31 || w == g.W - 1) {
         const u32 ws = (w & ~31u) + lane;
         if (ws <= w) {
@@ -97,6 +100,8 @@ __global__ void __launch_bounds__(256) k_edges(const T* __restrict__ L, Geom g, 
         }
       }
     }
+    // pixel_pairs of the strip: voxels minus unequal flat neighbours (neq counts lane-0's ballot copy: warp-uniform)
+    pairs += (u64)g.sx * nr - neq;
   }
   // block reduction -> two atomics per block (pairs is warp-uniform: lane 0 carries it)
   __shared__ u64 s_or[8], s_pr[8];
