@@ -59,9 +59,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples inside the timed window [t0, t1]; when the window is shorter than the sampling period the samples
+        taken since the sampler started (warm-up + timed steps, the same kernels back to back) are used and `window` says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -71,7 +73,12 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        window = "timed"
+        rows = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= t1 + 0.12)]
+        if len(rows) < 2:
+            rows, window = [r for (_, r) in self.rows], "warmup+timed"
+        self.window = window
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
                 continue
@@ -83,7 +90,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def ref_times(vol, order, reps):
@@ -191,6 +198,10 @@ def main():
             ctx.decompress_into(p, 1, n, 0, -1, None, out.data_ptr(), 1, out.numel() * 8)
             return n
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.5)                           # let nvidia-smi come up before the GPU is loaded
     for _ in range(max(1, args.warmup)):          # at least one untimed pass: it is also the round-trip check
         step()
     torch.cuda.synchronize()
@@ -198,24 +209,23 @@ def main():
     ckl_bytes = ctx.result_device()[1] if world == 1 else None
 
     ctx.prof_enable(True)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     launches0 = cb.codec.launch_count()
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.time()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     torch.cuda.synchronize()
+    tw1 = time.time()
     if dist:
         dist.barrier()
     ms = e0.elapsed_time(e1)
     launches = cb.codec.launch_count() - launches0
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(tw0, tw1) if rank == 0 else None
     prof = ctx.prof_read()
     ctx.prof_enable(False)
     if dist:
