@@ -342,29 +342,29 @@ __global__ void __launch_bounds__(256) k_path_walk(TraceParams P, u64 nhalf) {
 template <int MODE> struct NodeStore;
 
 template <> struct NodeStore<0> {
-  typedef uint2 Rec;
+  typedef uint2 Rec;      // 64-bit record (x = low word): entry k at bits [15k, 15k+15), remaining-edge nibble at bits 60..63
   uint2* rec; u8* adj; const u32* far;
   __device__ __forceinline__ void init(u32 i, uint4 f) {
-    const u32 p0 = f.x != NONE32, p1 = f.y != NONE32, p2 = f.z != NONE32, p3 = f.w != NONE32;
-    rec[i] = make_uint2((p0 ? (f.x & 0x7FFFu) : 0u) | ((p1 ? (f.y & 0x7FFFu) : 0u) << 15) | (p0 << 30) | (p1 << 31),
-                        (p2 ? (f.z & 0x7FFFu) : 0u) | ((p3 ? (f.w & 0x7FFFu) : 0u) << 15) | (p2 << 30) | (p3 << 31));
+    u64 v = 0;
+    if (f.x != NONE32) v |= (u64)(f.x & 0x7FFFu) | (1ull << 60);
+    if (f.y != NONE32) v |= ((u64)(f.y & 0x7FFFu) << 15) | (2ull << 60);
+    if (f.z != NONE32) v |= ((u64)(f.z & 0x7FFFu) << 30) | (4ull << 60);
+    if (f.w != NONE32) v |= ((u64)(f.w & 0x7FFFu) << 45) | (8ull << 60);
+    rec[i] = make_uint2((u32)v, (u32)(v >> 32));
   }
   __device__ __forceinline__ Rec load(u32 node) const { return rec[node]; }
-  __device__ __forceinline__ u32 adjacency(Rec w) const { return (w.x >> 30) | ((w.y >> 30) << 2); }
+  __device__ __forceinline__ u32 adjacency(Rec w) const { return w.y >> 28; }
   __device__ __forceinline__ void take(u32& node, u32 k, Rec& w) {
-    const u32 word = (k & 2u) ? w.y : w.x;
-    const u32 e = (word >> (15u * (k & 1u))) & 0x7FFFu;
-    const u32 bit = 0x40000000u << (k & 1u);
-    if (k & 2u) w.y &= ~bit; else w.x &= ~bit;
-    rec[node] = w;
+    const u64 v = ((u64)w.y << 32) | w.x;
+    const u32 e = (u32)(v >> (15u * k)) & 0x7FFFu;
+    reinterpret_cast<u32*>(rec + node)[1] = w.y & ~(0x10000000u << k);   // only the nibble word changes
     const u32 f = e >> 2, fk = e & 3u;
-    if (f != node) w = rec[f];                          // a self-loop keeps working on the same record
-    const u32 fbit = 0x40000000u << (fk & 1u);
-    if (fk & 2u) w.y &= ~fbit; else w.x &= ~fbit;
-    rec[f] = w;
+    w = rec[f];                                          // after the store: a self-loop sees its own update
+    w.y &= ~(0x10000000u << fk);
+    reinterpret_cast<u32*>(rec + f)[1] = w.y;
     node = f;
   }
-  __device__ __forceinline__ bool has_edges(u32 node) const { const uint2 w = rec[node]; return ((w.x | w.y) >> 30) != 0; }
+  __device__ __forceinline__ bool has_edges(u32 node) const { return (rec[node].y >> 28) != 0; }
 };
 
 template <> struct NodeStore<1> {
@@ -415,6 +415,10 @@ template <> struct NodeStore<2> {
 
 __device__ __forceinline__ int replay_mode(u32 N) { return N <= REPLAY_CAP0 ? 0 : (N <= REPLAY_CAP1 ? 1 : 2); }
 
+__device__ __forceinline__ void st_ev(u32* base, u32 idx, u32 v) {     // event store: st.global through an opaque 64-bit base
+  asm volatile("st.global.u32 [%0], %1;" ::"l"(base + idx), "r"(v));
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(32) k_replay(TraceParams P) {
   extern __shared__ u64 smem64[];
@@ -433,6 +437,7 @@ __global__ void __launch_bounds__(32) k_replay(TraceParams P) {
   __syncwarp();
   u32* ev = P.ev + P.offs[0 * n1 + z];
   uint2* gstack = P.stack + P.offs[1 * n1 + z];
+  asm volatile("" : "+l"(ev));                        // opaque base: one IMAD.WIDE per event address in the serial loop
   ChainRec* chains = P.chain + P.offs[2 * n1 + z];
   const u32 evCap = P.caps[(u64)z * 4 + 0], stackCap = P.caps[(u64)z * 4 + 1], chainCap = P.caps[(u64)z * 4 + 2];
   const u32* nodeVertex = P.nodeVertex + nb;
@@ -450,49 +455,46 @@ __global__ void __launch_bounds__(32) k_replay(TraceParams P) {
     if (lane == 0) {
       if (nch >= chainCap) { atomicExch(&P.scal[SC_ERROR], 3ull); ok = false; }
       else {
-        u32 node = start, sp = 0, nB = 0;
+        u32 node = start, sp = 0, ne = nev;                   // ne: running event index of the slice
         const u32 begin = nev;
-        u32* evp = ev + nev;                                   // events are appended through a bumped pointer
-        u32* const evLimit = ev + evCap - 2;
-        bool firstT = true, t2 = false, justPopped = false, firstIsB = false;
-        u32 t2f = 0, poppedB = 0, adjStart = nodeVertex[start];
+        const u32 evLimit = evCap - 2;
+        bool firstT = true, t2 = false;
+        u32 t2f = 0, poppedB = 0, popMark = NONE32, adjStart = nodeVertex[start];
         typename NodeStore<MODE>::Rec w = S.load(node);
+        const u32 a0 = S.adjacency(w);
+        const bool firstIsB = (a0 & (a0 - 1)) != 0;           // the chain opens with a 'b'
         for (;;) {
-          if (evp > evLimit) { atomicExch(&P.scal[SC_ERROR], 1ull); ok = false; break; }
+          if (ne > evLimit) { atomicExch(&P.scal[SC_ERROR], 1ull); ok = false; break; }
           const u32 a = S.adjacency(w);
           if (a == 0) {
             // a 't': dead end after a move, or -- directly after a pop -- a spurious branch (remove_spurious_branches)
             if (firstT) {
-              firstT = false;
-              if (nB == 1 && firstIsB) { t2 = true; t2f = (u32)(evp - ev) - begin; adjStart = nodeVertex[node]; }   // remove_initial_branch applies
+              firstT = false;      // no pop yet, so the stack depth is the number of 'b's so far
+              if (sp == 1 && firstIsB) { t2 = true; t2f = ne - begin; adjStart = nodeVertex[node]; }   // remove_initial_branch applies
             }
-            if (justPopped && !(t2 && poppedB == begin)) { ev[poppedB] = (u32)EV_S << 30; *evp++ = (u32)EV_S << 30; }
-            else *evp++ = (u32)EV_T << 30;
+            if (ne == popMark && !(t2 && poppedB == begin)) { st_ev(ev, poppedB, (u32)EV_S << 30); st_ev(ev, ne++, (u32)EV_S << 30); }
+            else st_ev(ev, ne++, (u32)EV_T << 30);
             if (sp == 0) break;
             --sp;
             const uint2 e = sp < REPLAY_STACK ? sstack[sp] : gstack[sp - REPLAY_STACK];
             node = e.x;
             poppedB = e.y;
-            justPopped = true;
+            popMark = ne;                                      // a 't' emitted before any other event is spurious
             w = S.load(node);
             continue;
           }
-          justPopped = false;
           if (a & (a - 1)) {                                  // popcount > 1: branch point
             if (sp >= stackCap + REPLAY_STACK) { atomicExch(&P.scal[SC_ERROR], 2ull); ok = false; break; }
-            const u32 bi = (u32)(evp - ev);
-            const uint2 e = make_uint2(node, bi);
+            const uint2 e = make_uint2(node, ne);
             if (sp < REPLAY_STACK) sstack[sp] = e; else gstack[sp - REPLAY_STACK] = e;
             sp++;
-            if (bi == begin) firstIsB = true;
-            *evp++ = (u32)EV_B << 30;
-            nB++;
+            st_ev(ev, ne++, (u32)EV_B << 30);
           }
           const u32 k = __ffs(a) - 1;                          // priority: right, left, down, up
-          *evp++ = ((u32)EV_E << 30) | (node * 4 + k);
+          st_ev(ev, ne++, ((u32)EV_E << 30) | (node * 4 + k));
           S.take(node, k, w);
         }
-        nev = (u32)(evp - ev);
+        nev = ne;
         ChainRec& rec = chains[nch];
         rec.adjStart = adjStart;
         rec.symBegin = begin;
