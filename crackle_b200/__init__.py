@@ -1,5 +1,10 @@
 """crackle_b200: B200-native (sm_100a) implementation of seung-lab/crackle's per-z-slice compress / decompress
 hot path behind the reference's own interface.  See DESIGN.md and INTEGRATION.md."""
+import os as _os
+
+# the z-chunk pipeline uses up to 2 streams per chunk: give them their own hardware work queues (read at CUDA context creation)
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from .codec import Context, compress, decompress, decompress_range, default_context, header  # noqa: F401
 
 __all__ = ["Context", "compress", "decompress", "decompress_range", "default_context", "header"]

@@ -55,6 +55,7 @@ SYMBOLS = {
     "ckl_launch_count": (u64, []),
     "ckl_ctx_set_stream": (cint, [vp, vp]),
     "ckl_ctx_own_stream": (cint, [vp]),
+    "ckl_ctx_set_chunks": (cint, [vp, cint]),
     "ckl_crc32c": (cint, [vp, vp, cint, u64, ctypes.POINTER(u32)]),
     "ckl_sort_unique_u64": (cint, [vp, vp, u64, cint, ctypes.POINTER(u64)]),
 }

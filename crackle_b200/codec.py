@@ -52,6 +52,11 @@ class Context:
         else:
             self._check(_capi.lib().ckl_ctx_set_stream(self._h, ctypes.c_void_p(int(cuda_stream_ptr))))
 
+    def set_chunks(self, chunks: int = 0):
+        """z-chunk pipelining of compress / decompress: 0 = automatic (large volumes), 1 = off, K = always K chunks.
+        Output is identical for every setting."""
+        self._check(_capi.lib().ckl_ctx_set_chunks(self._h, int(chunks)))
+
     def prof_enable(self, on=True):
         _capi.lib().ckl_prof_enable(self._h, int(on))
 

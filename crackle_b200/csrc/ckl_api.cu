@@ -3,9 +3,13 @@
 // Stream assembly follows crackle::compress_helper (src/crackle.hpp:34-217) and the prologue of
 // crackle::decompress (src/crackle.hpp:503-582); header emit/parse follows src/header.hpp:98-267.
 // Error strings match the reference's std::runtime_error texts so a binding can re-raise them unchanged.
+#include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <functional>
 #include <mutex>
+#include <thread>
 
 #include "ckl_internal.cuh"
 
@@ -28,10 +32,17 @@ struct ShardJob {
 };
 
 unsigned long long g_ckl_launches = 0;
+int g_ckl_grid_mult = 1;
+
+// The chunk pipeline drives up to 2 streams per chunk; with the default of 8 hardware work queues the streams would
+// alias and serialise each other.  Honoured only if the CUDA context is created after this library is loaded.
+namespace { struct EnvInit { EnvInit() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); } } g_env_init; }
 
 // optional per-stage timing with CUDA events on the context's stream
 struct Prof {
   bool on = false;
+  int id = 0;                    // 0 = the context itself, k + 1 = its k-th chunk context
+  cudaEvent_t base = nullptr;    // CKL_TIMELINE=1: stage begin / end times relative to this event go to stderr
   struct Rec { std::string name; cudaEvent_t a, b; };
   std::vector<Rec> pending;
   std::vector<std::pair<std::string, double>> acc;   // name -> accumulated ms
@@ -48,6 +59,12 @@ struct Prof {
     for (auto& r : pending) {
       cudaEventSynchronize(r.b);
       float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+      if (base) {
+        float t0 = 0, t1 = 0;
+        if (cudaEventElapsedTime(&t0, base, r.a) == cudaSuccess && cudaEventElapsedTime(&t1, base, r.b) == cudaSuccess)
+          fprintf(stderr, "TL %d %-20s %9.3f %9.3f\n", id, r.name.c_str(), t0, t1);
+        else cudaGetLastError();
+      }
       size_t i = 0;
       for (; i < acc.size(); i++) if (acc[i].first == r.name) break;
       if (i == acc.size()) { acc.emplace_back(r.name, 0.0); cnt.push_back(0); }
@@ -71,6 +88,7 @@ struct ckl_ctx {
   CrcTables* dtab = nullptr;
   ull* scal = nullptr;     // device scalars
   ull* hscal = nullptr;    // pinned mirror
+  ull* hscal2 = nullptr;   // second mirror, read through the side stream
   DBuf labels_dev, DV, DH;
   CclBufs ccl;
   TraceBufs tr;
@@ -80,6 +98,13 @@ struct ckl_ctx {
   DBuf result; u64 result_bytes = 0;
   DBuf stream_dev, out_dev, tmp32, keys, codes;
   ShardJob job;
+  // z-chunk pipelining (single-GPU compress / decompress of large volumes): child contexts, each with its own streams
+  // and workspace, process disjoint z-ranges concurrently so the latency-bound stages of one chunk (chain replay,
+  // decode chains) overlap the bandwidth-bound stages of the others (edge extraction, paint).
+  std::vector<ckl_ctx*> kids;
+  bool is_kid = false;
+  int chunks = 0;                          // 0 = automatic, 1 = off, K = force K chunks
+  cudaEvent_t ev_done = nullptr;
 };
 
 static void set_err(char* err, size_t n, const std::string& m) {
@@ -161,11 +186,13 @@ extern "C" int ckl_ctx_create(int device, ckl_ctx** out) {
     }
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
     crc_build_tables(c->htab);
     CUDA_CHECK(cudaMalloc(&c->dtab, sizeof(CrcTables)));
     CUDA_CHECK(cudaMemcpy(c->dtab, &c->htab, sizeof(CrcTables), cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMalloc(&c->scal, SC_COUNT * sizeof(ull)));
     CUDA_CHECK(cudaMallocHost(&c->hscal, SC_COUNT * sizeof(ull)));
+    CUDA_CHECK(cudaMallocHost(&c->hscal2, SC_COUNT * sizeof(ull)));
   } catch (const CklError& e) {
     delete c;
     return e.code;
@@ -176,15 +203,20 @@ extern "C" int ckl_ctx_create(int device, ckl_ctx** out) {
 
 extern "C" void ckl_ctx_destroy(ckl_ctx* c) {
   if (!c) return;
+  for (ckl_ctx* k : c->kids) ckl_ctx_destroy(k);
+  c->kids.clear();
   cudaSetDevice(c->device);
   if (c->st) cudaStreamSynchronize(c->st);
   if (c->st2) { cudaStreamSynchronize(c->st2); cudaStreamDestroy(c->st2); }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_done) cudaEventDestroy(c->ev_done);
+  if (c->prof.base && !c->is_kid) cudaEventDestroy(c->prof.base);
   if (c->own_st) cudaStreamDestroy(c->own_st);
   if (c->dtab) cudaFree(c->dtab);
   if (c->scal) cudaFree(c->scal);
   if (c->hscal) cudaFreeHost(c->hscal);
+  if (c->hscal2) cudaFreeHost(c->hscal2);
   delete c;
 }
 extern "C" const char* ckl_ctx_error(const ckl_ctx* c) { return c ? c->err.c_str() : "null context"; }
@@ -260,19 +292,21 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   c->ccl.runStart.ensure(J.runs * 4);
   c->ccl.compRank.ensure(J.runs * 4);
   c->ccl.compPix.ensure(J.runs * 4);
-  STAGE(c, "ccl_solve", launch_ccl_solve(g, c->DV.as<u32>(), c->DH.as<u32>(), c->ccl, c->dtab, c->scal, st));
+  // The tracing chain is the critical path and, up to the replay, as issue-bound as the CCL chain: it runs first and
+  // alone.  The CCL / label chain is queued once the replay is -- that kernel keeps one warp per scheduler busy a fifth of
+  // the time, and the CCL work fits into the issue slots it leaves free.
+  CUDA_CHECK(cudaMemcpyAsync(c->hscal2, c->scal, SC_COUNT * sizeof(ull), cudaMemcpyDeviceToHost, st2));
   CUDA_CHECK(cudaStreamSynchronize(st2));
-  read_scalars(c);
-  J.ncomp = c->hscal[SC_COMPONENTS];
-  const u64 evCap = c->hscal[SC_SYMCAP], stackCap = c->hscal[SC_STACKCAP], chainCap = c->hscal[SC_CHAINCAP], cpCap = c->hscal[SC_CPCAP];
-  const u64 nodes = c->hscal[SC_NODES];
-  const u32 maxNodes = (u32)c->hscal[SC_MAXNODES];
+  const u64 evCap = c->hscal2[SC_SYMCAP], stackCap = c->hscal2[SC_STACKCAP], chainCap = c->hscal2[SC_CHAINCAP], cpCap = c->hscal2[SC_CPCAP];
+  const u64 nodes = c->hscal2[SC_NODES];
+  const u32 maxNodes = (u32)c->hscal2[SC_MAXNODES];
   if (maxNodes >= (1u << 28)) throw CklError(CKL_ERR_ARG, "crackle_b200: slice has too many crack-graph nodes");
   c->tr.nodeVertex.ensure(nodes * 4 + 16);
   c->tr.nodeAdj.ensure(nodes + 16);
   c->tr.seFar.ensure(nodes * 16 + 16);
   c->tr.seLen.ensure(nodes * 16 + 16);
   c->tr.ev.ensure(evCap * 4 + 16);
+  c->tr.evRec.ensure(evCap * 16 + 16);
   c->tr.evCp.ensure((evCap + g.sz) * 4 + 16);
   c->tr.stack.ensure(stackCap * 8);
   c->tr.chain.ensure(chainCap * sizeof(ChainRec));
@@ -284,7 +318,10 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   launch_trace_post(g, c->tr, c->scal, evCap, st2);
   c->prof.end(st2);
   CUDA_CHECK(cudaEventRecord(c->ev_join, st2));
-  // component ranks, crcs, component labels
+  // connected components, component ranks, crcs, component labels
+  STAGE(c, "ccl_solve", launch_ccl_solve(g, c->DV.as<u32>(), c->DH.as<u32>(), c->ccl, c->dtab, c->scal, st));
+  read_scalars(c);
+  J.ncomp = c->hscal[SC_COMPONENTS];
   const u32 init_term = gf_mul(gf_xpow32(c->htab.pw, (u32)g.sxy), 0xFFFFFFFFu);
   STAGE(c, "ccl_finish", launch_ccl_finish(g, c->ccl, J.runs, c->dtab, init_term, nullptr, st));
   c->lb.mapping.ensure(J.ncomp * 8 + 8);
@@ -444,6 +481,266 @@ extern "C" int ckl_shard_fetch(ckl_ctx* c, uint8_t* keys, uint64_t* components_p
   API_END(c)
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// z-chunk pipelining helpers
+struct ChunkErr { int code = 0; std::string msg; };
+
+static void ensure_kids(ckl_ctx* c, int K) {
+  while ((int)c->kids.size() < K) {
+    ckl_ctx* k = nullptr;
+    const int rc = ckl_ctx_create(c->device, &k);
+    if (rc) throw CklError(rc, "crackle_b200: failed to create a chunk context");
+    k->is_kid = true;
+    k->chunks = 1;
+    // stream priorities stagger the chunks: chunk 0 runs ahead, each later chunk fills what the earlier ones leave
+    // idle (numerically lower = higher priority); inside a chunk the tracing chain outranks the CCL / label chain
+    int lo = 0, hi = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const int idx = (int)c->kids.size();
+    int p2 = std::min(hi + idx, lo), p1 = std::min(hi + idx + 1, lo);
+    {
+      const char* e = getenv("CKL_PRIO");      // tuning aid: 0 = every chunk alike (side stream high, main stream default)
+      if (e && atoi(e) == 0) { p2 = hi; p1 = lo; }
+    }
+    cudaStreamDestroy(k->st2);
+    cudaStreamDestroy(k->own_st);
+    k->st2 = k->own_st = k->st = nullptr;
+    c->kids.push_back(k);          // owned from here on (destroyed with the parent even if stream creation fails)
+    CUDA_CHECK(cudaStreamCreateWithPriority(&k->own_st, cudaStreamNonBlocking, p1));
+    k->st = k->own_st;
+    CUDA_CHECK(cudaStreamCreateWithPriority(&k->st2, cudaStreamNonBlocking, p2));
+  }
+}
+struct GridMultScope {        // finer grids while chunks run concurrently (see g_ckl_grid_mult)
+  int saved;
+  GridMultScope() : saved(g_ckl_grid_mult) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("CKL_GRID_MULT"); env = e ? atoi(e) : 0; if (env < 0) env = 0; }
+    g_ckl_grid_mult = env ? env : 8;
+  }
+  ~GridMultScope() { g_ckl_grid_mult = saved; }
+};
+// chunk count for a volume of `sz` slices: explicit setting, CKL_CHUNKS, or automatic (large volumes only)
+// Automatic policy: only when the volume crosses PCIe (host pointers) -- there the chunks overlap copies with compute.
+// Device-resident volumes are not chunked: measured on B200 (tools/chunk_matrix.sh) the stages of different chunks compete
+// for the same SM resources (shared memory of the replay, issue slots of the walkers) and the total does not shrink.
+static int pick_chunks(const ckl_ctx* c, u64 sxy, u64 sz, u64 bytes_per_voxel, bool host_io) {
+  if (c->is_kid) return 1;
+  int K = c->chunks;
+  if (K == 0) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("CKL_CHUNKS"); env = e ? atoi(e) : 0; if (env < 0) env = 0; }
+    K = env;
+  }
+  if (K == 0) K = (host_io && sxy * sz * bytes_per_voxel >= (1ull << 28) && sz >= 64) ? 4 : 1;
+  if ((u64)K > sz) K = (int)sz;
+  if (K > 64) K = 64;
+  return K < 1 ? 1 : K;
+}
+// run fn(k) for k in [0, K) on K host threads (each drives its own child context); first error in chunk order wins
+static void run_chunks(ckl_ctx* c, int K, const std::function<void(int)>& fn) {
+  std::vector<ChunkErr> errs(K);
+  std::vector<std::thread> th;
+  auto body = [&](int k) {
+    try {
+      CUDA_CHECK(cudaSetDevice(c->device));
+      fn(k);
+    } catch (const CklError& e) { errs[k].code = e.code; errs[k].msg = e.what(); cudaGetLastError(); }
+    catch (const std::exception& e) { errs[k].code = CKL_ERR_CUDA; errs[k].msg = e.what(); }
+  };
+  for (int k = 1; k < K; k++) th.emplace_back(body, k);
+  body(0);
+  for (auto& t : th) t.join();
+  for (int k = 0; k < K; k++)
+    if (errs[k].code) {
+      for (int j = 0; j < K; j++) { cudaStreamSynchronize(c->kids[j]->st); if (c->kids[j]->st2) cudaStreamSynchronize(c->kids[j]->st2); c->kids[j]->job.active = false; }
+      throw CklError(errs[k].code, errs[k].msg);
+    }
+}
+// children start after everything already queued on the parent's stream
+static bool timeline_on() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CKL_TIMELINE"); v = (e && atoi(e) > 0) ? 1 : 0; }
+  return v == 1;
+}
+static void timeline_base(ckl_ctx* c) {
+  if (!c->prof.on || !timeline_on() || c->is_kid) return;
+  if (!c->prof.base) CUDA_CHECK(cudaEventCreate(&c->prof.base));
+  CUDA_CHECK(cudaEventRecord(c->prof.base, c->st));
+  fprintf(stderr, "TL base\n");
+}
+static void fork_kids(ckl_ctx* c, int K) {
+  CUDA_CHECK(cudaEventRecord(c->ev_fork, c->st));
+  for (int k = 0; k < K; k++) {
+    c->kids[k]->prof.on = c->prof.on;
+    c->kids[k]->prof.id = k + 1;
+    c->kids[k]->prof.base = c->prof.base;
+    CUDA_CHECK(cudaStreamWaitEvent(c->kids[k]->st, c->ev_fork, 0));
+  }
+}
+// the parent's stream continues after everything the children queued
+static void join_kids(ckl_ctx* c, int K) {
+  for (int k = 0; k < K; k++) {
+    CUDA_CHECK(cudaEventRecord(c->kids[k]->ev_done, c->kids[k]->st));
+    CUDA_CHECK(cudaStreamWaitEvent(c->st, c->kids[k]->ev_done, 0));
+  }
+}
+static void merge_kid_prof(ckl_ctx* c, int K) {
+  if (!c->prof.on) return;
+  std::vector<std::pair<std::string, double>> sum;
+  for (int k = 0; k < K; k++) {
+    Prof& p = c->kids[k]->prof;
+    p.collect();
+    for (size_t i = 0; i < p.acc.size(); i++) {
+      size_t j = 0;
+      for (; j < sum.size(); j++) if (sum[j].first == p.acc[i].first) break;
+      if (j == sum.size()) sum.emplace_back(p.acc[i].first, 0.0);
+      sum[j].second += p.acc[i].second;
+    }
+    p.acc.clear(); p.cnt.clear();
+  }
+  for (auto& e : sum) {      // one call of the parent = the chunks' stage times added up (they overlap in wall time)
+    size_t i = 0;
+    for (; i < c->prof.acc.size(); i++) if (c->prof.acc[i].first == e.first) break;
+    if (i == c->prof.acc.size()) { c->prof.acc.emplace_back(e.first, 0.0); c->prof.cnt.push_back(0); }
+    c->prof.acc[i].second += e.second; c->prof.cnt[i]++;
+  }
+}
+
+__global__ void k_add_u32(u32* __restrict__ dst, const u32* __restrict__ src, u64 n) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];                    // uint32 wrap == the reference's atomic<uint32> counters
+}
+
+// Single-GPU compress of a large volume as K z-chunks: each chunk runs the shard stages (edges -> CCL / tracing ->
+// labels) on its own child context and streams; the chunks are then merged exactly like z-shards on different GPUs
+// (global pixel-pair / max-label decisions, merged sorted unique table, summed markov statistics) and every chunk
+// writes its keys, N_z, crack codes and CRCs straight into its place in the one output stream.
+static void compress_chunked(ckl_ctx* c, const void* labels, int labels_on_device, int width, u64 sx, u64 sy, u64 sz, int fortran_order,
+                             int order_in, int K, uint64_t* out_bytes) {
+  ensure_kids(c, K);
+  GridMultScope fine_grids;
+  const u64 sxy = sx * sy, voxels = sxy * sz;
+  std::vector<u64> z0(K + 1);
+  for (int k = 0; k <= K; k++) z0[k] = sz * (u64)k / (u64)K;
+  std::vector<ckl_shard_summary> sum(K);
+  std::vector<int> guess(K);
+  fork_kids(c, K);
+  // phase A: everything that does not need a global decision.  The crack format (pixel pairs) is guessed from the
+  // chunk's own statistics and verified below.
+  run_chunks(c, K, [&](int k) {
+    ckl_ctx* q = c->kids[k];
+    const u8* src = (const u8*)labels + z0[k] * sxy * (u64)width;
+    shard_begin_impl(q, src, labels_on_device, width, sx, sy, z0[k + 1] - z0[k], &sum[k]);
+    guess[k] = (i64)sum[k].pairs < (i64)sum[k].voxels / 2;
+    shard_encode_impl(q, guess[k], ckl_byte_width(sum[k].max_label), order_in);
+  });
+  u64 pairs = 0, maxl = 0;
+  for (int k = 0; k < K; k++) {
+    pairs += sum[k].pairs;
+    if (k && sum[k].first_voxel == sum[k - 1].last_voxel) pairs++;      // the pair straddling the chunk boundary (lib.hpp:249-256)
+    if (sum[k].max_label > maxl) maxl = sum[k].max_label;
+  }
+  const int permissible = (i64)pairs < (i64)voxels / 2;                   // crackle.hpp:50-55
+  const int stored = ckl_byte_width(maxl);                               // crackle.hpp:233-235
+  {
+    std::vector<int> redo;
+    for (int k = 0; k < K; k++) if (guess[k] != permissible) redo.push_back(k);
+    if (!redo.empty())
+      run_chunks(c, K, [&](int k) {
+        if (guess[k] == permissible) return;
+        ckl_ctx* q = c->kids[k];
+        const u8* src = (const u8*)labels + z0[k] * sxy * (u64)width;
+        shard_begin_impl(q, src, labels_on_device, width, sx, sy, z0[k + 1] - z0[k], &sum[k]);
+        shard_encode_impl(q, permissible, stored, order_in);
+      });
+  }
+  cudaStream_t st = c->st;
+  join_kids(c, K);
+  u64 ncomp = 0, ncp = 0, nloc = 0;
+  std::vector<u64> compBase(K + 1), codeBase(K + 1);
+  for (int k = 0; k < K; k++) { compBase[k] = ncomp; ncomp += c->kids[k]->job.ncomp; ncp += c->kids[k]->job.ncp; nloc += c->kids[k]->job.nuniq_local; }
+  compBase[K] = ncomp;
+  int order = order_in;
+  if (order > 0 && ncp == 0) order = 0;                                  // crackle.hpp:107-118
+  // global sorted unique label table = sort + unique of the concatenated per-chunk tables (labels.hpp:99-109)
+  u64 nu = 0;
+  if (nloc) {
+    c->lb.mapping.ensure(nloc * 8 + 8);
+    u64 o = 0;
+    for (int k = 0; k < K; k++) {
+      const u64 n = c->kids[k]->job.nuniq_local;
+      if (n) CUDA_CHECK(cudaMemcpyAsync(c->lb.mapping.as<u64>() + o, c->kids[k]->lb.uniq.p, n * 8, cudaMemcpyDeviceToDevice, st));
+      o += n;
+    }
+    nu = labels_sort_unique(c->lb, nloc, stored, st);
+  }
+  if (order > 0) {                                                       // markov.hpp:193-220: counters summed over all slices
+    const u64 cells = 4ull << (2 * order);
+    c->mk.stats.ensure(cells * 4);
+    CUDA_CHECK(cudaMemcpyAsync(c->mk.stats.p, c->kids[0]->mk.stats.p, cells * 4, cudaMemcpyDeviceToDevice, st));
+    for (int k = 1; k < K; k++) {
+      k_add_u32<<<(u32)((cells + 255) / 256), 256, 0, st>>>(c->mk.stats.as<u32>(), c->kids[k]->mk.stats.as<u32>(), cells);
+      LAUNCH_CHECK();
+    }
+  }
+  fork_kids(c, K);
+  // phase B: keys against the global table, markov coding against the global model, code sizes
+  run_chunks(c, K, [&](int k) {
+    shard_finish_impl(c->kids[k], c->lb.uniq.as<u64>(), nu, order > 0 ? c->mk.stats.as<u32>() : nullptr, order, false);
+  });
+  u64 codes_bytes = 0;
+  for (int k = 0; k < K; k++) { codeBase[k] = codes_bytes; codes_bytes += c->kids[k]->job.codes_bytes; }
+  const int kw = ckl_byte_width(nu), cw = ckl_byte_width(sxy);
+  const u64 labels_bytes = 8 + nu * (u64)stored + sz * (u64)cw + ncomp * (u64)kw;
+  const u64 off_z = 29, off_lab = off_z + 4ull * (sz + 1), off_model = off_lab + labels_bytes;
+  const u64 off_nz = off_lab + 8 + nu * (u64)stored, off_keys = off_nz + sz * (u64)cw;
+  const u64 off_codes = off_model + model_bytes_for(order);
+  const u64 off_crcs = off_codes + codes_bytes + 4;
+  const u64 total = off_crcs + 4ull * sz;
+  c->result.ensure(total + 16);
+  c->tmp32.ensure(sz * 4 + 16);
+  u8* R = c->result.as<u8>();
+  // phase C: every chunk places its pieces (asynchronous launches on the chunk's own stream)
+  for (int k = 0; k < K; k++) {
+    ckl_ctx* q = c->kids[k];
+    const Geom& g = q->job.g;
+    cudaStream_t qs = q->st;
+    k_gather_stride4<<<(g.sz + 255) / 256, 256, 0, qs>>>(q->tr.sliceInfo.as<u32>(), g.sz, 3, c->tmp32.as<u32>() + z0[k]);
+    LAUNCH_CHECK();
+    launch_write_le_u32(q->ccl.nz.as<u32>(), g.sz, cw, R + off_nz + z0[k] * (u64)cw, qs);
+    launch_write_keys(q->lb.mapping.as<u64>(), q->job.ncomp, c->lb.uniq.as<u64>(), nu, kw, R + off_keys + compBase[k] * (u64)kw, qs);
+    if (order > 0) launch_markov_copy(g, q->tr, q->mk, R + off_codes + codeBase[k], qs);
+    else launch_pack_order0(g, q->tr, R + off_codes + codeBase[k], qs);
+    launch_write_le_u32(q->ccl.sliceCrc.as<u32>(), g.sz, 4, R + off_crcs + 4ull * z0[k], qs);
+  }
+  join_kids(c, K);
+  // header, z index + its crc (crackle.hpp:173-185), unique table, markov model, labels crc (crackle.hpp:187, 211)
+  u8 hb[29];
+  header_bytes_v1(hb, width, stored, permissible, fortran_order, order, (u32)sx, (u32)sy, (u32)sz, labels_bytes);
+  CUDA_CHECK(cudaMemcpyAsync(R, hb, 29, cudaMemcpyHostToDevice, st));
+  launch_write_le_u32(c->tmp32.as<u32>(), sz, 4, R + off_z, st);
+  u32* crc_tmp = c->tmp32.as<u32>() + sz;
+  launch_crc_bytes(R + off_z, 4ull * sz, c->dtab, c->htab, crc_tmp, st);
+  k_store_bytes_u32<<<1, 1, 0, st>>>(R + off_z + 4ull * sz, crc_tmp);
+  LAUNCH_CHECK();
+  u8 nub[8];
+  for (int i = 0; i < 8; i++) nub[i] = (u8)(nu >> (8 * i));
+  CUDA_CHECK(cudaMemcpyAsync(R + off_lab, nub, 8, cudaMemcpyHostToDevice, st));
+  launch_write_uniq(c->lb.uniq.as<u64>(), nu, stored, R + off_lab + 8, st);
+  if (order > 0) CUDA_CHECK(cudaMemcpyAsync(R + off_model, c->kids[0]->mk.stored.p, model_bytes_for(order), cudaMemcpyDeviceToDevice, st));
+  launch_crc_bytes(R + off_lab, labels_bytes, c->dtab, c->htab, crc_tmp + 1, st);
+  k_store_bytes_u32<<<1, 1, 0, st>>>(R + off_codes + codes_bytes, crc_tmp + 1);
+  LAUNCH_CHECK();
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  merge_kid_prof(c, K);
+  c->prof.collect();
+  for (int k = 0; k < K; k++) c->kids[k]->job.active = false;
+  c->result_bytes = total;
+  if (out_bytes) *out_bytes = total;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // single-GPU compress = the three shard stages + stream assembly on the device
 extern "C" int ckl_compress(ckl_ctx* c, const void* labels, int labels_on_device, int data_width, uint64_t sx, uint64_t sy, uint64_t sz,
@@ -455,6 +752,7 @@ extern "C" int ckl_compress(ckl_ctx* c, const void* labels, int labels_on_device
   if (markov_model_order < 0 || markov_model_order > 12) throw CklError(CKL_ERR_ARG, "crackle_b200: markov_model_order must be in [0, 12]");
   const u64 voxels = sx * sy * sz;
   cudaStream_t st = c->st;
+  timeline_base(c);
   if (voxels == 0) {   // crackle.hpp:96-98: header only (crack format from pairs(0) < 0 == false)
     u8 hb[29];
     header_bytes_v1(hb, data_width, 1, 0, fortran_order, markov_model_order, (u32)sx, (u32)sy, (u32)sz, 0);
@@ -464,6 +762,11 @@ extern "C" int ckl_compress(ckl_ctx* c, const void* labels, int labels_on_device
     c->result_bytes = 29;
     if (out_bytes) *out_bytes = 29;
     return CKL_OK;
+  }
+  {
+    if (sx * sy >= (1ull << 30)) throw CklError(CKL_ERR_ARG, "crackle_b200: slice too large (sx*sy must be < 2^30)");
+    const int K = pick_chunks(c, sx * sy, sz, (u64)data_width, !labels_on_device);
+    if (K > 1) { compress_chunked(c, labels, labels_on_device, data_width, sx, sy, sz, fortran_order, markov_model_order, K, out_bytes); return CKL_OK; }
   }
   ckl_shard_summary s;
   shard_begin_impl(c, labels, labels_on_device, data_width, sx, sy, sz, &s);
@@ -550,18 +853,19 @@ __global__ void k_crc_compare(const u32* __restrict__ computed, const u8* __rest
   if (s != computed[i]) atomicMin(&scal[SC_CRC_BAD], (ull)i);
 }
 
-extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_device, uint64_t num_bytes, int64_t z_start, int64_t z_end,
-                              int has_label, uint64_t label, void* out, int out_on_device, uint64_t out_capacity) {
-  API_BEGIN(c)
+// hbin: host view of the stream (may be null), dbin: device view (may be null -> uploaded); at least one is given.
+static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t num_bytes, int64_t z_start, int64_t z_end,
+                            int has_label, uint64_t label, void* out, int out_on_device, uint64_t out_capacity) {
   cudaStream_t st = c->st;
+  timeline_base(c);
   if (num_bytes < 29) throw CklError(CKL_ERR_STREAM, "crackle: Input too small to be a valid stream. Bytes: " + std::to_string(num_bytes));
   // the small sections are parsed on the host; a device-resident stream is read back piecewise (never as a whole)
   std::vector<u8> buf_head, buf_z, buf_lab, buf_nz, buf_model;
   auto fetch = [&](u64 offset, u64 n, std::vector<u8>& buf) -> const u8* {
-    if (!binary_on_device) return (const u8*)binary + offset;
+    if (hbin) return hbin + offset;
     buf.resize(n ? n : 1);
     if (n) {
-      CUDA_CHECK(cudaMemcpyAsync(buf.data(), (const u8*)binary + offset, n, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaMemcpyAsync(buf.data(), dbin + offset, n, cudaMemcpyDeviceToHost, st));
       CUDA_CHECK(cudaStreamSynchronize(st));
     }
     return buf.data();
@@ -581,7 +885,7 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   const u64 szr = (u64)(z_end - z_start);
   const u64 sx = h.sx, sy = h.sy, sxy = sx * sy;
   const u64 voxels = sxy * szr;
-  if (voxels == 0) return CKL_OK;
+  if (voxels == 0) return;
   if (sxy >= (1ull << 30)) throw CklError(CKL_ERR_ARG, "crackle_b200: slice too large (sx*sy must be < 2^30)");
   const int ow = has_label ? 1 : (int)h.data_width;
   if (out_capacity < voxels * (u64)ow) throw CklError(CKL_ERR_ARG, "crackle_b200: output buffer too small");
@@ -647,11 +951,30 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
     }
   }
   // device copies
-  const u8* dstream = (const u8*)binary;
-  if (!binary_on_device) {
+  const u8* dstream = dbin;
+  if (!dstream) {
     c->stream_dev.ensure(num_bytes + 8);
-    CUDA_CHECK(cudaMemcpyAsync(c->stream_dev.p, binary, num_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(c->stream_dev.p, hbin, num_bytes, cudaMemcpyHostToDevice, st));
     dstream = c->stream_dev.as<u8>();
+  }
+  // Large Fortran-order outputs: K z-chunks on child contexts (each a z-range decode into its own part of the output),
+  // so one chunk's decode chains / CCL overlap another chunk's paint and, for host outputs, its device->host copy.
+  {
+    const int K = h.fortran_order ? pick_chunks(c, sxy, szr, (u64)ow, !out_on_device) : 1;
+    if (K > 1) {
+      ensure_kids(c, K);
+      GridMultScope fine_grids;
+      fork_kids(c, K);
+      run_chunks(c, K, [&](int k) {
+        const i64 a = z_start + (i64)(szr * (u64)k / (u64)K), b = z_start + (i64)(szr * (u64)(k + 1) / (u64)K);
+        const u64 o = (u64)(a - z_start) * sxy * (u64)ow;
+        decompress_impl(c->kids[k], hbin, dstream, num_bytes, a, b, has_label, label, (u8*)out + o, out_on_device, (u64)(b - a) * sxy * (u64)ow);
+      });
+      join_kids(c, K);
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      merge_kid_prof(c, K);
+      return;
+    }
   }
   DecodeBufs& D = c->dc;
   D.codeOff.ensure((szr + 1) * 8); D.keyBase.ensure(szr * 8); D.stackOff.ensure((szr + 1) * 8);
@@ -740,8 +1063,22 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   STAGE(c, "d_paint", launch_paint(g, c->DV.as<u32>(), c->ccl, D.runLabel.as<u64>(), ow, has_label, label, (int)h.fortran_order, dout, st));
   if (!out_on_device) CUDA_CHECK(cudaMemcpyAsync(out, dout, voxels * (u64)ow, cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
-  c->prof.collect();
+  if (!c->is_kid) c->prof.collect();
+}
+
+extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_device, uint64_t num_bytes, int64_t z_start, int64_t z_end,
+                              int has_label, uint64_t label, void* out, int out_on_device, uint64_t out_capacity) {
+  API_BEGIN(c)
+  decompress_impl(c, binary_on_device ? nullptr : (const u8*)binary, binary_on_device ? (const u8*)binary : nullptr, num_bytes, z_start, z_end,
+                  has_label, label, out, out_on_device, out_capacity);
   API_END(c)
+}
+
+// z-chunk pipelining of the single-GPU paths: 0 = automatic (large volumes), 1 = off, K = always K chunks
+extern "C" int ckl_ctx_set_chunks(ckl_ctx* c, int chunks) {
+  if (!c || chunks < 0) return CKL_ERR_ARG;
+  c->chunks = chunks;
+  return CKL_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------

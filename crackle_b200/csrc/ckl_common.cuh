@@ -31,7 +31,13 @@ struct CklError : std::runtime_error {
 
 // every kernel launch is followed by LAUNCH_CHECK(): error check + a process-wide launch counter (bench.py reports it)
 extern unsigned long long g_ckl_launches;
-#define LAUNCH_CHECK() do { g_ckl_launches++; CUDA_CHECK(cudaGetLastError()); } while (0)
+// grid-cap multiplier of the grid-stride kernels: > 1 while z-chunks run concurrently, so blocks are short and the
+// hardware block scheduler can interleave the chunks by stream priority instead of queueing behind persistent grids
+extern int g_ckl_grid_mult;
+#define LAUNCH_CHECK() do { __atomic_fetch_add(&g_ckl_launches, 1ull, __ATOMIC_RELAXED); CUDA_CHECK(cudaGetLastError()); } while (0)
+
+// 64-bit index / 32-bit divisor: the full 64-bit division costs ~70 instructions; almost every index fits 32 bits
+__host__ __device__ __forceinline__ u64 fdiv(u64 a, u32 d) { return (a >> 32) ? a / d : (u64)((u32)a / d); }
 
 // Grow-only device buffer (the context keeps these across calls so steady-state calls do no cudaMalloc).
 struct DBuf {

@@ -14,7 +14,7 @@
 static u32 grid1(u64 n, u32 bs, u32 cap_blocks) {
   u64 b = (n + bs - 1) / bs;
   if (b < 1) b = 1;
-  if (b > cap_blocks) b = cap_blocks;
+  if (b > (u64)cap_blocks * (u64)g_ckl_grid_mult) b = (u64)cap_blocks * (u64)g_ckl_grid_mult;
   return (u32)b;
 }
 
@@ -651,9 +651,9 @@ void launch_decode_mark(const Geom& g, const u8* stream, int order, DecodeBufs& 
 __global__ void __launch_bounds__(256) k_planes_from_cracks(Geom g, u32* EV, u32* EH) {
   const u64 nwords = g.words(), stride = (u64)gridDim.x * blockDim.x;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) {
-    const u64 row = i / g.W;
+    const u64 row = fdiv(i, g.W);
     const u32 w = (u32)(i - row * g.W);
-    const u32 y = (u32)(row % g.sy);
+    const u32 y = (u32)(row - fdiv(row, g.sy) * g.sy);
     const u32 valid = (w == g.W - 1 && (g.sx & 31)) ? ((1u << (g.sx & 31)) - 1u) : 0xFFFFFFFFu;
     EV[i] = ~EV[i] & valid & ~(w == 0 ? 1u : 0u);
     EH[i] = y >= 1 ? (~EH[i] & valid) : 0u;
@@ -704,9 +704,9 @@ __global__ void __launch_bounds__(256) k_paint(Geom g, const u32* __restrict__ D
   const u64 nwords = g.words();
   const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
   for (u64 i = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < nwords; i += nwarps) {
-    const u64 row = i / g.W;
+    const u64 row = fdiv(i, g.W);
     const u32 w = (u32)(i - row * g.W);
-    const u32 z = (u32)(row / g.sy), y = (u32)(row - (u64)z * g.sy);
+    const u32 z = (u32)fdiv(row, g.sy), y = (u32)(row - (u64)z * g.sy);
     const u32 x = w * 32 + lane;
     if (x >= g.sx) continue;
     const u32 dv = DV[i];
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(256) k_paint_rows(Geom g, const u32* __restric
   const u64 rows = g.rows();
   const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
   for (u64 row = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += nwarps) {
-    const u32 z = (u32)(row / g.sy);
+    const u32 z = (u32)fdiv(row, g.sy);
     const u64* rl = runLabel + runBase[z] + rowBase[row];
     OUT* o = out + row * g.sx;
     const u32* dvrow = DV + row * g.W;

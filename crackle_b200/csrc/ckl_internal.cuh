@@ -51,7 +51,7 @@ struct TraceBufs {
   DBuf seFar, seLen;                            // per (node, direction) slot: far node << 2 | arrival dir, length
   DBuf bounds;                                  // per slice: E, S, C + caps (2 x 4 x u32 x sz)
   DBuf offs;                                    // per slice u64 offsets: events, stack, chain, cp  (4 x (sz+1))
-  DBuf ev, evCp, stack, chain, cp;              // sized from scal[SC_*CAP]
+  DBuf ev, evRec, evCp, stack, chain, cp;       // sized from scal[SC_*CAP]
   DBuf sliceInfo;                               // per slice: ncp, nchains, boc_bytes, code_bytes (4 x u32 x sz)
   DBuf codeOff;                                 // u64 x (sz+1) byte offsets of each slice's crack code
 };

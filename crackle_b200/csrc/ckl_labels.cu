@@ -12,7 +12,7 @@
 static u32 grid1d(u64 n, u32 bs) {
   u64 b = (n + bs - 1) / bs;
   if (b < 1) b = 1;
-  if (b > 148ull * 32) b = 148ull * 32;
+  if (b > 148ull * 32 * (u64)g_ckl_grid_mult) b = 148ull * 32 * (u64)g_ckl_grid_mult;
   return (u32)b;
 }
 

@@ -128,7 +128,7 @@ static int num_sms() {
 }
 static u32 grid_for(u64 items, u32 per_block, u32 blocks_per_sm) {
   u64 need = (items + per_block - 1) / per_block;
-  u64 cap = (u64)num_sms() * blocks_per_sm;
+  u64 cap = (u64)num_sms() * blocks_per_sm * (u64)g_ckl_grid_mult;
   if (need < 1) need = 1;
   return (u32)(need < cap ? need : cap);
 }
@@ -248,9 +248,9 @@ __global__ void __launch_bounds__(256) k_run_init(Geom g, const u32* __restrict_
                                                    u32* __restrict__ runStart) {
   const u64 nwords = g.words(), stride = (u64)gridDim.x * blockDim.x;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) {
-    const u64 row = i / g.W;
+    const u64 row = fdiv(i, g.W);
     const u32 w = (u32)(i - row * g.W);
-    const u32 z = (u32)(row / g.sy), y = (u32)(row - (u64)z * g.sy);
+    const u32 z = (u32)fdiv(row, g.sy), y = (u32)(row - (u64)z * g.sy);
     const u32 dv = DV[i];
     u32 starts = dv | (w == 0 ? 1u : 0u);
     const u32 rb = rowBase[row] + wordPrefix[i];

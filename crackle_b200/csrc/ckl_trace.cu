@@ -45,7 +45,7 @@ static int sms() {
 }
 static u32 grid_cap(u64 items, u32 per_block, u32 blocks_per_sm) {
   u64 need = (items + per_block - 1) / per_block;
-  u64 cap = (u64)sms() * blocks_per_sm;
+  u64 cap = (u64)sms() * blocks_per_sm * (u64)g_ckl_grid_mult;
   if (need < 1) need = 1;
   return (u32)(need < cap ? need : cap);
 }
@@ -85,9 +85,9 @@ __global__ void __launch_bounds__(256) k_vw_build(Geom g, VGeom vg, const u32* _
     const u64 i = it * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 z = NONE32, e = 0, s = 0, c = 0;
     if (i < vg.wordsAll) {
-      const u64 row = i / vg.Wv;
+      const u64 row = fdiv(i, vg.Wv);
       const u32 w = (u32)(i - row * vg.Wv);
-      z = (u32)(row / vg.sye);
+      z = (u32)fdiv(row, vg.sye);
       const u32 y = (u32)(row - (u64)z * vg.sye);
       const u64 prow = ((u64)z * g.sy + y) * g.W;           // pixel-plane row (valid when y < sy)
       u32 r = 0, rp = 0, d = 0, u = 0;
@@ -231,6 +231,8 @@ struct TraceParams {
   const u64* offs;         // 4 arrays of (sz+1): events, stack, chain, cp
   const u32* caps;         // per slice 4 x u32
   u32* ev;                 // events
+  u32 pwChunk, exChunk;    // slots / events per warp chunk of the path walkers
+  uint4* evRec;            // per event: walk task {output offset, x, y, length | direction << 29 | flip << 31}
   u32* evCp;               // per event: exclusive codepoint offset inside the slice (creation order); one extra slot per slice
   uint2* stack;
   ChainRec* chain;
@@ -252,14 +254,19 @@ __global__ void __launch_bounds__(256) k_node_init(TraceParams P) {
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < vg.wordsAll; i += stride) {
     u32 n = P.VW[i].w;
     if (!n) continue;
-    const u64 row = i / vg.Wv;
+    const u64 row = fdiv(i, vg.Wv);
     const u32 w = (u32)(i - row * vg.Wv);
-    const u32 z = (u32)(row / vg.sye), y = (u32)(row - (u64)z * vg.sye);
+    const u32 z = (u32)fdiv(row, vg.sye), y = (u32)(row - (u64)z * vg.sye);
     u64 id = P.nodeBase[z] + P.rowBase[row] + P.nodePrefix[i];
+    const uint4 word = P.VW[i];
+    const u32 l = (word.x << 1) | (w ? (P.VW[i - 1].x >> 31) : 0u);      // left edge of vertex b = right edge of vertex b - 1
     while (n) {
       const u32 b = __ffs(n) - 1;
       n &= n - 1;
-      P.nodeVertex[id++] = y * vg.sxe + w * 32 + b;
+      P.nodeVertex[id] = y * vg.sxe + w * 32 + b;
+      // static adjacency nibble in walk-priority order: bit 0 right, 1 left, 2 down, 3 up
+      P.nodeAdj[id] = (u8)(((word.x >> b) & 1u) | (((l >> b) & 1u) << 1) | (((word.y >> b) & 1u) << 2) | (((word.z >> b) & 1u) << 3));
+      id++;
     }
   }
 }
@@ -282,46 +289,77 @@ __device__ __forceinline__ bool se_step(const uint4* __restrict__ vw, u32 Wv, u3
 // the result at BOTH ends.  Pass 0 walks the right / down slots; pass 1 walks the left / up slots that pass 0 did
 // not already fill from the other end (most super-edges leave one node rightwards or downwards and arrive at the
 // other from the left or from above, so almost every path is walked once instead of twice).
+// grid = (chunks, slices); a lane takes the next slot of its warp's chunk as soon as its current path reaches a node
+// (the refill reads the node's static adjacency nibble, so slots without an edge cost one byte load).
 #define SE_UNSET 0xFEFEFEFEu
+// Small chunks = many warps per slice = few slices in flight at once: the vertex words the walkers chase (541 KB per
+// 1024^2 slice) then stay L2-resident instead of streaming from DRAM once per step.
+#define PW_CHUNK 128u
 template <int PASS>
-__global__ void __launch_bounds__(256) k_path_walk(TraceParams P, u64 nhalf) {
+__global__ void __launch_bounds__(256) k_path_walk(TraceParams P) {
   const VGeom vg = P.vg;
-  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u32 lane = threadIdx.x & 31;
+  const u32 ltmask = (1u << lane) - 1u;
   const u32 limit = 2u * vg.sxe * vg.sye + 8u;
-  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < nhalf; t += stride) {
-    const u64 gnode = t >> 1;
-    const u32 k0 = (u32)(t & 1) * 2 + PASS;              // pass 0: right, down; pass 1: left, up
-    const u64 s = gnode * 4 + k0;
-    u32 kk = k0;
-    const u32 z = slice_of(P.nodeBase, P.g.sz, gnode);
+  for (u32 z = blockIdx.y; z < P.g.sz; z += gridDim.y) {
+    const u32 N = P.sliceNodes[z];
+    if (!N) continue;
+    const u64 nb = P.nodeBase[z];
     const u64 rowz = (u64)z * vg.sye;
     const uint4* vw = P.VW + rowz * vg.Wv;
-    const u32 v = P.nodeVertex[gnode];
-    u32 y = v / vg.sxe, x = v - y * vg.sxe;
-    uint4 word = __ldg(vw + (u64)y * vg.Wv + (x >> 5));
-    const u32 b = x & 31;
-    u32 has;
-    if (kk == 0) has = (word.x >> b) & 1u;
-    else if (kk == 2) has = (word.y >> b) & 1u;
-    else if (kk == 3) has = (word.z >> b) & 1u;
-    else has = b ? ((word.x >> (b - 1)) & 1u) : (x ? (__ldg(vw + (u64)y * vg.Wv + (x >> 5) - 1).x >> 31) : 0u);
-    if (!has) { P.seFar[s] = NONE32; P.seLen[s] = 0; continue; }
-    if (PASS == 1 && P.seFar[s] != SE_UNSET) continue;   // filled from the other end
-    u32 len = 1;
-    bool ok = true;
-    while (!se_step(vw, vg.Wv, x, y, kk, word)) {
-      if (++len > limit) { atomicExch(&P.scal[SC_ERROR], 4ull); ok = false; break; }
+    const u8* adj = P.nodeAdj + nb;
+    const u32* nodeVertex = P.nodeVertex + nb;
+    u32* seFar = P.seFar + nb * 4;
+    u32* seLen = P.seLen + nb * 4;
+    const u32 nitems = 2u * N;
+    const u32 PWC = P.pwChunk;
+    const u32 nchunks = (nitems + PWC - 1) / PWC;
+    for (u32 chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); chunk < nchunks; chunk += gridDim.x * (blockDim.x >> 5)) {
+      u32 next = chunk * PWC;
+      const u32 end = min(nitems, next + PWC);
+      bool active = false;
+      u32 x = 0, y = 0, kk = 0, len = 0, slot = 0;
+      uint4 word;
+      for (;;) {
+        const u32 idle = __ballot_sync(FULL_MASK, !active);
+        if (idle) {
+          const u32 i = next + __popc(idle & ltmask);
+          if (!active && i < end) {
+            const u32 node = i >> 1, k0 = (i & 1u) * 2u + PASS;      // pass 0: right, down; pass 1: left, up
+            const u32 s = node * 4 + k0;
+            if (!((adj[node] >> k0) & 1u)) { seFar[s] = NONE32; seLen[s] = 0; }
+            else if (PASS == 0 || seFar[s] == SE_UNSET) {            // pass 1: not filled from the other end
+              const u32 v = nodeVertex[node];
+              y = v / vg.sxe; x = v - y * vg.sxe;
+              kk = k0; len = 0; slot = s;
+              active = true;
+            }
+          }
+          next += __popc(idle);
+        }
+        if (!__any_sync(FULL_MASK, active)) {
+          if (next >= end) break;
+          continue;
+        }
+        if (active) {
+          if (++len > limit) {
+            atomicExch(&P.scal[SC_ERROR], 4ull);
+            seFar[slot] = NONE32; seLen[slot] = 0;
+            active = false;
+          } else if (se_step(vw, vg.Wv, x, y, kk, word)) {
+            const u64 row = rowz + y;
+            const u32 far = P.rowBase[row] + P.nodePrefix[row * vg.Wv + (x >> 5)] + __popc(word.w & ((1u << (x & 31)) - 1u));
+            const u32 fk = kk ^ 1u;
+            seFar[slot] = (far << 2) | fk;
+            seLen[slot] = len;
+            const u32 twin = far * 4 + fk;
+            seFar[twin] = slot;                                      // (this node << 2) | departure direction
+            seLen[twin] = len;
+            active = false;
+          }
+        }
+      }
     }
-    if (!ok) { P.seFar[s] = NONE32; P.seLen[s] = 0; continue; }
-    const u64 row = rowz + y;
-    const u32 far = P.rowBase[row] + P.nodePrefix[row * vg.Wv + (x >> 5)] + __popc(word.w & ((1u << (x & 31)) - 1u));
-    const u32 fk = kk ^ 1u;
-    const u64 nb = P.nodeBase[z];
-    P.seFar[s] = (far << 2) | fk;
-    P.seLen[s] = len;
-    const u64 twin = (nb + far) * 4 + fk;
-    P.seFar[twin] = ((u32)(gnode - nb) << 2) | k0;
-    P.seLen[twin] = len;
   }
 }
 
@@ -592,9 +630,78 @@ __global__ void __launch_bounds__(256) k_event_post(TraceParams P) {
 // direction index -> codepoint: right 1, left 3, down 2, up 0  (crackcodes.hpp:20-26)
 __device__ __forceinline__ u8 dir_code(u32 kk) { return (u8)((0x0231u >> (4 * kk)) & 0xFu); }
 
-// grid = (chunks, slices); lanes fetch the next event of their warp's chunk as soon as their current super-edge
-// is written out (same lane-refill scheme as k_path_walk).
-#define EX_CHUNK 256u
+// 6a. per event (fully parallel): the walk task of a super-edge event -- output position, start vertex, direction,
+// length, reversed/flipped inside a removed initial branch -- as one 16-byte record; 'b' / 't' escape pairs are
+// written here directly (they depend only on the previous kept symbol; kept 't's in between alternate).
+#define EX_CHUNK 128u
+#define EX_LEN_MASK 0x1FFFFFFFu        // record.w = length | direction << 29 | flip << 31
+__global__ void __launch_bounds__(256) k_event_setup(TraceParams P) {
+  const Geom g = P.g;
+  const VGeom vg = P.vg;
+  const u64 n1 = (u64)g.sz + 1;
+  for (u32 z = blockIdx.y; z < g.sz; z += gridDim.y) {
+    const u32 nch = P.sliceInfo[(u64)z * 4 + 1];
+    if (!nch) continue;
+    const ChainRec* chains = P.chain + P.offs[2 * n1 + z];
+    const u32 nev = chains[nch - 1].symEnd;            // sliceInfo[0] holds ncp by now; events end with the last chain
+    const u32* ev = P.ev + P.offs[z];
+    const u32* pre = P.evCp + P.offs[z] + z;
+    uint4* recs = P.evRec + P.offs[z];
+    u8* cpz = P.cp + P.offs[3 * n1 + z];
+    const u64 nb = P.nodeBase[z];
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nev; i += gridDim.x * blockDim.x) {
+      const u32 e = ev[i], t = e >> 30;
+      uint4 rec = make_uint4(0, 0, 0, 0);
+      if (t != EV_S) {
+        const ChainRec& c = chains[chain_of(chains, nch, i)];
+        const u32 rel = pre[i] - pre[c.symBegin];
+        if (t == EV_E) {
+          const u32 slot = e & 0x3FFFFFFFu;
+          const u32 len = P.seLen[nb * 4 + slot];
+          const u32 v = P.nodeVertex[nb + (slot >> 2)];
+          rec.z = v / vg.sxe; rec.y = v - rec.z * vg.sxe;
+          u32 flip = 0;
+          if (c.t2f && i < c.symBegin + c.t2f) {
+            // inside a removed initial branch: the move run is reversed and every move flipped
+            const u32 fcp = pre[c.symBegin + c.t2f] - pre[c.symBegin];
+            rec.x = c.outBase + (fcp - 1 - rel); flip = 1;
+          } else rec.x = c.outBase + rel;
+          if (len > EX_LEN_MASK) atomicExch(&P.scal[SC_ERROR], 4ull);
+          rec.w = (len & EX_LEN_MASK) | ((slot & 3u) << 29) | (flip << 31);
+        } else {
+          u32 tcount = 0, j = i;
+          int prev = -1;                                        // previous kept move (direction index), -1 = none
+          while (j > c.symBegin) {
+            j--;
+            const u32 q = ev[j], qt = q >> 30;
+            if (qt == EV_S) continue;
+            if (qt == EV_T) { tcount++; continue; }
+            if (qt == EV_B) break;                              // cannot happen (a 'b' is always followed by a move)
+            if (c.t2f && j < c.symBegin + c.t2f) prev = (int)((ev[c.symBegin + 1] & 3u) ^ 1u);   // reversed run ends with flip(first move)
+            else prev = (int)((P.seFar[nb * 4 + (q & 0x3FFFFFFFu)] & 3u) ^ 1u);                  // last move = opposite of arrival dir
+            break;
+          }
+          u8* ob = cpz + c.outBase + rel;
+          if (t == EV_B) {
+            // (UP,DOWN) unless first symbol of the chain or the previous codepoint is DOWN -> (LEFT,RIGHT)
+            const bool alt = (i == c.symBegin) || (tcount == 0 && prev == 2);
+            ob[0] = alt ? 3 : 0;
+            ob[1] = alt ? 1 : 2;
+          } else {
+            // (DOWN,UP) unless the previous codepoint is UP -> (RIGHT,LEFT); consecutive 't's alternate
+            const bool alt = ((prev == 3) ? 1u : 0u) ^ (tcount & 1u);
+            ob[0] = alt ? 1 : 2;
+            ob[1] = alt ? 3 : 0;
+          }
+        }
+      }
+      recs[i] = rec;
+    }
+  }
+}
+
+// 6b. the walk: grid = (chunks, slices); a lane takes the next task record of its warp's chunk as soon as its current
+// super-edge is written out, so the refill is one 16-byte load and the loop body is the step itself.
 __global__ void __launch_bounds__(256) k_expand(TraceParams P) {
   const Geom g = P.g;
   const VGeom vg = P.vg;
@@ -605,83 +712,39 @@ __global__ void __launch_bounds__(256) k_expand(TraceParams P) {
     const u32 nch = P.sliceInfo[(u64)z * 4 + 1];
     if (!nch) continue;
     const ChainRec* chains = P.chain + P.offs[2 * n1 + z];
-    const u32 nev = chains[nch - 1].symEnd;            // sliceInfo[0] holds ncp by now; events end with the last chain
-    const u32* ev = P.ev + P.offs[z];
-    const u32* pre = P.evCp + P.offs[z] + z;
+    const u32 nev = chains[nch - 1].symEnd;
+    const uint4* recs = P.evRec + P.offs[z];
     u8* cpz = P.cp + P.offs[3 * n1 + z];
-    const u64 nb = P.nodeBase[z];
     const uint4* vw = P.VW + (u64)z * vg.sye * vg.Wv;
-    const u32 nchunks = (nev + EX_CHUNK - 1) / EX_CHUNK;
+    const u32 EXC = P.exChunk;
+    const u32 nchunks = (nev + EXC - 1) / EXC;
     for (u32 chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); chunk < nchunks; chunk += gridDim.x * (blockDim.x >> 5)) {
-      u32 next = chunk * EX_CHUNK;
-      const u32 end = min(nev, next + EX_CHUNK);
-      bool active = false;
+      u32 next = chunk * EXC;
+      const u32 end = min(nev, next + EXC);
       u32 x = 0, y = 0, kk = 0, left = 0, flip = 0;
-      int step = 1;
       u8* o = nullptr;
       uint4 word;
       for (;;) {
-        const u32 idle = __ballot_sync(FULL_MASK, !active);
+        const u32 idle = __ballot_sync(FULL_MASK, left == 0);
         if (idle) {
           const u32 i = next + __popc(idle & ltmask);
-          if (!active && i < end) {
-            const u32 e = ev[i], t = e >> 30;
-            if (t != EV_S) {
-              const ChainRec& c = chains[chain_of(chains, nch, i)];
-              u8* out = cpz + c.outBase;
-              const u32 rel = pre[i] - pre[c.symBegin];
-              if (t == EV_E) {
-                const u32 slot = e & 0x3FFFFFFFu;
-                kk = slot & 3u;
-                left = P.seLen[nb * 4 + slot];
-                const u32 v = P.nodeVertex[nb + (slot >> 2)];
-                y = v / vg.sxe; x = v - y * vg.sxe;
-                if (c.t2f && i < c.symBegin + c.t2f) {
-                  // inside a removed initial branch: the move run is reversed and every move flipped
-                  const u32 fcp = pre[c.symBegin + c.t2f] - pre[c.symBegin];
-                  o = out + (fcp - 1 - rel); step = -1; flip = 1;
-                } else { o = out + rel; step = 1; flip = 0; }
-                active = left != 0;
-              } else {
-                // 'b' / 't': the pair depends on the previous kept symbol; kept 't's in between alternate
-                u32 tcount = 0, j = i;
-                int prev = -1;                                        // previous kept move (direction index), -1 = none
-                while (j > c.symBegin) {
-                  j--;
-                  const u32 q = ev[j], qt = q >> 30;
-                  if (qt == EV_S) continue;
-                  if (qt == EV_T) { tcount++; continue; }
-                  if (qt == EV_B) break;                              // cannot happen (a 'b' is always followed by a move)
-                  if (c.t2f && j < c.symBegin + c.t2f) prev = (int)((ev[c.symBegin + 1] & 3u) ^ 1u);   // reversed run ends with flip(first move)
-                  else prev = (int)((P.seFar[nb * 4 + (q & 0x3FFFFFFFu)] & 3u) ^ 1u);                  // last move = opposite of arrival dir
-                  break;
-                }
-                u8* ob = out + rel;
-                if (t == EV_B) {
-                  // (UP,DOWN) unless first symbol of the chain or the previous codepoint is DOWN -> (LEFT,RIGHT)
-                  const bool alt = (i == c.symBegin) || (tcount == 0 && prev == 2);
-                  ob[0] = alt ? 3 : 0;
-                  ob[1] = alt ? 1 : 2;
-                } else {
-                  // (DOWN,UP) unless the previous codepoint is UP -> (RIGHT,LEFT); consecutive 't's alternate
-                  const bool alt = ((prev == 3) ? 1u : 0u) ^ (tcount & 1u);
-                  ob[0] = alt ? 1 : 2;
-                  ob[1] = alt ? 3 : 0;
-                }
-              }
-            }
+          if (left == 0 && i < end) {
+            const uint4 r = __ldg(recs + i);
+            left = r.w & EX_LEN_MASK;
+            kk = (r.w >> 29) & 3u; flip = r.w >> 31;
+            x = r.y; y = r.z;
+            o = cpz + r.x;
           }
           next += __popc(idle);
         }
-        if (!__any_sync(FULL_MASK, active)) {
+        if (!__any_sync(FULL_MASK, left != 0)) {
           if (next >= end) break;
           continue;
         }
-        if (active) {
+        if (left) {
           *o = dir_code(kk ^ flip);
-          o += step;
-          if (--left == 0) active = false;
-          else se_step(vw, vg.Wv, x, y, kk, word);
+          o += flip ? -1 : 1;
+          if (--left) se_step(vw, vg.Wv, x, y, kk, word);
         }
       }
     }
@@ -700,10 +763,16 @@ void launch_trace_walk(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes, 
     return;
   }
   CUDA_CHECK(cudaMemsetAsync(T.seFar.p, 0xFE, total_nodes * 16, st));     // SE_UNSET
-  k_path_walk<0><<<grid_cap(total_nodes * 2, 256, 8), 256, 0, st>>>(P, total_nodes * 2);
-  LAUNCH_CHECK();
-  k_path_walk<1><<<grid_cap(total_nodes * 2, 256, 8), 256, 0, st>>>(P, total_nodes * 2);
-  LAUNCH_CHECK();
+  {
+    const u32 gy = g.sz < 65535u ? g.sz : 65535u;
+    u32 gx = (2u * max_nodes + 8 * P.pwChunk - 1) / (8 * P.pwChunk);
+    if (gx > 64) gx = 64;
+    if (gx < 1) gx = 1;
+    k_path_walk<0><<<dim3(gx, gy), 256, 0, st>>>(P);
+    LAUNCH_CHECK();
+    k_path_walk<1><<<dim3(gx, gy), 256, 0, st>>>(P);
+    LAUNCH_CHECK();
+  }
   // slices are replayed by the instantiation matching their node count (the others return at once)
   const size_t stack_bytes = (size_t)REPLAY_STACK * 8;
   {
@@ -732,10 +801,16 @@ void launch_trace_post(const Geom& g, TraceBufs& T, ull* scal, u64 total_ev_cap,
   LAUNCH_CHECK();
   if (total_ev_cap) {
     const u64 per_slice = (total_ev_cap + g.sz - 1) / g.sz;
-    u32 gx = (u32)((per_slice + 8 * EX_CHUNK - 1) / (8 * EX_CHUNK));
-    if (gx > 32) gx = 32;
+    u32 gx = (u32)((per_slice + 8 * P.exChunk - 1) / (8 * P.exChunk));
+    if (gx > 64) gx = 64;
     if (gx < 1) gx = 1;
-    k_expand<<<dim3(gx, g.sz < 65535u ? g.sz : 65535u), 256, 0, st>>>(P);
+    const u32 gy = g.sz < 65535u ? g.sz : 65535u;
+    u32 gs = (u32)((per_slice + 255) / 256);
+    if (gs > 64) gs = 64;
+    if (gs < 1) gs = 1;
+    k_event_setup<<<dim3(gs, gy), 256, 0, st>>>(P);
+    LAUNCH_CHECK();
+    k_expand<<<dim3(gx, gy), 256, 0, st>>>(P);
     LAUNCH_CHECK();
   }
   // total codepoints (for the "all slices empty" rule, crackle.hpp:107-118)
@@ -802,9 +877,17 @@ static TraceParams make_params(const Geom& g, TraceBufs& T, ull* scal) {
   P.seFar = T.seFar.as<u32>(); P.seLen = T.seLen.as<u32>(); P.nodeAdj = T.nodeAdj.as<u8>();
   P.offs = T.offs.as<u64>();
   P.caps = T.bounds.as<u32>() + (u64)g.sz * 4;
-  P.ev = T.ev.as<u32>(); P.evCp = T.evCp.as<u32>(); P.stack = T.stack.as<uint2>(); P.chain = T.chain.as<ChainRec>();
+  P.ev = T.ev.as<u32>(); P.evRec = T.evRec.as<uint4>(); P.evCp = T.evCp.as<u32>(); P.stack = T.stack.as<uint2>(); P.chain = T.chain.as<ChainRec>();
   P.cp = T.cp.as<u8>(); P.sliceInfo = T.sliceInfo.as<u32>();
   P.scal = scal;
+  static u32 pwc = 0, exc = 0;
+  if (!pwc) {
+    const char* a = getenv("CKL_PW_CHUNK"); const char* b = getenv("CKL_EX_CHUNK");     // tuning aids
+    const int va = a ? atoi(a) : 0, vb = b ? atoi(b) : 0;
+    exc = vb >= 32 ? (u32)vb : EX_CHUNK;
+    pwc = va >= 32 ? (u32)va : PW_CHUNK;
+  }
+  P.pwChunk = pwc; P.exChunk = exc;
   return P;
 }
 

@@ -143,6 +143,11 @@ CKL_API int ckl_prof_read(ckl_ctx* ctx, char* buf, size_t cap);
  * is what torch uses by default).  ckl_ctx_own_stream goes back to the context's private non-blocking stream. */
 CKL_API int ckl_ctx_set_stream(ckl_ctx* ctx, void* stream);
 CKL_API int ckl_ctx_own_stream(ckl_ctx* ctx);
+/* z-chunk pipelining of ckl_compress / ckl_decompress: large volumes are processed as K z-ranges on child contexts
+ * (own streams + workspaces) so the latency-bound stages of one range overlap the bandwidth-bound stages of the others;
+ * the chunks are merged like the reference merges z-slabs (crackle/operations.py:424-548 zstack) -- output bytes are
+ * identical to the unchunked path.  chunks: 0 = automatic (default), 1 = off, K = always K chunks. */
+CKL_API int ckl_ctx_set_chunks(ckl_ctx* ctx, int chunks);
 /* Number of kernels this library has launched in this process. */
 CKL_API uint64_t ckl_launch_count(void);
 /* CRC-32C (Castagnoli) of a host or device buffer, computed on the GPU (src/crc.hpp:39-57). */
