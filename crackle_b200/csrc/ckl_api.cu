@@ -302,6 +302,7 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   const u32 maxNodes = (u32)c->hscal2[SC_MAXNODES];
   if (maxNodes >= (1u << 28)) throw CklError(CKL_ERR_ARG, "crackle_b200: slice has too many crack-graph nodes");
   c->tr.nodeVertex.ensure(nodes * 4 + 16);
+  c->tr.nodeP.ensure(nodes * 4 + 16);
   c->tr.nodeAdj.ensure(nodes + 16);
   c->tr.seFar.ensure(nodes * 16 + 16);
   c->tr.seLen.ensure(nodes * 16 + 16);

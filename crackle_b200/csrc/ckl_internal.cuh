@@ -44,7 +44,8 @@ void launch_crc_finalize_slices(u32* sliceCrc, u32 sz, u32 init_term, cudaStream
 
 // ---- tracing + packing (ckl_trace.cu) ------------------------------------------------------------------
 struct TraceBufs {
-  DBuf VW;                                      // uint4 {r,d,u,n} per 32-vertex word of the (sx+1) x (sy+1) vertex grid
+  DBuf VW;                                      // uint4 = 32 adjacency nibbles per 32-vertex word of the (sx+1) x (sy+1) vertex grid
+  DBuf NM, nodeP;                               // node mask per 32-vertex word; padded linear vertex index per node
   DBuf nodePrefix, rowNodes, rowBase;           // node numbering: per vertex word / per vertex row
   DBuf sliceNodes, nodeBase;                    // per slice: node count (u32), first global node index (u64 x (sz+1))
   DBuf nodeVertex, nodeAdj;                     // per node: vertex index (u32), remaining-edge nibble (u8, global replay)
