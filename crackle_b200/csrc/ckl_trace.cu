@@ -547,26 +547,24 @@ __global__ void __launch_bounds__(32) k_replay(TraceParams P) {
       else {
         u32 node = start, sp = 0, low = 0, ne = nev;          // ne: running event index of the slice; low: lowest stack index valid in the ring
         const u32 begin = nev;
-        const u32 evLimit = evCap - 2;
-        bool firstT = true, t2 = false;
-        u32 t2f = 0, poppedB = 0, popMark = NONE32, adjStart = nodeVertex[start];
+        bool firstT = true;
+        u32 t2f = 0, adjStart = nodeVertex[start];
         typename NodeStore<MODE>::Rec w = S.load(node);
         const u32 a0 = S.adjacency(w);
         const bool firstIsB = (a0 & (a0 - 1)) != 0;           // the chain opens with a 'b'
+        // The serial loop only records what happened: moves, 'b's, and 't's carrying the event index of the 'b' they
+        // return to.  Spurious branches (remove_spurious_branches) are marked afterwards, in parallel, by k_event_post.
+        // Event / stack capacities are exact upper bounds (k_trace_caps), so the loop carries no capacity checks.
         for (;;) {
-          if (ne > evLimit) { atomicExch(&P.scal[SC_ERROR], 1ull); ok = false; break; }
           const u32 a = S.adjacency(w);
-          if (a == 0) {
-            // a 't': dead end after a move, or -- directly after a pop -- a spurious branch (remove_spurious_branches)
-            if (firstT) {
+          if (a == 0) {                                        // dead end: a 't'
+            if (__builtin_expect(firstT, 0)) {
               firstT = false;      // no pop yet, so the stack depth is the number of 'b's so far
-              if (sp == 1 && firstIsB) { t2 = true; t2f = ne - begin; adjStart = nodeVertex[node]; }   // remove_initial_branch applies
+              if (sp == 1 && firstIsB) { t2f = ne - begin; adjStart = nodeVertex[node]; }   // remove_initial_branch applies
             }
-            if (ne == popMark && !(t2 && poppedB == begin)) { st_ev(ev, poppedB, (u32)EV_S << 30); st_ev(ev, ne++, (u32)EV_S << 30); }
-            else st_ev(ev, ne++, (u32)EV_T << 30);
-            if (sp == 0) break;
+            if (sp == 0) { st_ev(ev, ne++, ((u32)EV_T << 30) | 0x3FFFFFFFu); break; }
             --sp;
-            if (sp < low) {                                    // below the ring: refill from the global copy
+            if (__builtin_expect(sp < low, 0)) {               // below the ring: refill from the global copy
               const u32 lo2 = sp + 1 >= REPLAY_REFILL ? sp + 1 - REPLAY_REFILL : 0u;
               for (u32 base = lo2; base <= sp; base += 16) {
                 uint2 t[16];
@@ -578,25 +576,26 @@ __global__ void __launch_bounds__(32) k_replay(TraceParams P) {
               low = lo2;
             }
             const uint2 e = lds64(ssa + (sp & (REPLAY_STACK - 1)) * 8u);
+            st_ev(ev, ne++, ((u32)EV_T << 30) | e.y);          // payload: the 'b' this 't' returns to
             node = e.x;
-            poppedB = e.y;
-            popMark = ne;                                      // a 't' emitted before any other event is spurious
             w = S.load(node);
             continue;
           }
-          if (a & (a - 1)) {                                  // popcount > 1: branch point
-            if (sp >= stackCap) { atomicExch(&P.scal[SC_ERROR], 2ull); ok = false; break; }
-            const uint2 e = make_uint2(node, ne);
-            sts64(ssa + (sp & (REPLAY_STACK - 1)) * 8u, e);
-            gstack[sp] = e;
-            if (sp >= low + REPLAY_STACK) low = sp - REPLAY_STACK + 1;
-            sp++;
-            st_ev(ev, ne++, (u32)EV_B << 30);
-          }
+          // branch point (popcount > 1): push, branch-free -- the slot above the top of the stack is scratch, and the
+          // 'b' event written here is overwritten by the move below when nothing was pushed
+          const u32 push = (a & (a - 1)) ? 1u : 0u;
+          const uint2 e = make_uint2(node, ne);
+          sts64(ssa + (sp & (REPLAY_STACK - 1)) * 8u, e);
+          gstack[sp] = e;
+          st_ev(ev, ne, (u32)EV_B << 30);
+          low = max(low, max(sp + 1u, (u32)REPLAY_STACK) - REPLAY_STACK);   // the write above (pushed or scratch) replaced entry sp - REPLAY_STACK
+          sp += push; ne += push;
           const u32 k = (0x12131210u >> (2u * a)) & 3u;        // ctz of the nibble by table (priority: right, left, down, up)
           st_ev(ev, ne++, ((u32)EV_E << 30) | (node * 4 + k));
           S.take(node, k, w);
         }
+        if (ne > evCap || sp > stackCap) { atomicExch(&P.scal[SC_ERROR], 1ull); ok = false; }
+        const bool t2 = t2f != 0;
         nev = ne;
         ChainRec& rec = chains[nch];
         rec.adjStart = adjStart;
@@ -634,6 +633,23 @@ __global__ void __launch_bounds__(256) k_event_post(TraceParams P) {
     ChainRec* chains = P.chain + P.offs[2 * n1 + z];
     const u32* seLen = P.seLen + P.nodeBase[z] * 4;
     const u32 nev = P.sliceInfo[(u64)z * 4 + 0], nch = P.sliceInfo[(u64)z * 4 + 1];
+    // (0) remove_spurious_branches (crackcodes.hpp:250-281): a 't' directly after a 't' closes a branch that emitted no
+    // symbol -- that 't' and the 'b' the previous 't' returned to (its payload) disappear, unless that 'b' is the chain's
+    // first symbol and the initial branch is being removed.  Types change to 's' with the payload kept, so a neighbour
+    // reading a converted 't' still finds its payload; a 'b' is always followed by a move, never by a 't'.
+    for (u32 i = threadIdx.x; i < nev; i += blockDim.x) {
+      const u32 e = ev[i];
+      if ((e >> 30) != EV_T || i == 0) continue;
+      const u32 q = ev[i - 1], qt = q >> 30;
+      if (qt != EV_T && qt != EV_S) continue;
+      const ChainRec& c = chains[chain_of(chains, nch, i)];
+      if (i <= c.symBegin) continue;
+      const u32 pb = q & 0x3FFFFFFFu;
+      if (c.t2f && pb == c.symBegin) continue;
+      ev[pb] = (u32)EV_S << 30;
+      ev[i] = ((u32)EV_S << 30) | (e & 0x3FFFFFFFu);
+    }
+    __syncthreads();
     // (a) remove_initial_branch: the leading 'b' and the first 't' of the chain disappear
     for (u32 c = threadIdx.x; c < nch; c += blockDim.x)
       if (chains[c].t2f) { ev[chains[c].symBegin] = (u32)EV_S << 30; ev[chains[c].symBegin + chains[c].t2f] = (u32)EV_S << 30; }
