@@ -540,11 +540,39 @@ static void ensure_crcH(CclBufs& B, u32 sxy, const CrcTables* d_tables, cudaStre
 //   MODE 1 (decompress): label of the run = uniq[key[keyBase[z] + comp]]   (labels::decode_flat, labels.hpp:453-506)
 // grid = (chunks, slices): no per-run slice search.
 struct RunLabelSrc { const u8* uniq; const u8* keys; u64 n_uniq, n_keys; int sw, kw; const u64* keyBase; u64* runLabel; };
-__device__ __forceinline__ u64 ld_le_dev(const u8* p, int w) {
+// little-endian field of a compile-time width at an arbitrary (unaligned) stream offset
+template <int W>
+__device__ __forceinline__ u64 ld_le_w(const u8* __restrict__ p) {
   u64 v = 0;
-  for (int i = 0; i < w; i++) v |= (u64)p[i] << (8 * i);
+#pragma unroll
+  for (int i = 0; i < W; i++) v |= (u64)p[i] << (8 * i);
   return v;
 }
+__device__ __forceinline__ u64 ld_le_dev(const u8* __restrict__ p, int w) {
+  switch (w) {                                             // warp-uniform
+    case 1: return p[0];
+    case 2: return ld_le_w<2>(p);
+    case 4: return ld_le_w<4>(p);
+    default: return ld_le_w<8>(p);
+  }
+}
+// d(x) * h(x) for the 16-bit differences of component ids: the eight multiples h x^16 .. h x^23 once, then the two bytes of
+// d select among them (Horner over bytes: the high byte's sum is multiplied by x^8 through the byte table).
+__device__ __forceinline__ u32 gf_mul_d16(u32 d, u32 h, const u32* t0) {
+  h = t0[h & 0xFF] ^ (h >> 8);                            // * x^8
+  h = t0[h & 0xFF] ^ (h >> 8);                            // * x^16: the 16 low bits of d are x^16 .. x^31
+  u32 a = 0, b = 0;                                       // a: bits 15..8 of d (x^0 .. x^7), b: bits 7..0 (x^8 .. x^15)
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    a ^= h & (0u - ((d >> (15 - j)) & 1u));
+    b ^= h & (0u - ((d >> (7 - j)) & 1u));
+    h = (h >> 1) ^ (CKL_CRC_POLY & (0u - (h & 1u)));
+  }
+  return a ^ t0[b & 0xFF] ^ (b >> 8);
+}
+
+// One warp owns a contiguous range of a slice's runs and walks it 32 runs at a time, so the component of the run before
+// lane 0's comes from the previous iteration (one lone find per range instead of one per 32 runs).
 template <int MODE>
 __global__ void __launch_bounds__(256) k_run_finish(Geom g, const u32* __restrict__ parent, const u32* __restrict__ sliceRuns,
                                                      const u64* __restrict__ runBase, const u32* __restrict__ compRank,
@@ -555,23 +583,30 @@ __global__ void __launch_bounds__(256) k_run_finish(Geom g, const u32* __restric
   for (u32 i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t[0][i];
   __syncthreads();
   const u32 lane = threadIdx.x & 31;
+  const u32 wps = gridDim.x * (blockDim.x >> 5);                  // warps per slice
+  const u32 wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   for (u32 z = blockIdx.y; z < g.sz; z += gridDim.y) {
     const u32 n = sliceRuns[z];
     const u64 gb = runBase[z];
     const u32* par = parent + gb;
     const u32* rank = compRank + gb;
+    const u32 L = (((n + wps - 1) / wps) + 31u) & ~31u;           // runs per warp, a multiple of 32
+    const u32 lo = wid * L;
+    if (lo >= n) continue;
+    const u32 hi = min(n, lo + L);
+    const u64 cb = compBase[z];
+    const u64 kb = MODE == 1 ? src.keyBase[z] : 0;
+    u32 carry = lo ? rank[uf_find(par, lo - 1)] : 0u;             // component of the run before the range (warp-uniform)
     u32 x = 0;
-    const u32 per = gridDim.x * blockDim.x;
-    const u32 nloop = (n + per - 1) / per;
-    for (u32 k = 0; k < nloop; k++) {
-      const u32 i = k * per + blockIdx.x * blockDim.x + threadIdx.x;
+    for (u32 i0 = lo; i0 < hi; i0 += 32) {
+      const u32 i = i0 + lane;
       u32 c = 0;
-      if (i < n) {
+      if (i < hi) {
         const u32 root = uf_find(par, i);
         c = rank[root];
-        if (MODE == 0) { if (root == i) compPix[compBase[z] + c] = runStart[gb + i]; }
+        if (MODE == 0) { if (root == i) compPix[cb + c] = runStart[gb + i]; }
         else {
-          const u64 ki = src.keyBase[z] + c;
+          const u64 ki = kb + c;
           u64 label = 0;
           if (ki < src.n_keys) {
             const u64 key = ld_le_dev(src.keys + ki * (u64)src.kw, src.kw);
@@ -581,10 +616,14 @@ __global__ void __launch_bounds__(256) k_run_finish(Geom g, const u32* __restric
         }
       }
       u32 cprev = __shfl_up_sync(FULL_MASK, c, 1);
-      if (lane == 0) cprev = (i > 0 && i < n) ? rank[uf_find(par, i - 1)] : 0u;
-      if (i < n) {
+      if (lane == 0) cprev = carry;
+      carry = __shfl_sync(FULL_MASK, c, 31);
+      if (i < hi) {
         const u32 d = c ^ cprev;
-        if (d) x ^= gf_mul_id(d, H[(u32)g.sxy - runStart[gb + i]], t0);
+        if (d) {
+          const u32 h = H[(u32)g.sxy - runStart[gb + i]];
+          x ^= d < 65536u ? gf_mul_d16(d, h, t0) : gf_mul(d, h);
+        }
       }
     }
     x = __reduce_xor_sync(FULL_MASK, x);
