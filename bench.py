@@ -34,6 +34,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--prof", action="store_true", help="print per-stage timings to stderr")
+    ap.add_argument("--chunks", type=int, default=0, help="z-chunk pipelining: 0 = library default (host-resident volumes only), 1 = off, K = force")
     return ap.parse_args()
 
 
@@ -175,6 +176,7 @@ def main():
     ctx = cb.Context(local)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
+    ctx.set_chunks(args.chunks)
 
     # each rank owns a z-slab of a (sx, sy, sz*world) volume: weak scaling, per-GPU work fixed
     vol = synth.jittered_voronoi_torch(shape, args.cell, np.uint64, seed=0, id_bits=40, device="cuda", z0=rank * sz,
@@ -262,7 +264,10 @@ def main():
         roof = {"bound": "hbm", "kernel": tr.get("kernel", dom), "stage": dom, "side": "decompress" if dom.startswith("d_") else "compress",
                 "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
                 "traffic": tr.get("dram_bytes"), "algorithmic_bytes_per_launch": alg, "kernel_ms": stage_ms[dom],
-                "note": "dominant stage is the latency-bound serial chain replay; the full-width streaming kernels are listed under roofline_streaming"}
+                "note": ("stage with the largest CUDA-event time inside the timed region (stages of the tracing chain and of the CCL / label "
+                         "chain overlap on two streams); `achieved` = algorithmic bytes of the whole compress (or decompress) call / that stage's "
+                         "time.  trace_walk = node numbering + path walkers + the serial chain replay (k_replay, one warp per slice, latency-"
+                         "bound); the full-width HBM streaming kernels are listed under roofline_streaming")}
         for k in ("edges", "d_paint"):
             if k in stage_ms:
                 a2 = alg / (stage_ms[k] * 1e-3) / 1e9
@@ -322,7 +327,9 @@ def main():
         assert torch.equal(hout.view(torch.int64), hvol.view(torch.int64))
         line["e2e"] = {"value": 2.0 * V / te / 1e9, "unit": "GVox/s", "h2d_bytes_per_step": int(V * 8 + n),
                        "d2h_bytes_per_step": int(n + V * 8), "ms_per_step": te * 1e3,
-                       "api": "ckl_compress / ckl_decompress with pinned HOST buffers (what fastcrackle.compress/decompress bind)"}
+                       "api": "ckl_compress / ckl_decompress with pinned HOST buffers (what fastcrackle.compress/decompress bind)",
+                       "chunks": "library default: 4 z-chunks on child contexts for host-resident volumes, so H2D / D2H copies of one chunk "
+                                 "overlap the kernels of the others" if args.chunks == 0 else args.chunks}
         del hvol, hout, hstream
 
     if not args.no_cpu and world == 1 and rank == 0:

@@ -94,6 +94,7 @@ struct ckl_ctx {
   TraceBufs tr;
   MarkovBufs mk;
   LabelBufs lb;
+  LabelBufs lb_merge;      // scratch of ckl_sort_unique_u64 (its `mapping` is borrowed from the caller per call)
   DecodeBufs dc;
   DBuf result; u64 result_bytes = 0;
   DBuf stream_dev, out_dev, tmp32, keys, codes;
@@ -1140,7 +1141,7 @@ extern "C" int ckl_crc32c(ckl_ctx* c, const void* data, int on_device, uint64_t 
 extern "C" int ckl_sort_unique_u64(ckl_ctx* c, uint64_t* data_device, uint64_t n, int key_bytes, uint64_t* n_unique) {
   API_BEGIN(c)
   if (!n_unique) throw CklError(CKL_ERR_ARG, "crackle_b200: null output");
-  LabelBufs tmp;
+  LabelBufs& tmp = c->lb_merge;                               // context-owned scratch: steady-state calls do no cudaMalloc
   tmp.mapping.p = data_device; tmp.mapping.cap = n * 8;      // borrowed, not owned
   u64 cnt = 0;
   try {

@@ -14,6 +14,8 @@ crackle/operations.py:258-295 `_zstack_flat_labels` and :424-548 `zstack`):
 The per-shard compute is behind a small backend interface so the host logic can be exercised on CPU with gloo
 (tests/test_dist_cpu.py supplies an oracle-backed fake); the product backend is `CudaShardBackend` (C-ABI)."""
 import ctypes
+import os
+import time
 
 import numpy as np
 import torch
@@ -171,9 +173,22 @@ class ShardedCodec:
         return [o[:c] for o, c in zip(out, counts)]
 
     # -- compress --------------------------------------------------------------------------------------------
+    def _mark(self, name):
+        """CKL_DIST_PROF=1: wall-clock phase times of compress() (device synchronised), printed by rank 0."""
+        if not self._prof:
+            return
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        t = time.perf_counter()
+        self._marks.append((name, (t - self._t0) * 1e3))
+        self._t0 = t
+
     def compress(self, vol, z0, sz_total, markov_model_order=0, fortran_order=True):
         be, dist, W, R = self.be, self.dist, self.world, self.rank
+        self._prof = os.environ.get("CKL_DIST_PROF") == "1"
+        self._marks, self._t0 = [], time.perf_counter()
         s = be.begin(vol)
+        self._mark("begin")
         sx, sy, sz_local = be.shape
         data_width = be.width
         # (1) global scalars from the per-shard summaries
@@ -188,8 +203,10 @@ class ShardedCodec:
         assert sum(sz_all) == sz_total, "shards do not cover the volume"
         permissible = pairs < voxels // 2          # crackle.hpp:50-55
         stored = byte_width(max_label)             # crackle.hpp:233-235
+        self._mark("summaries")
         # (2) per-shard encode
         nu_local, ncomp_local, ncp_local = be.encode(permissible, stored, markov_model_order)
+        self._mark("encode")
         cnt = self._all_gather_i64([nu_local, ncomp_local, ncp_local])
         nu_all = [int(c[0]) for c in cnt]
         ncomp_all = [int(c[1]) for c in cnt]
@@ -200,6 +217,7 @@ class ShardedCodec:
         parts = self._all_gather_var(be.unique(), nu_all)
         guniq = be.sort_unique(torch.cat(parts) if W > 1 else parts[0].clone(), stored)
         nu = int(guniq.numel())
+        self._mark("unique_merge")
         # (4) global markov statistics
         gstats = None
         if order > 0:
@@ -207,12 +225,14 @@ class ShardedCodec:
             dist.all_reduce(gstats, op=dist.ReduceOp.SUM)     # int32 two's complement add == uint32 wrap (markov.hpp:210-213)
         # (5) per-shard pieces against the global table / model
         pc = be.finish(guniq, gstats)
+        self._mark("finish")
         nz, code_sizes, crcs = be.small_pieces()
         sizes = self._all_gather_i64([pc["keys_bytes"], pc["codes_bytes"]])
         keys_all = [int(a[0]) for a in sizes]
         codes_all = [int(a[1]) for a in sizes]
         small = torch.from_numpy(np.concatenate([nz.view(np.int64), code_sizes.astype(np.int64), crcs.astype(np.int64)])).to(self._dev())
         smalls = self._all_gather_var(small, [3 * z for z in sz_all])
+        self._mark("small_gathers")
         # (6) gather keys and codes on rank 0 straight into their place in the stream
         kw, cw = byte_width(nu), byte_width(sx * sy)
         labels_bytes = 8 + nu * stored + sz_total * cw + sum(keys_all)
@@ -242,10 +262,12 @@ class ShardedCodec:
             if codes_all[R]:
                 dist.send(ct[: codes_all[R]], dst=0)
             return None
+        self._mark("keys_codes_gather")
         # (7) rank 0: the small sections (crackle.hpp:171-216, labels.hpp:123-152)
-        nz_g = np.concatenate([p.cpu().numpy()[: z].view(np.uint64) for p, z in zip(smalls, sz_all)])
-        cs_g = np.concatenate([p.cpu().numpy()[z: 2 * z].astype(np.uint32) for p, z in zip(smalls, sz_all)])
-        cr_g = np.concatenate([p.cpu().numpy()[2 * z: 3 * z].astype(np.uint32) for p, z in zip(smalls, sz_all)])
+        sm_np = [p.cpu().numpy() for p in smalls]
+        nz_g = np.concatenate([p[: z].view(np.uint64) for p, z in zip(sm_np, sz_all)])
+        cs_g = np.concatenate([p[z: 2 * z].astype(np.uint32) for p, z in zip(sm_np, sz_all)])
+        cr_g = np.concatenate([p[2 * z: 3 * z].astype(np.uint32) for p, z in zip(sm_np, sz_all)])
         zidx = cs_g.astype("<u4").tobytes()
         uniq_np = guniq.cpu().numpy().view(np.uint64)
         head = header_bytes(data_width, stored, int(permissible), fortran_order, order, sx, sy, sz_total, labels_bytes)
@@ -259,6 +281,9 @@ class ShardedCodec:
         lcrc = be.crc32c(final[off_lab:off_model])
         tail = int(lcrc).to_bytes(4, "little") + cr_g.astype("<u4").tobytes()
         final[total - len(tail):] = be.to_device(tail)
+        self._mark("assemble")
+        if self._prof:
+            print("CKL_DIST_PROF " + " ".join(f"{k}={v:.2f}" for k, v in self._marks), flush=True)
         return final
 
     # -- decompress ------------------------------------------------------------------------------------------
