@@ -15,7 +15,9 @@
 
 void launch_exscan_u32_u64(const u32* in, u32 n, u32 stride, u64* out, ull* total_out, u64 add_each, cudaStream_t st);
 void launch_markov_copy(const Geom& g, TraceBufs& T, MarkovBufs& M, u8* dst, cudaStream_t st);
-void launch_trace_walk(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes, u32 max_nodes, cudaStream_t st);
+bool launch_trace_nodes(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes, cudaStream_t st);
+void launch_trace_paths(const Geom& g, TraceBufs& T, ull* scal, u32 max_nodes, cudaStream_t st);
+void launch_trace_replay(const Geom& g, TraceBufs& T, ull* scal, u32 max_nodes, cudaStream_t st);
 void launch_trace_post(const Geom& g, TraceBufs& T, ull* scal, u64 total_ev_cap, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------------
@@ -313,9 +315,17 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   c->tr.stack.ensure(stackCap * 8);
   c->tr.chain.ensure(chainCap * sizeof(ChainRec));
   c->tr.cp.ensure(cpCap);
-  c->prof.begin("trace_walk", st2);
-  launch_trace_walk(g, c->tr, c->scal, nodes, maxNodes, st2);
+  c->prof.begin("trace_nodes", st2);
+  const bool any_nodes = launch_trace_nodes(g, c->tr, c->scal, nodes, st2);
   c->prof.end(st2);
+  if (any_nodes) {
+    c->prof.begin("trace_paths", st2);
+    launch_trace_paths(g, c->tr, c->scal, maxNodes, st2);
+    c->prof.end(st2);
+    c->prof.begin("trace_replay", st2);                    // k_replay alone: the serial, latency-bound kernel
+    launch_trace_replay(g, c->tr, c->scal, maxNodes, st2);
+    c->prof.end(st2);
+  }
   c->prof.begin("trace_post", st2);
   launch_trace_post(g, c->tr, c->scal, evCap, st2);
   c->prof.end(st2);

@@ -832,27 +832,34 @@ __global__ void __launch_bounds__(256) k_expand(TraceParams P) {
 
 static TraceParams make_params(const Geom& g, TraceBufs& T, ull* scal);
 
-void launch_trace_walk(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes, u32 max_nodes, cudaStream_t st) {
+// node numbering -> vertices; returns false when the shard has no crack-graph nodes at all
+bool launch_trace_nodes(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes, cudaStream_t st) {
   TraceParams P = make_params(g, T, scal);
   const VGeom vg = P.vg;
   k_node_init<<<grid_cap(vg.wordsAll, 256, 8), 256, 0, st>>>(P);
   LAUNCH_CHECK();
   if (!total_nodes) {
     CUDA_CHECK(cudaMemsetAsync(T.sliceInfo.p, 0, (u64)g.sz * 16, st));
-    return;
+    return false;
   }
   CUDA_CHECK(cudaMemsetAsync(T.seFar.p, 0xFE, total_nodes * 16, st));     // SE_UNSET
-  {
-    const u32 gy = g.sz < 65535u ? g.sz : 65535u;
-    u32 gx = (2u * max_nodes + 8 * P.pwChunk - 1) / (8 * P.pwChunk);
-    if (gx > 64) gx = 64;
-    if (gx < 1) gx = 1;
-    k_path_walk<0><<<dim3(gx, gy), 256, 0, st>>>(P);
-    LAUNCH_CHECK();
-    k_path_walk<1><<<dim3(gx, gy), 256, 0, st>>>(P);
-    LAUNCH_CHECK();
-  }
-  // slices are replayed by the instantiation matching their node count (the others return at once)
+  return true;
+}
+// super-edges between nodes
+void launch_trace_paths(const Geom& g, TraceBufs& T, ull* scal, u32 max_nodes, cudaStream_t st) {
+  TraceParams P = make_params(g, T, scal);
+  const u32 gy = g.sz < 65535u ? g.sz : 65535u;
+  u32 gx = (2u * max_nodes + 8 * P.pwChunk - 1) / (8 * P.pwChunk);
+  if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
+  k_path_walk<0><<<dim3(gx, gy), 256, 0, st>>>(P);
+  LAUNCH_CHECK();
+  k_path_walk<1><<<dim3(gx, gy), 256, 0, st>>>(P);
+  LAUNCH_CHECK();
+}
+// the serial chain replay: slices are replayed by the instantiation matching their node count (the others return at once)
+void launch_trace_replay(const Geom& g, TraceBufs& T, ull* scal, u32 max_nodes, cudaStream_t st) {
+  TraceParams P = make_params(g, T, scal);
   const size_t stack_bytes = (size_t)REPLAY_STACK * 8;
   {
     const u32 n0 = max_nodes < REPLAY_CAP0 ? max_nodes : REPLAY_CAP0;
