@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -78,8 +79,18 @@ struct Prof {
 };
 #define STAGE(c, name, ...) do { (c)->prof.begin(name, (c)->st); __VA_ARGS__; (c)->prof.end((c)->st); } while (0)
 
+// Staggered start of concurrent z-chunks: chunk k's decode stage starts (on the GPU) when chunk k-1's has finished, so the
+// chunks run one stage apart -- a latency-bound stage of one beside a bandwidth- or issue-bound stage of another -- instead
+// of in lockstep, where identical kernels only share the machine.
+struct Stagger {
+  std::vector<cudaEvent_t> ev;
+  std::atomic<int> seq{0};           // number of chunks that have recorded their event (host-side ordering of record / wait)
+};
+
 struct ckl_ctx {
   Prof prof;
+  Stagger* stg = nullptr;            // set on chunk contexts for the duration of a staggered call
+  int stg_index = 0;
   int device = 0;
   cudaStream_t st = nullptr, own_st = nullptr;
   cudaStream_t st2 = nullptr;            // side stream: the tracing chain runs beside the CCL / label chain
@@ -977,11 +988,18 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
       ensure_kids(c, K);
       GridMultScope fine_grids;
       fork_kids(c, K);
-      run_chunks(c, K, [&](int k) {
-        const i64 a = z_start + (i64)(szr * (u64)k / (u64)K), b = z_start + (i64)(szr * (u64)(k + 1) / (u64)K);
-        const u64 o = (u64)(a - z_start) * sxy * (u64)ow;
-        decompress_impl(c->kids[k], hbin, dstream, num_bytes, a, b, has_label, label, (u8*)out + o, out_on_device, (u64)(b - a) * sxy * (u64)ow);
-      });
+      Stagger stg;
+      for (int k = 0; k < K; k++) { stg.ev.push_back(c->kids[k]->ev_join); c->kids[k]->stg = &stg; c->kids[k]->stg_index = k; }
+      try {
+        run_chunks(c, K, [&](int k) {
+          const i64 a = z_start + (i64)(szr * (u64)k / (u64)K), b = z_start + (i64)(szr * (u64)(k + 1) / (u64)K);
+          const u64 o = (u64)(a - z_start) * sxy * (u64)ow;
+          try {
+            decompress_impl(c->kids[k], hbin, dstream, num_bytes, a, b, has_label, label, (u8*)out + o, out_on_device, (u64)(b - a) * sxy * (u64)ow);
+          } catch (...) { stg.seq.store(1 << 30, std::memory_order_release); throw; }     // never leave a later chunk spinning
+        });
+      } catch (...) { for (int k = 0; k < K; k++) c->kids[k]->stg = nullptr; throw; }
+      for (int k = 0; k < K; k++) c->kids[k]->stg = nullptr;
       join_kids(c, K);
       CUDA_CHECK(cudaStreamSynchronize(st));
       merge_kid_prof(c, K);
@@ -1019,6 +1037,10 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
     wordOff[szr] = tw;
   }
   const u64 total_words = wordOff[szr];
+  if (c->stg) {                      // staggered chunk: wait (on the GPU) for the previous chunk's decode stage
+    while (c->stg->seq.load(std::memory_order_acquire) < c->stg_index) std::this_thread::yield();
+    if (c->stg_index > 0) CUDA_CHECK(cudaStreamWaitEvent(st, c->stg->ev[c->stg_index - 1], 0));
+  }
   c->prof.begin("d_decode", st);
   bool decoded = false;
   if (parallel_ok) {
@@ -1039,6 +1061,11 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
                          D.stack.as<u32>(), D.stackOff.as<u64>(), c->scal, st);
   }
   c->prof.end(st);
+  if (c->stg) {
+    CUDA_CHECK(cudaEventRecord(c->stg->ev[c->stg_index], st));
+    int expect = c->stg_index;
+    c->stg->seq.compare_exchange_strong(expect, c->stg_index + 1, std::memory_order_release);
+  }
   launch_planes_from_cracks(g, (int)h.crack_format, c->DV.as<u32>(), c->DH.as<u32>(), st);
   STAGE(c, "d_ccl_count", launch_ccl_count(g, c->DV.as<u32>(), c->ccl, c->scal, st));
   read_scalars(c);

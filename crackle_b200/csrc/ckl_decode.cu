@@ -417,14 +417,47 @@ __device__ __forceinline__ int2 disp_before(const u32* __restrict__ Mz, const u3
 
 // serial over the events of a slice: lanes load 32 events and their segment displacements, lane 0 runs the chain /
 // revisit-stack logic.  Outputs per event: start position of its segment and Q at the segment's first codepoint.
+// per event (fully parallel): displacement of the segment that ends at the event (written to segStart, which the chain
+// pass below reads and then overwrites with the segment's start position) and Q at the segment's first codepoint
+__global__ void __launch_bounds__(256) k_dec_evsum(const DecSlice* __restrict__ ds, u32 sz, const u32* __restrict__ Mw, const u32* __restrict__ Sw,
+                                                    const int2* __restrict__ Qw, const u64* __restrict__ evOff, const u32* __restrict__ evIdx,
+                                                    int2* __restrict__ segStart, int2* __restrict__ segQ) {
+  for (u32 z = blockIdx.y; z < sz; z += gridDim.y) {
+    const DecSlice d = ds[z];
+    const u64 e0 = evOff[z];
+    const u32 nev = (u32)(evOff[z + 1] - e0);
+    const u32* Mz = Mw + d.wordOff;
+    const u32* Sz = Sw + d.wordOff;
+    const int2* Qz = Qw + d.wordOff;
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < nev; j += gridDim.x * blockDim.x) {
+      const u32 ei = evIdx[e0 + j] & 0x3FFFFFFFu;
+      const u32 first = j ? (evIdx[e0 + j - 1] & 0x3FFFFFFFu) + 1 : 0u;
+      const int2 qf = disp_before(Mz, Sz, Qz, first);
+      const int2 ql = disp_before(Mz, Sz, Qz, ei - 1);       // the codepoint before an event is the dropped first-of-pair
+      segStart[e0 + j] = make_int2(ql.x - qf.x, ql.y - qf.y);
+      segQ[e0 + j] = qf;
+    }
+  }
+}
+
 #define DEC_STACK 512
+__device__ __forceinline__ u32 dec_smem_addr(const void* p) {
+  u32 a = (u32)__cvta_generic_to_shared(p);
+  asm volatile("" : "+r"(a));          // opaque: keep the address in a register instead of rematerialising it
+  return a;
+}
+__device__ __forceinline__ int2 dec_lds64(u32 a) {
+  int2 v;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void dec_sts64(u32 a, int2 v) { asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
 __global__ void __launch_bounds__(32) k_dec_chain(Geom g, const DecSlice* __restrict__ ds, const u8* __restrict__ stream,
                                                    const u32* __restrict__ Mw, const u32* __restrict__ Sw, const int2* __restrict__ Qw,
                                                    const u64* __restrict__ evOff, const u32* __restrict__ evIdx,
                                                    int2* __restrict__ segStart, int2* __restrict__ segQ, int2* __restrict__ gstack,
                                                    u32* __restrict__ nevUsed, ull* scal) {
   __shared__ int2 sstack[DEC_STACK];
-  __shared__ u32 s_ev[32];
   __shared__ int2 s_sum[32], s_start[32];
   __shared__ u32 s_used;
   const u32 z = blockIdx.x, lane = threadIdx.x;
@@ -447,38 +480,46 @@ __global__ void __launch_bounds__(32) k_dec_chain(Geom g, const DecSlice* __rest
     s_used = nev;
   }
   int2* gst = gstack + e0;
+  // shared memory through explicit 32-bit shared-space addresses (the serial loop below otherwise re-derives the shared
+  // window base on every access); event types travel as a ballot mask in a register
+  const u32 a_sum = dec_smem_addr(s_sum), a_start = dec_smem_addr(s_start), a_stack = dec_smem_addr(sstack);
+  // the next batch's inputs are loaded before the serial pass over the current one (one coalesced load each)
+  int2 nsum = make_int2(0, 0);
+  u32 nev_w = 0;
+  if (lane < nev) { nsum = segStart[e0 + lane]; nev_w = evIdx[e0 + lane]; }
   for (u32 base = 0; base < nev; base += 32) {
     const u32 j = base + lane;
-    if (j < nev) {
-      const u32 ev = evIdx[e0 + j];
-      const u32 ei = ev & 0x3FFFFFFFu;
-      const u32 first = j ? (evIdx[e0 + j - 1] & 0x3FFFFFFFu) + 1 : 0u;
-      const int2 qf = disp_before(Mz, Sz, Qz, first);
-      const int2 ql = disp_before(Mz, Sz, Qz, ei - 1);       // the codepoint before an event is the dropped first-of-pair
-      s_ev[lane] = ev;
-      s_sum[lane] = make_int2(ql.x - qf.x, ql.y - qf.y);
-      segQ[e0 + j] = qf;
-    }
+    const int2 csum = nsum;
+    const u32 m = nev_w >> 30;
+    const bool is_t = j < nev && (m == 0 || m == 3);
+    if (j + 32 < nev) { nsum = segStart[e0 + j + 32]; nev_w = evIdx[e0 + j + 32]; }
+    s_sum[lane] = csum;
+    const u32 tmask = __ballot_sync(FULL_MASK, is_t);
     __syncwarp();
     if (lane == 0 && !stop) {
       const u32 n = min(32u, nev - base);
+#pragma unroll 4
       for (u32 k = 0; k < n; k++) {
-        if (open == 0) {                                 // next chain: start vertex from the BOC index
+        if (__builtin_expect(open == 0, 0)) {            // next chain: start vertex from the BOC index
           u32 vx, vy;
           if (!it.next(vx, vy)) { used = base + k; stop = true; break; }
           if (vx > g.sx || vy > g.sy) { atomicExch(&scal[SC_ERROR], 11ull); used = base + k; stop = true; break; }
           x = (int)vx; y = (int)vy; sp = 0; open = 1;
         }
-        s_start[k] = make_int2(x, y);
-        x += s_sum[k].x; y += s_sum[k].y;
-        const u32 m = s_ev[k] >> 30;
-        if (m == 0 || m == 3) {                           // 't'
+        dec_sts64(a_start + k * 8u, make_int2(x, y));
+        const int2 sm = dec_lds64(a_sum + k * 8u);
+        x += sm.x; y += sm.y;
+        if ((tmask >> k) & 1u) {                          // 't'
           open--;
-          if (sp > 0) { --sp; const int2 q = sp < DEC_STACK ? sstack[sp] : gst[sp - DEC_STACK]; x = q.x; y = q.y; }
+          if (sp > 0) {
+            --sp;
+            const int2 q = sp < DEC_STACK ? dec_lds64(a_stack + sp * 8u) : gst[sp - DEC_STACK];
+            x = q.x; y = q.y;
+          }
         } else {                                          // 'b': reference quirk -- pushed as x + sx*y (crackcodes.hpp:772,850)
           open++;
           const int2 q = x == (int)g.sx ? make_int2(0, y + 1) : make_int2(x, y);
-          if (sp < DEC_STACK) sstack[sp] = q; else gst[sp - DEC_STACK] = q;
+          if (sp < DEC_STACK) dec_sts64(a_stack + sp * 8u, q); else gst[sp - DEC_STACK] = q;
           sp++;
         }
       }
@@ -633,6 +674,16 @@ void launch_decode_mark(const Geom& g, const u8* stream, int order, DecodeBufs& 
   k_dec_compact<<<dec_grid(g.sz, 1, 8), 256, 0, st>>>(ds, g.sz, order, D.ncp.as<u32>(), D.Mw.as<u32>(), D.Sw.as<u32>(), D.evOff.as<u64>(),
                                                       D.evIdx.as<u32>(), D.evBaseW.as<u32>());
   LAUNCH_CHECK();
+  {
+    const u64 per_slice = (total_events + g.sz - 1) / g.sz;
+    u32 gx = (u32)((per_slice + 255) / 256);
+    if (gx > 32) gx = 32;
+    if (gx < 1) gx = 1;
+    k_dec_evsum<<<dim3(gx, g.sz < 65535u ? g.sz : 65535u), 256, 0, st>>>(ds, g.sz, D.Mw.as<u32>(), D.Sw.as<u32>(), D.Qw.as<int2>(),
+                                                                          D.evOff.as<u64>(), D.evIdx.as<u32>(), D.segStart.as<int2>(),
+                                                                          D.segQ.as<int2>());
+    LAUNCH_CHECK();
+  }
   k_dec_chain<<<g.sz, 32, 0, st>>>(g, ds, stream, D.Mw.as<u32>(), D.Sw.as<u32>(), D.Qw.as<int2>(), D.evOff.as<u64>(), D.evIdx.as<u32>(),
                                    D.segStart.as<int2>(), D.segQ.as<int2>(), D.gstack.as<int2>(), D.nevUsed.as<u32>(), scal);
   LAUNCH_CHECK();
