@@ -262,7 +262,17 @@ static void shard_begin_impl(ckl_ctx* c, const void* labels, int on_device, int 
   if (on_device) J.labels = labels;
   else {
     c->labels_dev.ensure(voxels * (u64)width);
+    if (c->stg) {                    // staggered chunk: the host->device copies of the chunks go one after the other (they share
+                                     // PCIe anyway), so chunk k computes while chunk k+1 is still in flight
+      while (c->stg->seq.load(std::memory_order_acquire) < c->stg_index) std::this_thread::yield();
+      if (c->stg_index > 0) CUDA_CHECK(cudaStreamWaitEvent(c->st, c->stg->ev[c->stg_index - 1], 0));
+    }
     CUDA_CHECK(cudaMemcpyAsync(c->labels_dev.p, labels, voxels * (u64)width, cudaMemcpyHostToDevice, c->st));
+    if (c->stg) {
+      CUDA_CHECK(cudaEventRecord(c->stg->ev[c->stg_index], c->st));
+      int expect = c->stg_index;
+      c->stg->seq.compare_exchange_strong(expect, c->stg_index + 1, std::memory_order_release);
+    }
     J.labels = c->labels_dev.p;
   }
   const Geom& g = J.g;
@@ -651,14 +661,23 @@ static void compress_chunked(ckl_ctx* c, const void* labels, int labels_on_devic
   std::vector<int> guess(K);
   fork_kids(c, K);
   // phase A: everything that does not need a global decision.  The crack format (pixel pairs) is guessed from the
-  // chunk's own statistics and verified below.
-  run_chunks(c, K, [&](int k) {
-    ckl_ctx* q = c->kids[k];
-    const u8* src = (const u8*)labels + z0[k] * sxy * (u64)width;
-    shard_begin_impl(q, src, labels_on_device, width, sx, sy, z0[k + 1] - z0[k], &sum[k]);
-    guess[k] = (i64)sum[k].pairs < (i64)sum[k].voxels / 2;
-    shard_encode_impl(q, guess[k], ckl_byte_width(sum[k].max_label), order_in);
-  });
+  // chunk's own statistics and verified below.  Host-resident input: the chunks' uploads are staggered.
+  Stagger stg;
+  if (!labels_on_device)
+    for (int k = 0; k < K; k++) { stg.ev.push_back(c->kids[k]->ev_done); c->kids[k]->stg = &stg; c->kids[k]->stg_index = k; }
+  try {
+    run_chunks(c, K, [&](int k) {
+      ckl_ctx* q = c->kids[k];
+      const u8* src = (const u8*)labels + z0[k] * sxy * (u64)width;
+      try {
+        shard_begin_impl(q, src, labels_on_device, width, sx, sy, z0[k + 1] - z0[k], &sum[k]);
+      } catch (...) { stg.seq.store(1 << 30, std::memory_order_release); throw; }      // never leave a later chunk spinning
+      q->stg = nullptr;
+      guess[k] = (i64)sum[k].pairs < (i64)sum[k].voxels / 2;
+      shard_encode_impl(q, guess[k], ckl_byte_width(sum[k].max_label), order_in);
+    });
+  } catch (...) { for (int k = 0; k < K; k++) c->kids[k]->stg = nullptr; throw; }
+  for (int k = 0; k < K; k++) c->kids[k]->stg = nullptr;
   u64 pairs = 0, maxl = 0;
   for (int k = 0; k < K; k++) {
     pairs += sum[k].pairs;

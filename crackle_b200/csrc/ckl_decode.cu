@@ -773,7 +773,7 @@ __global__ void __launch_bounds__(256) k_paint(Geom g, const u32* __restrict__ D
 template <typename OUT, bool MASK>
 __global__ void __launch_bounds__(256) k_paint_rows(Geom g, const u32* __restrict__ DV, const u32* __restrict__ rowBase,
                                                      const u64* __restrict__ runBase, const u64* __restrict__ runLabel, u64 label,
-                                                     OUT* __restrict__ out) {
+                                                     OUT* __restrict__ out, const bool STREAM) {
   const u32 lane = threadIdx.x & 31;
   const u32 lmask = (2u << lane) - 1u;
   const u64 rows = g.rows();
@@ -792,7 +792,8 @@ __global__ void __launch_bounds__(256) k_paint_rows(Geom g, const u32* __restric
         const u32 x = (w0 + k) * 32 + lane;
         if (x < g.sx) {
           const u64 v = rl[carry + __popc(dv & lmask)];
-          o[x] = MASK ? (OUT)(v == label) : (OUT)v;
+          const OUT r = MASK ? (OUT)(v == label) : (OUT)v;
+          if (STREAM) __stcs(o + x, r); else o[x] = r;    // streaming store: the output is written once and not re-read here
         }
         carry += __popc(dv);
       }
@@ -807,7 +808,9 @@ void launch_paint(const Geom& g, const u32* DV, const CclBufs& B, const u64* run
   const u32* rb = B.rowBase.as<u32>();
   const u64* rB = B.runBase.as<u64>();
 #define PAINT(T, M, F) k_paint<T, M, F><<<grid, 256, 0, st>>>(g, DV, wp, rb, rB, runLabel, label, (T*)out)
-#define PAINTR(T, M) k_paint_rows<T, M><<<grid1(g.rows(), 8, 148 * 8), 256, 0, st>>>(g, DV, rb, rB, runLabel, label, (T*)out)
+  static int stream_st = -1;
+  if (stream_st < 0) { const char* e = getenv("CKL_PAINT_CS"); stream_st = e ? atoi(e) : 1; }
+#define PAINTR(T, M) k_paint_rows<T, M><<<grid1(g.rows(), 8, 148 * 8), 256, 0, st>>>(g, DV, rb, rB, runLabel, label, (T*)out, stream_st != 0)
   if (has_label) {
     if (fortran_order) PAINTR(u8, true); else PAINT(u8, true, false);
   } else if (fortran_order) {
