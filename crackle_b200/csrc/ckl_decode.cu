@@ -571,30 +571,22 @@ __global__ void __launch_bounds__(256) k_dec_mark(Geom g, const DecSlice* __rest
           continue;
         }
         if (drop & fb) continue;
+        // one branch-free body for the four moves (0 up, 1 right, 2 down, 3 left), so the lanes of a warp stay together:
+        // vertical moves mark EV at column x (row y-1 going up, y going down), horizontal moves mark EH at row y
+        // (column x-1 going left, x going right); cracks on the image border are not stored
         const u32 m = (M >> (2 * k)) & 3u;
-        u32* a = nullptr;
-        u32 bit = 0;
-        if (m == 0) {          // up: vertical crack at column x, row y-1
-          if (y <= 0 || x < 0 || x > sx || y > sy) { bad = true; break; }
-          if (x > 0 && x < sx) { a = EV + (u64)(y - 1) * g.W + (x >> 5); bit = 1u << (x & 31); }
-          y--;
-        } else if (m == 2) {   // down: vertical crack at column x, row y
-          if (y >= sy || y < 0 || x < 0 || x > sx) { bad = true; break; }
-          if (x > 0 && x < sx) { a = EV + (u64)y * g.W + (x >> 5); bit = 1u << (x & 31); }
-          y++;
-        } else if (m == 3) {   // left: horizontal crack above pixel (x-1, y)
-          if (x <= 0 || x > sx || y < 0 || y > sy) { bad = true; break; }
-          if (y > 0 && y < sy) { a = EH + (u64)y * g.W + ((x - 1) >> 5); bit = 1u << ((x - 1) & 31); }
-          x--;
-        } else {               // right: horizontal crack above pixel (x, y)
-          if (x >= sx || x < 0 || y < 0 || y > sy) { bad = true; break; }
-          if (y > 0 && y < sy) { a = EH + (u64)y * g.W + (x >> 5); bit = 1u << (x & 31); }
-          x++;
-        }
-        if (a) {
+        const u32 isH = m & 1u, neg = (0x9u >> m) & 1u;
+        const int step = neg ? -1 : 1;
+        const int nx = x + (isH ? step : 0), ny = y + (isH ? 0 : step);
+        if ((u32)nx > (u32)sx || (u32)ny > (u32)sy || (u32)x > (u32)sx || (u32)y > (u32)sy) { bad = true; break; }
+        const int col = x - (int)(isH & neg), row = y - (int)((isH ^ 1u) & neg);
+        const bool interior = isH ? (y > 0 && y < sy) : (x > 0 && x < sx);
+        if (interior) {
+          u32* a = (isH ? EH : EV) + (u64)row * g.W + (col >> 5);
           if (a != pend) { if (pend) atomicOr(pend, pmask); pend = a; pmask = 0; }
-          pmask |= bit;
+          pmask |= 1u << (col & 31);
         }
+        x = nx; y = ny;
       }
       if (pend) atomicOr(pend, pmask);
       if (bad) atomicExch(&scal[SC_ERROR], 11ull);
