@@ -77,14 +77,9 @@ static VGeom vgeom(const Geom& g) {
   return v;
 }
 
-// bits 0..7 of v -> bit 0 of each nibble of the result
-__device__ __forceinline__ u32 spread8(u32 v) {
-  v &= 0xFFu;
-  v = (v | (v << 12)) & 0x000F000Fu;
-  v = (v | (v << 6)) & 0x03030303u;
-  v = (v | (v << 3)) & 0x11111111u;
-  return v;
-}
+// one vertex's adjacency nibble (bit 0 right, 1 left, 2 down, 3 up) out of a byte-planar vertex word: the four plane bits
+// of vertex b sit at bits b, 8 + b, 16 + b, 24 + b; the multiply gathers them into the top byte (no carries: sums <= 15)
+__device__ __forceinline__ u32 vertex_nibble(u32 word, u32 b) { return ((((word >> b) & 0x01010101u) * 0x01020408u) >> 24); }
 // 1. vertex words + node mask + per-slice bounds: bounds[z] = {E edges, S node slots with an edge, C start-capable nodes}
 __global__ void __launch_bounds__(256) k_vw_build(Geom g, VGeom vg, const u32* __restrict__ DV, const u32* __restrict__ DH, int perm,
                                                    uint4* __restrict__ VW, u32* __restrict__ NM, u32* __restrict__ cnt, u32* bounds) {
@@ -121,15 +116,16 @@ __global__ void __launch_bounds__(256) k_vw_build(Geom g, VGeom vg, const u32* _
         const u32 sm = b == 31 ? 0u : (stop & ~((2u << b) - 1u));
         if (sm == 0 || !((u >> (__ffs(sm) - 1)) & 1u)) n |= 1u << b;
       }
-      // adjacency nibbles of the 32 vertices (bit 0 right, 1 left, 2 down, 3 up), 8 per u32.  Degree-2 nodes (the
-      // corner candidates) are stored as 0 so that "popcount != 2" is the walkers' only node test.
+      // adjacency of the 32 vertices, 8 vertices per u32 as four byte planes: byte 0 right, 1 left, 2 down, 3 up (three
+      // byte permutes per word; a walker gathers one vertex's nibble with a shift, a mask and a multiply).  Degree-2 nodes
+      // (the corner candidates) are stored as 0 so that "popcount != 2" is the walkers' only node test.
       const u32 pass = ~(n & ~(sum0 | four));                // clear the corner nodes (degree exactly 2)
       const u32 rr = r & pass, dd = d & pass;
       uint4 nib;
-      nib.x = spread8(rr) | (spread8(l) << 1) | (spread8(dd) << 2) | (spread8(u) << 3);
-      nib.y = spread8(rr >> 8) | (spread8(l >> 8) << 1) | (spread8(dd >> 8) << 2) | (spread8(u >> 8) << 3);
-      nib.z = spread8(rr >> 16) | (spread8(l >> 16) << 1) | (spread8(dd >> 16) << 2) | (spread8(u >> 16) << 3);
-      nib.w = spread8(rr >> 24) | (spread8(l >> 24) << 1) | (spread8(dd >> 24) << 2) | (spread8(u >> 24) << 3);
+      nib.x = __byte_perm(__byte_perm(rr, l, 0x0040), __byte_perm(dd, u, 0x0040), 0x5410);
+      nib.y = __byte_perm(__byte_perm(rr, l, 0x0051), __byte_perm(dd, u, 0x0051), 0x5410);
+      nib.z = __byte_perm(__byte_perm(rr, l, 0x0062), __byte_perm(dd, u, 0x0062), 0x5410);
+      nib.w = __byte_perm(__byte_perm(rr, l, 0x0073), __byte_perm(dd, u, 0x0073), 0x5410);
       VW[i] = nib;
       NM[i] = n;
       cnt[i] = __popc(n);
@@ -286,7 +282,7 @@ __global__ void __launch_bounds__(256) k_node_init(TraceParams P) {
       n &= n - 1;
       const u32 q = b >> 3;
       const u32 c = q == 0 ? word.x : (q == 1 ? word.y : (q == 2 ? word.z : word.w));
-      const u32 nib = (c >> ((b & 7u) * 4u)) & 15u;
+      const u32 nib = vertex_nibble(c, b & 7u);
       P.nodeVertex[id] = y * vg.sxe + w * 32 + b;
       P.nodeP[id] = y * vg.S + w * 32 + b;
       P.nodeAdj[id] = (u8)(nib ? nib : 5u);          // a corner node is stored as 0; its edges are right and down
@@ -300,7 +296,7 @@ __global__ void __launch_bounds__(256) k_node_init(TraceParams P) {
 __device__ __forceinline__ bool nib_step(const u32* __restrict__ vn, u32 S, u32& p, u32& kk) {
   const u32 d = 1u - 2u * (kk & 1u);                 // +1 / -1
   p += (kk & 2u) ? d * S : d;
-  const u32 nib = (__ldg(vn + (p >> 3)) >> ((p & 7u) << 2)) & 15u;
+  const u32 nib = vertex_nibble(__ldg(vn + (p >> 3)), p & 7u);
   if ((0xE997u >> nib) & 1u) return true;            // popcount(nib) != 2
   const u32 a = nib & ~(1u << (kk ^ 1u));            // not back along the edge we came by: one bit left
   kk = (a >> 1) - (a >> 3);                          // one-hot {1,2,4,8} -> {0,1,2,3}
