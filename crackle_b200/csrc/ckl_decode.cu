@@ -222,7 +222,7 @@ void launch_decode_slices(const Geom& g, const u8* stream, const u64* codeOff, i
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Scan-parallel decoder (validated against the oracle by tools/proto_decode.py).
+// Scan-parallel decoder (validated against the oracle by tests/bringup/proto_decode.py).
 //   k_dec_markov   order > 0 only: serial bit decoder per slice -> packed 2-bit difference fields
 //   k_dec_classify per 16-field word: absolute moves (prefix sum mod 4) and the second-of-escape-pair mask S
 //                  (S[i] = opp[i] & ~S[i-1], solved per 32-field window with an add-carry trick); counts events

@@ -10,7 +10,7 @@
 //   write_boc_index / pack_codepoints                       src/crackcodes.hpp:318-372, :455-496
 //
 // The reference walk is a serial, order-dependent trail over the crack graph (one chain of ~10^5 moves per slice).
-// Here it is replayed on the CONTRACTED graph (validated against the oracle by tools/proto_trace.py):
+// Here it is replayed on the CONTRACTED graph (validated against the oracle by tests/bringup/proto_trace.py):
 //   1. k_vw_build     vertex words {r,d,u,n}: right / down / up edge bits of 32 vertices and the node mask n.
 //                     node = static degree 1, 3 or 4, or an (R,D)-only corner whose horizontal run to the right
 //                     does not end at a vertex with an up edge.  Every component's minimum vertex (the chain

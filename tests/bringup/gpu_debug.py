@@ -1,12 +1,12 @@
 """GPU bring-up helper: runs every golden vector + a few oracle-checked random volumes through the CUDA path and
-prints, per case, which stream section differs.  Usage (on a GPU box): python tools/gpu_debug.py [name-filter]"""
+prints, per case, which stream section differs.  Usage (on a GPU box): python tests/bringup/gpu_debug.py [name-filter]"""
 import os
 import sys
 import traceback
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import crackle_b200 as cb  # noqa: E402
 from oracle import oracle as O  # noqa: E402
