@@ -255,3 +255,39 @@ def test_noise_volumes_permissible_path(ctx):
         b = ctx.compress(v, 0)
         assert b == O.compress(v, 0)
         assert np.array_equal(cb.decompress(b), v)
+
+
+def test_config5_slab_2048x2048_u32_dense_labels(ctx):
+    # BASELINE.json configs[4] at slab size: 2048x2048 uint32 dense-label slices (cell 16, permutation ids), decompress
+    # + single-label extraction.  Slices this large have tens of thousands of crack-graph nodes, so the encoder's replay
+    # runs in its 16-bit and global-memory modes; bytes are checked against the oracle.
+    import torch
+    from oracle import oracle as O
+    from crackle_b200 import synth
+    import crackle_b200 as cb
+    t = synth.jittered_voronoi_torch((2048, 2048, 6), 16, np.uint32, seed=5, id_bits=0, sz_total=1024)
+    v = np.asfortranarray(t.cpu().numpy().transpose(2, 1, 0))
+    b = ctx.compress(t, 0)
+    assert b == O.compress(v, 0)
+    n = ctx.compress_ptr(t.data_ptr(), 1, 4, 2048, 2048, 6, True, 0)
+    p, _ = ctx.result_device()
+    out = torch.empty_like(t)
+    ctx.decompress_into(p, 1, n, 0, -1, None, out.data_ptr(), 1, out.numel() * 4)
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int32), t.view(torch.int32))
+    lab = int(v[1024, 1024, 3])
+    m = torch.empty(t.shape, dtype=torch.uint8, device="cuda")
+    ctx.decompress_into(p, 1, n, 0, -1, lab, m.data_ptr(), 1, m.numel())
+    torch.cuda.synchronize()
+    assert torch.equal(m.bool(), t.view(torch.int32) == lab)
+    assert np.array_equal(cb.decompress_range(b, 2, 4, label=lab), v[:, :, 2:4] == lab)
+
+
+def test_config3_slab_1024x1024_u64_bytes_vs_oracle(ctx):
+    # BASELINE.json configs[2] (the bench volume) on a 24-slice slab: byte-exact against the oracle for orders 0 and 5
+    from oracle import oracle as O
+    from crackle_b200 import synth
+    t = synth.jittered_voronoi_torch((1024, 1024, 24), 24, np.uint64, seed=0, id_bits=40, sz_total=1024)
+    v = np.asfortranarray(t.cpu().numpy().transpose(2, 1, 0))
+    for order in (0, 5):
+        assert ctx.compress(t, order) == O.compress(v, order)
