@@ -31,7 +31,7 @@ void launch_ccl_count(const Geom& g, const u32* DV, CclBufs& B, ull* scal, cudaS
 // phase 2 (parent/runStart/compRank/runComp/compPix must hold `total_runs`): union-find, ranks, N_z, crcs;
 // writes scal[SC_COMPONENTS]
 void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, const CrcTables* d_tables,
-                      ull* scal, cudaStream_t st);
+                      ull* scal, u64 total_runs, cudaStream_t st);
 // second half: per-run component ranks, per-slice CRCs and (compress) component first pixels / (decompress, `decode`
 // non-null) the label of every run
 struct CclDecodeSrc { const u8* uniq; const u8* keys; u64 n_uniq, n_keys; int sw, kw; const u64* keyBase; u64* runLabel; };

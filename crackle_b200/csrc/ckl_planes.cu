@@ -8,6 +8,8 @@
 //   cc3d::connected_components2d_4 / color_connectivity_graph + relabel   src/cc3d.hpp:114-369
 //       final ids = rank of each component's first pixel in x-fastest raster order
 //   crc32c(cc_labels)                                  src/labels.hpp:81, src/crackle.hpp:599-611
+#include <algorithm>
+
 #include "ckl_internal.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
@@ -363,8 +365,9 @@ __device__ __forceinline__ void link_word(const Geom& g, const u32* __restrict__
 #define CCL_SMEM_RUNS 12288
 __global__ void __launch_bounds__(256) k_band_ccl(Geom g, u32 nbands, const u32* __restrict__ DV, const u32* __restrict__ DH,
                                                    const u32* __restrict__ wordPrefix, const u32* __restrict__ rowBase,
-                                                   const u32* __restrict__ sliceRuns, const u64* __restrict__ runBase, u32* parent) {
-  __shared__ u32 spar[CCL_SMEM_RUNS];
+                                                   const u32* __restrict__ sliceRuns, const u64* __restrict__ runBase, u32* parent,
+                                                   const u32 smem_runs) {
+  extern __shared__ u32 spar[];                          // smem_runs entries
   const u64 nitems = (u64)g.sz * nbands;
   for (u64 item = blockIdx.x; item < nitems; item += gridDim.x) {
     const u32 z = (u32)(item / nbands), band = (u32)(item - (u64)z * nbands);
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(256) k_band_ccl(Geom g, u32 nbands, const u32*
     const u32 end = y1 < g.sy ? rowBase[row0 + (y1 - y0)] : sliceRuns[z];
     const u32 n = end - base;
     u32* gpar = parent + runBase[z] + base;
-    const bool sm = n <= CCL_SMEM_RUNS;
+    const bool sm = n <= smem_runs;
     volatile u32* par = sm ? spar : gpar;
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) par[i] = i;
     __syncthreads();
@@ -648,7 +651,7 @@ void launch_crc_finalize_slices(u32* sliceCrc, u32 sz, u32 init_term, cudaStream
 }
 
 void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, const CrcTables* d_tables, ull* scal,
-                      cudaStream_t st) {
+                      u64 total_runs, cudaStream_t st) {
   (void)d_tables;
   const u64 nwords = g.words();
   B.nz.ensure((u64)g.sz * 4);
@@ -659,8 +662,17 @@ void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, c
                                                          B.runStart.as<u32>());
   LAUNCH_CHECK();
   const u32 nbands = (g.sy + CCL_BAND - 1) / CCL_BAND;
-  k_band_ccl<<<grid_for((u64)g.sz * nbands, 1, 4), 256, 0, st>>>(g, nbands, DV, DH, B.wordPrefix.as<u32>(), B.rowBase.as<u32>(),
-                                                                  B.sliceRuns.as<u32>(), B.runBase.as<u64>(), parent);
+  {
+    // shared-memory capacity per band: twice the average number of runs per band (bands above it solve in global memory),
+    // between 3072 and CCL_SMEM_RUNS entries -- a smaller footprint keeps more blocks resident on this latency-bound kernel
+    const u64 avg = total_runs / ((u64)g.sz * nbands) + 1;
+    u32 cap = (u32)std::min<u64>(CCL_SMEM_RUNS, std::max<u64>(3072, 2 * avg));
+    cap = (cap + 1023u) & ~1023u;
+    const u32 per_sm = std::min<u32>(8u, (u32)((200u * 1024u) / (cap * 4u)));
+    k_band_ccl<<<grid_for((u64)g.sz * nbands, 1, per_sm), 256, (size_t)cap * 4, st>>>(g, nbands, DV, DH, B.wordPrefix.as<u32>(),
+                                                                                       B.rowBase.as<u32>(), B.sliceRuns.as<u32>(),
+                                                                                       B.runBase.as<u64>(), parent, cap);
+  }
   LAUNCH_CHECK();
   if (nbands > 1) {
     k_border_union<<<grid_for((u64)g.sz * (nbands - 1) * g.W, 256, 8), 256, 0, st>>>(g, nbands, DV, DH, B.wordPrefix.as<u32>(),
