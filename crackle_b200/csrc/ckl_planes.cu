@@ -425,16 +425,22 @@ __global__ void __launch_bounds__(256) k_root_rank(Geom g, const u32* __restrict
                                                     const u64* __restrict__ runBase, u32* __restrict__ compRank,
                                                     u32* __restrict__ nz) {
   __shared__ u32 sm[33];
+  constexpr u32 PER = 8;                                 // consecutive runs per thread: eight independent loads per block scan
   for (u32 z = blockIdx.x; z < g.sz; z += gridDim.x) {
     const u32 n = sliceRuns[z];
     const u64 gb = runBase[z];
     u32 carry = 0;
-    for (u32 i0 = 0; i0 < n; i0 += blockDim.x) {
-      const u32 i = i0 + threadIdx.x;
-      const u32 f = (i < n && __ldcg(parent + gb + i) == i) ? 1u : 0u;
+    for (u32 i0 = 0; i0 < n; i0 += blockDim.x * PER) {
+      const u32 i = i0 + threadIdx.x * PER;
+      u32 flags = 0;
+#pragma unroll
+      for (u32 j = 0; j < PER; j++)
+        if (i + j < n && __ldcg(parent + gb + i + j) == i + j) flags |= 1u << j;
       u32 tot;
-      const u32 ex = block_excl_scan(f, sm, tot);
-      if (f) compRank[gb + i] = carry + ex;
+      u32 r = carry + block_excl_scan(__popc(flags), sm, tot);
+#pragma unroll
+      for (u32 j = 0; j < PER; j++)
+        if ((flags >> j) & 1u) compRank[gb + i + j] = r++;
       carry += tot;
     }
     if (threadIdx.x == 0) nz[z] = carry;
