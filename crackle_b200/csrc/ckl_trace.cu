@@ -652,16 +652,26 @@ __global__ void __launch_bounds__(256) k_event_post(TraceParams P) {
     __syncthreads();
     // (b) codepoints per event -> exclusive prefix
     u32 carry = 0;
-    for (u32 i0 = 0; i0 < nev; i0 += blockDim.x) {
-      const u32 i = i0 + threadIdx.x;
-      u32 cnt = 0;
-      if (i < nev) {
-        const u32 e = ev[i], t = e >> 30;
-        cnt = t == EV_E ? seLen[e & 0x3FFFFFFFu] : (t == EV_S ? 0u : 2u);
+    constexpr u32 PER = 4;                               // consecutive events per thread: four independent loads per block scan
+    for (u32 i0 = 0; i0 < nev; i0 += blockDim.x * PER) {
+      const u32 i = i0 + threadIdx.x * PER;
+      u32 cnt[PER], sum = 0;
+#pragma unroll
+      for (u32 j = 0; j < PER; j++) {
+        cnt[j] = 0;
+        if (i + j < nev) {
+          const u32 e = ev[i + j], t = e >> 30;
+          cnt[j] = t == EV_E ? seLen[e & 0x3FFFFFFFu] : (t == EV_S ? 0u : 2u);
+        }
+        sum += cnt[j];
       }
       u32 tot;
-      const u32 ex = block_excl_scan(cnt, sm, tot);
-      if (i < nev) pre[i] = carry + ex;
+      u32 run = carry + block_excl_scan(sum, sm, tot);
+#pragma unroll
+      for (u32 j = 0; j < PER; j++) {
+        if (i + j < nev) pre[i + j] = run;
+        run += cnt[j];
+      }
       carry += tot;
     }
     if (threadIdx.x == 0) pre[nev] = carry;
