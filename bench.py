@@ -251,7 +251,7 @@ def main():
     # reverse); `traffic` = dram bytes of that stage's top kernel from the committed ncu capture (profiles/), per launch
     # stages that are exactly ONE kernel launch (the others bundle several kernels and, on the low-priority stream, include
     # time spent waiting for SMs): the dominant kernel is picked among these
-    one_kernel = {"edges": "k_edges<u64,8>", "trace_replay": "k_replay<0>", "d_paint": "k_paint_rows<u64,false>"}
+    one_kernel = {"edges": "k_edges<u64,16>", "trace_replay": "k_replay<0>", "d_paint": "k_paint_rows<u64,false>"}
     cand = {k: v for k, v in stage_ms.items() if k in one_kernel}
     dom = max(cand, key=cand.get) if cand else None
     traffic_tab = {}
