@@ -158,19 +158,23 @@ class ShardedCodec:
         return self.be.device
 
     def _all_gather_i64(self, vals):
+        """fixed-size all_gather of a few int64 per rank: one collective into one tensor, one device->host copy"""
         t = torch.tensor(vals, dtype=torch.int64, device=self._dev())
-        out = [torch.empty_like(t) for _ in range(self.world)]
-        self.dist.all_gather(out, t)
-        return [o.cpu().numpy().view(np.uint64) for o in out]
+        out = torch.empty(self.world * t.numel(), dtype=torch.int64, device=self._dev())
+        self.dist.all_gather_into_tensor(out, t)
+        a = out.cpu().numpy().view(np.uint64).reshape(self.world, t.numel())
+        return [a[r] for r in range(self.world)]
 
-    def _all_gather_var(self, t, counts):
-        """all_gather of 1-D tensors of different lengths (padded to the max)."""
+    def _all_gather_var(self, t, counts, to_host=False):
+        """all_gather of 1-D tensors of different lengths (padded to the max); to_host: numpy views of ONE host copy."""
         m = max(max(counts), 1)
         pad = torch.zeros(m, dtype=t.dtype, device=self._dev())
         pad[: t.numel()] = t
-        out = [torch.empty_like(pad) for _ in range(self.world)]
-        self.dist.all_gather(out, pad)
-        return [o[:c] for o, c in zip(out, counts)]
+        out = torch.empty(self.world * m, dtype=t.dtype, device=self._dev())
+        self.dist.all_gather_into_tensor(out, pad)
+        if to_host:
+            out = out.cpu().numpy()
+        return [out[r * m: r * m + c] for r, c in enumerate(counts)]
 
     # -- compress --------------------------------------------------------------------------------------------
     def _mark(self, name):
@@ -231,7 +235,7 @@ class ShardedCodec:
         keys_all = [int(a[0]) for a in sizes]
         codes_all = [int(a[1]) for a in sizes]
         small = torch.from_numpy(np.concatenate([nz.view(np.int64), code_sizes.astype(np.int64), crcs.astype(np.int64)])).to(self._dev())
-        smalls = self._all_gather_var(small, [3 * z for z in sz_all])
+        smalls = self._all_gather_var(small, [3 * z for z in sz_all], to_host=True)
         self._mark("small_gathers")
         # (6) gather keys and codes on rank 0 straight into their place in the stream
         kw, cw = byte_width(nu), byte_width(sx * sy)
@@ -264,7 +268,7 @@ class ShardedCodec:
             return None
         self._mark("keys_codes_gather")
         # (7) rank 0: the small sections (crackle.hpp:171-216, labels.hpp:123-152)
-        sm_np = [p.cpu().numpy() for p in smalls]
+        sm_np = smalls
         nz_g = np.concatenate([p[: z].view(np.uint64) for p, z in zip(sm_np, sz_all)])
         cs_g = np.concatenate([p[z: 2 * z].astype(np.uint32) for p, z in zip(sm_np, sz_all)])
         cr_g = np.concatenate([p[2 * z: 3 * z].astype(np.uint32) for p, z in zip(sm_np, sz_all)])
