@@ -49,6 +49,16 @@ class ThreadGroup:
                 torch.cuda.synchronize()
                 g.bar.wait()
 
+            def all_gather_into_tensor(self_, out, t):
+                torch.cuda.synchronize()
+                g.slots[rank] = t.clone()
+                g.bar.wait()
+                n = t.numel()
+                for i in range(g.world):
+                    out[i * n:(i + 1) * n].copy_(g.slots[i])
+                torch.cuda.synchronize()
+                g.bar.wait()
+
             def all_reduce(self_, t, op=None):
                 torch.cuda.synchronize()
                 g.slots[rank] = t.clone()
@@ -133,6 +143,6 @@ def test_sharded_equals_monolithic_threads(order, world):
 def test_sharded_nccl_torchrun():
     n = min(torch.cuda.device_count(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tools", "dist_check.py")]
+           "--master-port", "29533", os.path.join(ROOT, "tests", "bringup", "dist_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
