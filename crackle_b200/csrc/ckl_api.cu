@@ -1101,6 +1101,11 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
   CclDecodeSrc dsrc;
   dsrc.uniq = dstream + uniq_off; dsrc.keys = dstream + keys_off; dsrc.n_uniq = nu; dsrc.n_keys = n_keys; dsrc.sw = sw; dsrc.kw = kw;
   dsrc.keyBase = D.keyBase.as<u64>(); dsrc.runLabel = D.runLabel.as<u64>();
+  D.uniq64.ensure(nu * 8 + 8);
+  D.keys64.ensure(n_keys * 8 + 8);
+  launch_unpack_le(dsrc.uniq, sw, nu, D.uniq64.as<u64>(), st);
+  launch_unpack_le(dsrc.keys, kw, n_keys, D.keys64.as<u64>(), st);
+  dsrc.uniq64 = D.uniq64.as<u64>(); dsrc.keys64 = D.keys64.as<u64>();
   STAGE(c, "d_ccl_finish", launch_ccl_finish(g, c->ccl, runs, c->dtab, init_term, &dsrc, st));
   if (h.format_version > 0) {   // crackle.hpp:599-611
     k_crc_compare<<<(g.sz + 255) / 256, 256, 0, st>>>(c->ccl.sliceCrc.as<u32>(), dstream + num_bytes - 4ull * h.sz + 4ull * (u64)z_start, g.sz, c->scal);

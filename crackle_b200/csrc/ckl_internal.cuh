@@ -34,7 +34,9 @@ void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, c
                       ull* scal, u64 total_runs, cudaStream_t st);
 // second half: per-run component ranks, per-slice CRCs and (compress) component first pixels / (decompress, `decode`
 // non-null) the label of every run
-struct CclDecodeSrc { const u8* uniq; const u8* keys; u64 n_uniq, n_keys; int sw, kw; const u64* keyBase; u64* runLabel; };
+struct CclDecodeSrc { const u8* uniq; const u8* keys; u64 n_uniq, n_keys; int sw, kw; const u64* keyBase; u64* runLabel;
+                      const u64* uniq64 = nullptr; const u64* keys64 = nullptr; };   // aligned copies (launch_unpack_le), optional
+void launch_unpack_le(const u8* src, int width, u64 n, u64* dst, cudaStream_t st);
 void launch_ccl_finish(const Geom& g, CclBufs& B, u64 total_runs, const CrcTables* d_tables, u32 crc_init_term,
                        const CclDecodeSrc* decode, cudaStream_t st);
 // generic device CRC-32C of a byte buffer: result (finalised) written to *d_out
@@ -112,6 +114,7 @@ struct DecodeBufs {
   DBuf stack;       // per-slice revisit stacks
   DBuf stackOff;
   DBuf runLabel;    // u64 per run
+  DBuf uniq64, keys64;   // aligned copies of the stream's unique-label and key tables
 };
 void launch_decode_slices(const Geom& g, const u8* stream, const u64* codeOff, int permissible, int order,
                           const u8* model, u32* EV, u32* EH, u32* stack, const u64* stackOff, ull* scal, cudaStream_t st);

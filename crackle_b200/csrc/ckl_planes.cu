@@ -555,7 +555,8 @@ static void ensure_crcH(CclBufs& B, u32 sxy, const CrcTables* d_tables, cudaStre
 //   MODE 0 (compress):   first pixel of every component (-> label gather)
 //   MODE 1 (decompress): label of the run = uniq[key[keyBase[z] + comp]]   (labels::decode_flat, labels.hpp:453-506)
 // grid = (chunks, slices): no per-run slice search.
-struct RunLabelSrc { const u8* uniq; const u8* keys; u64 n_uniq, n_keys; int sw, kw; const u64* keyBase; u64* runLabel; };
+struct RunLabelSrc { const u8* uniq; const u8* keys; u64 n_uniq, n_keys; int sw, kw; const u64* keyBase; u64* runLabel;
+                     const u64* uniq64; const u64* keys64; };   // aligned copies of the two stream tables (may be null)
 // little-endian field of a compile-time width at an arbitrary (unaligned) stream offset
 template <int W>
 __device__ __forceinline__ u64 ld_le_w(const u8* __restrict__ p) {
@@ -625,8 +626,13 @@ __global__ void __launch_bounds__(256) k_run_finish(Geom g, const u32* __restric
           const u64 ki = kb + c;
           u64 label = 0;
           if (ki < src.n_keys) {
-            const u64 key = ld_le_dev(src.keys + ki * (u64)src.kw, src.kw);
-            if (key < src.n_uniq) label = ld_le_dev(src.uniq + key * (u64)src.sw, src.sw);
+            if (src.keys64) {                                   // aligned tables: one load each instead of kw + sw byte loads
+              const u64 key = src.keys64[ki];
+              if (key < src.n_uniq) label = src.uniq64[key];
+            } else {
+              const u64 key = ld_le_dev(src.keys + ki * (u64)src.kw, src.kw);
+              if (key < src.n_uniq) label = ld_le_dev(src.uniq + key * (u64)src.sw, src.sw);
+            }
           }
           src.runLabel[gb + i] = label;
         }
@@ -691,6 +697,18 @@ void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, c
   launch_exscan_u32_u64(B.nz.as<u32>(), g.sz, 1, B.compBase.as<u64>(), &scal[SC_COMPONENTS], 0, st);
 }
 
+// little-endian fields of `width` bytes at an arbitrary stream offset -> aligned uint64 array (the decoder's unique-label and
+// key tables: every run looks both up, so the unaligned byte loads are paid once per entry instead of once per run)
+__global__ void __launch_bounds__(256) k_unpack_le(const u8* __restrict__ src, int width, u64 n, u64* __restrict__ dst) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = ld_le_dev(src + i * (u64)width, width);
+}
+void launch_unpack_le(const u8* src, int width, u64 n, u64* dst, cudaStream_t st) {
+  if (!n) return;
+  k_unpack_le<<<grid_for(n, 256, 8), 256, 0, st>>>(src, width, n, dst);
+  LAUNCH_CHECK();
+}
+
 // second half of the solve: ranks -> per-run results + per-slice CRCs.  `decode` selects MODE 1 (run labels).
 void launch_ccl_finish(const Geom& g, CclBufs& B, u64 total_runs, const CrcTables* d_tables, u32 crc_init_term,
                        const CclDecodeSrc* decode, cudaStream_t st) {
@@ -706,6 +724,7 @@ void launch_ccl_finish(const Geom& g, CclBufs& B, u64 total_runs, const CrcTable
     if (decode) {
       src.uniq = decode->uniq; src.keys = decode->keys; src.n_uniq = decode->n_uniq; src.n_keys = decode->n_keys;
       src.sw = decode->sw; src.kw = decode->kw; src.keyBase = decode->keyBase; src.runLabel = decode->runLabel;
+      src.uniq64 = decode->uniq64; src.keys64 = decode->keys64;
       k_run_finish<1><<<grid, 256, 0, st>>>(g, B.parent.as<u32>(), B.sliceRuns.as<u32>(), B.runBase.as<u64>(), B.compRank.as<u32>(),
                                            B.runStart.as<u32>(), B.compBase.as<u64>(), B.crcH.as<u32>(), d_tables, B.compPix.as<u32>(),
                                            src, B.sliceCrc.as<u32>());
