@@ -92,7 +92,8 @@ def test_chunked_z_ranges_masks_and_errors(cctx):
 
 
 def test_chunked_device_resident_and_automatic(cctx):
-    # 256 x 256 x 1024 uint64 (512 MiB) crosses the automatic threshold: chunked by default, identical to chunks = 1
+    # 256 x 256 x 1024 uint64 (512 MiB).  The automatic policy chunks HOST-resident volumes of this size (4 z-chunks, staggered
+    # uploads) and leaves device-resident ones alone; every setting must give the bytes of chunks = 1.
     import torch
     from crackle_b200 import synth
     t = synth.jittered_voronoi_torch((256, 256, 1024), 24, np.uint64, seed=1, id_bits=40)
@@ -102,6 +103,13 @@ def test_chunked_device_resident_and_automatic(cctx):
     cctx.set_chunks(0)
     n0 = cctx.compress_ptr(t.data_ptr(), 1, 8, 256, 256, 1024, True, 0)
     assert n0 == n1 and cctx.result_bytes() == one
+    host = t.cpu().numpy()                                   # (sz, sy, sx) C-contiguous == Fortran (sx, sy, sz)
+    nh = cctx.compress_ptr(host.ctypes.data, 0, 8, 256, 256, 1024, True, 0)          # automatic: chunked, staggered uploads
+    assert nh == n1 and cctx.result_bytes() == one
+    out_h = np.empty_like(host)
+    buf = np.frombuffer(one, dtype=np.uint8)
+    cctx.decompress_into(buf.ctypes.data, 0, buf.size, 0, -1, None, out_h.ctypes.data, 0, out_h.nbytes)   # automatic: chunked
+    assert np.array_equal(out_h, host)
     p, n = cctx.result_device()
     out = torch.empty_like(t)
     cctx.decompress_into(p, 1, n, 0, -1, None, out.data_ptr(), 1, out.numel() * 8)
@@ -110,6 +118,11 @@ def test_chunked_device_resident_and_automatic(cctx):
     cctx.set_chunks(5)
     cctx.compress_ptr(t.data_ptr(), 1, 8, 256, 256, 1024, True, 5)
     five = cctx.result_bytes()
+    out.zero_()
+    p, n = cctx.result_device()
+    cctx.decompress_into(p, 1, n, 0, -1, None, out.data_ptr(), 1, out.numel() * 8)   # 5 staggered chunks, markov order 5
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int64), t.view(torch.int64))
     cctx.set_chunks(1)
     cctx.compress_ptr(t.data_ptr(), 1, 8, 256, 256, 1024, True, 5)
     assert cctx.result_bytes() == five
