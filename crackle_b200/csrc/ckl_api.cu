@@ -1094,7 +1094,7 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
   }
   const u64 runs = c->hscal[SC_RUNS];
   c->ccl.parent.ensure(runs * 4); c->ccl.runStart.ensure(runs * 4); c->ccl.compRank.ensure(runs * 4);
-  c->ccl.runComp.ensure(runs * 4); c->ccl.compPix.ensure(runs * 4);
+  c->ccl.compPix.ensure(runs * 4);
   STAGE(c, "d_ccl_solve", launch_ccl_solve(g, c->DV.as<u32>(), c->DH.as<u32>(), c->ccl, c->dtab, c->scal, runs, st));
   const u32 init_term = gf_mul(gf_xpow32(c->htab.pw, (u32)g.sxy), 0xFFFFFFFFu);
   D.runLabel.ensure(runs * 8 + 8);

@@ -708,36 +708,6 @@ void launch_planes_from_cracks(const Geom& g, int permissible, u32* EV, u32* EH,
   LAUNCH_CHECK();
 }
 
-// label of every run: component rank -> key -> unique label (decode_flat)
-__global__ void __launch_bounds__(256) k_run_labels(Geom g, u64 total_runs, const u64* __restrict__ runBase, const u32* __restrict__ runComp,
-                                                     const u8* __restrict__ uniq, const u8* __restrict__ keys, u64 n_uniq, u64 n_keys,
-                                                     int sw, int kw, const u64* __restrict__ keyBase, u64* __restrict__ runLabel) {
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < total_runs; r += stride) {
-    u32 lo = 0, hi = g.sz;
-    while (hi - lo > 1) { const u32 m = (lo + hi) >> 1; if (runBase[m] <= r) lo = m; else hi = m; }
-    const u64 ki = keyBase[lo] + runComp[r];
-    u64 label = 0;
-    if (ki < n_keys) {
-      const u64 k = ld_le(keys + ki * (u64)kw, kw);
-      if (k < n_uniq) label = ld_le(uniq + k * (u64)sw, sw);
-    }
-    runLabel[r] = label;
-  }
-}
-void launch_run_labels(const Geom& g, const CclBufs& B, const u8* stream, u64 uniq_off, u64 keys_off, u64 n_uniq, u64 n_keys_total,
-                       int stored_width, int key_width, const u64* keyBase, u64* runLabel, cudaStream_t st) {
-  // total runs lives in runBase[sz]; the caller passes it through B.runBase on the host side via scal; we re-read here
-  u64 total_runs = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&total_runs, B.runBase.as<u64>() + g.sz, 8, cudaMemcpyDeviceToHost, st));
-  CUDA_CHECK(cudaStreamSynchronize(st));
-  if (!total_runs) return;
-  k_run_labels<<<grid1(total_runs, 256, 148 * 16), 256, 0, st>>>(g, total_runs, B.runBase.as<u64>(), B.runComp.as<u32>(),
-                                                                 stream + uniq_off, stream + keys_off, n_uniq, n_keys_total,
-                                                                 stored_width, key_width, keyBase, runLabel);
-  LAUNCH_CHECK();
-}
-
 // paint: one warp per 32-pixel word, lane <-> pixel; the only full-width write of decompress.
 template <typename OUT, bool MASK, bool FORTRAN>
 __global__ void __launch_bounds__(256) k_paint(Geom g, const u32* __restrict__ DV, const u32* __restrict__ wordPrefix,

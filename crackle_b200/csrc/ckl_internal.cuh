@@ -19,7 +19,7 @@ enum {
 // ---- planes + CCL (ckl_planes.cu) ------------------------------------------------------------------------
 struct CclBufs {
   DBuf wordPrefix, rowRuns, rowBase, sliceRuns, runBase;   // per word / row / slice
-  DBuf parent, runStart, compRank, runComp;                // per run (allocated once the run total is known)
+  DBuf parent, runStart, compRank;                         // per run (allocated once the run total is known)
   DBuf nz, compBase, compPix;                              // per slice / per component
   DBuf sliceCrc;                                           // raw CRC accumulators, per slice
   DBuf crcH, crcHl; u64 crcHn = 0;                         // H[m] = sum_{j=1..m} x^(32j) mod P for m <= sxy (built once)
@@ -28,7 +28,7 @@ struct CclBufs {
 void launch_edges(const void* labels, int width, const Geom& g, u32* DV, u32* DH, ull* scal, cudaStream_t st);
 // phase 1: per-row run prefixes, per-slice run counts and bases; writes scal[SC_RUNS]
 void launch_ccl_count(const Geom& g, const u32* DV, CclBufs& B, ull* scal, cudaStream_t st);
-// phase 2 (parent/runStart/compRank/runComp/compPix must hold `total_runs`): union-find, ranks, N_z, crcs;
+// phase 2 (parent/runStart/compRank/compPix must hold `total_runs`): union-find, ranks, N_z, crcs;
 // writes scal[SC_COMPONENTS]
 void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, const CrcTables* d_tables,
                       ull* scal, u64 total_runs, cudaStream_t st);
@@ -124,7 +124,5 @@ void launch_decode_classify(const Geom& g, const u8* stream, int order, const u8
 void launch_decode_mark(const Geom& g, const u8* stream, int order, DecodeBufs& D, u64 total_events, u64 total_words, u32* EV, u32* EH,
                         ull* scal, cudaStream_t st);
 void launch_planes_from_cracks(const Geom& g, int permissible, u32* EV, u32* EH, cudaStream_t st);
-void launch_run_labels(const Geom& g, const CclBufs& B, const u8* stream, u64 uniq_off, u64 keys_off, u64 n_uniq,
-                       u64 n_keys_total, int stored_width, int key_width, const u64* keyBase, u64* runLabel, cudaStream_t st);
 void launch_paint(const Geom& g, const u32* DV, const CclBufs& B, const u64* runLabel, int out_width, int has_label,
                   u64 label, int fortran_order, void* out, cudaStream_t st);

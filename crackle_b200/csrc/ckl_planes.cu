@@ -447,72 +447,10 @@ __global__ void __launch_bounds__(256) k_root_rank(Geom g, const u32* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256) k_run_resolve(Geom g, u64 total_runs, const u32* __restrict__ parent,
-                                                      const u64* __restrict__ runBase, const u32* __restrict__ compRank,
-                                                      const u32* __restrict__ runStart, const u64* __restrict__ compBase,
-                                                      u32* __restrict__ runComp, u32* __restrict__ compPix) {
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < total_runs; r += stride) {
-    // slice of this run: last z with runBase[z] <= r
-    u32 lo = 0, hi = g.sz;
-    while (hi - lo > 1) { const u32 m = (lo + hi) >> 1; if (runBase[m] <= r) lo = m; else hi = m; }
-    const u64 gb = runBase[lo];
-    const u32 i = (u32)(r - gb);
-    const u32 root = uf_find(parent + gb, i);
-    const u32 c = compRank[gb + root];
-    runComp[r] = c;
-    if (root == i) compPix[compBase[lo] + c] = runStart[r];
-  }
-}
-
 // CRC-32C of the virtual uint32 image cc[pixel] = runComp[run(pixel)].  The image is constant along runs and runs
 // tile the slice in raster order, so with d_r = comp[r] ^ comp[r-1] placed at the run start and extending to the
 // end of the image (GF(2)-linearity of the raw CRC):  raw = XOR_r  d_r(x) * H[sxy - start_r],
 // H[m] = sum_{j=1..m} x^(32 j) mod P  (table built once per context).  One short GF(2) multiply per RUN.
-__device__ __forceinline__ u32 gf_mul_id(u32 d, u32 h, const u32* t0) {
-  if (d < 65536u) {
-    h = t0[h & 0xFF] ^ (h >> 8);                          // * x^8
-    h = t0[h & 0xFF] ^ (h >> 8);                          // * x^16: the 16 low bits of d are x^16 .. x^31
-    u32 p = 0;
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-      p ^= h & (0u - ((d >> (15 - j)) & 1u));
-      h = (h >> 1) ^ (CKL_CRC_POLY & (0u - (h & 1u)));
-    }
-    return p;
-  }
-  return gf_mul(d, h);
-}
-
-__global__ void __launch_bounds__(256) k_run_crc(Geom g, u64 total_runs, const u64* __restrict__ runBase, const u32* __restrict__ runComp,
-                                                  const u32* __restrict__ runStart, const u32* __restrict__ H,
-                                                  const CrcTables* __restrict__ tabs, u32* sliceCrc) {
-  __shared__ u32 t0[256];
-  for (u32 i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t[0][i];
-  __syncthreads();
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  const u64 nloop = (total_runs + stride - 1) / stride;
-  for (u64 k = 0; k < nloop; k++) {
-    const u64 r = k * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u32 crc = 0, z = 0xFFFFFFFFu;
-    if (r < total_runs) {
-      u32 lo = 0, hi = g.sz;
-      while (hi - lo > 1) { const u32 m = (lo + hi) >> 1; if (runBase[m] <= r) lo = m; else hi = m; }
-      z = lo;
-      const u32 prev = r == runBase[z] ? 0u : runComp[r - 1];
-      const u32 d = runComp[r] ^ prev;
-      if (d) crc = gf_mul_id(d, H[(u32)g.sxy - runStart[r]], t0);
-    }
-    const u32 z0 = __shfl_sync(FULL_MASK, z, 0);
-    if (__all_sync(FULL_MASK, z == z0)) {
-      const u32 x = __reduce_xor_sync(FULL_MASK, crc);
-      if ((threadIdx.x & 31) == 0 && z0 != 0xFFFFFFFFu && x) atomicXor(sliceCrc + z0, x);
-    } else if (z != 0xFFFFFFFFu && crc) {
-      atomicXor(sliceCrc + z, crc);
-    }
-  }
-}
-
 // H table: level tables by one thread (H[0..B], H[k*B]), then a parallel fill  H[kB + j] = H[kB] * x^(32 j) ^ H[j]
 #define CRCH_B 1024u
 __global__ void k_crcH_levels(const CrcTables* __restrict__ tabs, u32 n, u32* __restrict__ Hl, u32* __restrict__ Gk) {
