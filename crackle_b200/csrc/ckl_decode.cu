@@ -276,29 +276,34 @@ __global__ void __launch_bounds__(32) k_dec_markov(const DecSlice* __restrict__ 
   u32* out = fields + d.wordOff;
   u64 n = 0;
   if (d.blen) {
-    const u8* mdl = msm ? smodel : model;
-    BitReader br;
-    br.init(stream + d.body, d.blen);
-    const u32 top = 2 * (order - 1);
-    u32 acc = br.peek(2);          // first symbol: 2 raw bits (it is the absolute move; the running sum starts at 0)
-    br.skip(2);
-    u32 ctx = acc << top;
-    n = 1;
-    u64 pos = 2;
-    const u64 nbit = (u64)d.blen * 8;
-    while (pos < nbit) {
-      const u32 v = br.peek(3);
-      u32 rank, len;
-      if (!(v & 1)) { rank = 0; len = 1; } else if (!(v & 2)) { rank = 1; len = 2; } else if (!(v & 4)) { rank = 2; len = 3; } else { rank = 3; len = 3; }
-      const u32 dsym = mdl[(u64)ctx * 4 + rank];
-      br.skip(len);
-      pos += len;
-      ctx = (ctx >> 2) + (dsym << top);
-      acc |= dsym << (2 * (u32)(n & 15));
-      n++;
-      if ((n & 15) == 0) { out[(n >> 4) - 1] = acc; acc = 0; }
+    // Lean serial loop (a lone warp issues about one instruction every four cycles, so the instruction count is the cost):
+    // a two-word bit window read with one funnel shift, code length and rank of the 0 / 10 / 110 / 111 code from two 16-bit
+    // tables indexed by the next three bits, the model row read through an explicit shared-space address, 32-bit counters.
+    u32 ma = (u32)__cvta_generic_to_shared(smodel);
+    asm volatile("" : "+r"(ma));
+    const u32 top2 = 2 * (order - 1) + 2;            // the context is kept pre-multiplied by 4 (the model row offset)
+    u64 wi = 0;
+    u32 cur = dec_word(d, stream, nullptr, 0, wi++), nxt = dec_word(d, stream, nullptr, 0, wi++);
+    u32 bp = 2;                                       // bit position inside `cur`; the window is (nxt : cur) >> bp
+    u32 acc = cur & 3u;                               // first symbol: 2 raw bits (it is the absolute move; the running sum starts at 0)
+    u32 ctx4 = acc << top2, sh = 2, cnt = 1;
+    int rem = (int)(d.blen * 8u) - 2;                 // code sizes are far below 2^28 bytes (checked by the caller)
+    u32* o = out;
+    while (rem > 0) {
+      const u32 v2 = (__funnelshift_r(cur, nxt, bp) & 7u) * 2u;
+      const u32 len = (0xD9D9u >> v2) & 3u, rank = (0xC484u >> v2) & 3u;     // 0 -> (1, 0); 10 -> (2, 1); 110 -> (3, 2); 111 -> (3, 3)
+      u32 dsym;
+      if (msm) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(dsym) : "r"(ma + ctx4 + rank));
+      else dsym = model[(u64)ctx4 + rank];
+      bp += len; rem -= (int)len;
+      ctx4 = ((ctx4 >> 2) & ~3u) + (dsym << top2);
+      acc |= dsym << sh;
+      sh += 2; cnt++;
+      if (sh == 32) { *o++ = acc; acc = 0; sh = 0; }
+      if (bp >= 32) { bp -= 32; cur = nxt; nxt = dec_word(d, stream, nullptr, 0, wi++); }
     }
-    if (n & 15) out[n >> 4] = acc;
+    if (sh) *o = acc;
+    n = cnt;
   }
   ncpOut[z] = (u32)n;
 }
