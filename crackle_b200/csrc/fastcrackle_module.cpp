@@ -34,9 +34,10 @@ static py::bytes compress(const py::array& labels, const bool allow_pins = false
   uint64_t n = 0;
   char err[512] = {0};
   int rc;
+  const void* src = labels.data();          // every pybind11 / numpy accessor is called while the GIL is still held
   {
     py::gil_scoped_release nogil;
-    rc = crackle_b200_compress(labels.data(), width, sx, sy, sz, fortran_order ? 1 : 0, (int)markov_model_order, &out, &n, err, sizeof err);
+    rc = crackle_b200_compress(src, width, sx, sy, sz, fortran_order ? 1 : 0, (int)markov_model_order, &out, &n, err, sizeof err);
   }
   if (rc) throw std::runtime_error(err);
   py::bytes b(reinterpret_cast<const char*>(out), n);
@@ -66,10 +67,12 @@ static py::array decompress(const py::buffer buffer, int64_t z_start = 0, int64_
   else if (h.data_width == 4) arr = py::array_t<uint32_t>(voxels);
   else arr = py::array_t<uint64_t>(voxels);
   int rc;
+  void* dst = arr.mutable_data();
+  const uint64_t dst_bytes = (uint64_t)arr.nbytes();
   {
     py::gil_scoped_release nogil;
-    rc = crackle_b200_decompress(data, nbytes, z_start, z_end, label.has_value() ? 1 : 0, label.value_or(0), arr.mutable_data(),
-                                 (uint64_t)arr.nbytes(), err, sizeof err);
+    rc = crackle_b200_decompress(data, nbytes, z_start, z_end, label.has_value() ? 1 : 0, label.value_or(0), dst, dst_bytes, err,
+                                 sizeof err);
   }
   if (rc) throw std::runtime_error(err);
   return arr;
