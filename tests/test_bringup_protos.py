@@ -15,3 +15,8 @@ def _load(name):
 def test_chain_pass_as_scans_matches_the_serial_pass():
     # round-2 groundwork: the decoder's serial chain pass restated as scans + one sort by stack level
     _load("proto_chain_scan").main()
+
+
+def test_prefix_code_parse_as_a_scan_matches_the_serial_parse():
+    # round-2 groundwork: the order-N bitstream's code boundaries from a three-state automaton scan
+    _load("proto_markov_parse").main()
