@@ -1,10 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- compress + decompress throughput of the per-z-slice crackle hot path on B200.
 
-Contract: python bench.py --gpus N --steps K --warmup W [--impl reference]
-A "step" = one compress of the resident volume followed by one decompress of the resulting stream (each voxel is
-processed twice per step); value = 2*V*N / step time in GVox/s.  Inputs (8.6 GB per GPU at 1024^3 uint64) are larger
-than L2, so no explicit L2 flush is needed between iterations.  One JSON line on stdout (rank 0)."""
+Contract: python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c2|c4|c5] [--scaling strong|weak]
+
+Workloads (BASELINE.json `configs`):
+  c3 (default)  1024^3 uint64 jittered-Voronoi segmentation, order 0 -- the configuration the metric is quoted on.
+                N > 1: ONE 1024^3 volume z-sharded over the N ranks (strong scaling, rank r owns slices
+                [r*1024/N, (r+1)*1024/N)); --scaling weak gives every rank its own 1024^3 slab of a 1024x1024x1024N volume.
+  c2 / c4       512^3 uint64 (~10k labels), markov order 0 / 5
+  c5            2048x2048x1024 uint32 dense labels (cell 16): decompress-only plus decompress(label=...) mask extraction,
+                z-sharded over the N ranks
+A "step" = one compress of the resident volume followed by one decompress of the resulting stream (c5: one full decode plus
+one single-label mask decode); every voxel is processed twice per step; value = 2*V_total / step time in GVox/s.
+Inputs are far larger than L2 (8.6 GB at 1024^3 uint64), so no explicit L2 flush is needed between iterations.
+One JSON line on stdout (rank 0)."""
 import argparse
 import json
 import os
@@ -18,7 +27,21 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "compress+decompress GVox/s (uint64 1024^3)"
+WORKLOADS = {
+    #        shape               dtype      cell order mode
+    "c3": ((1024, 1024, 1024), "uint64", 24, 0, "roundtrip"),
+    "c2": ((512, 512, 512), "uint64", 24, 0, "roundtrip"),
+    "c4": ((512, 512, 512), "uint64", 24, 5, "roundtrip"),
+    "c5": ((2048, 2048, 1024), "uint32", 16, 0, "decode"),
+}
+
+
+def metric_name(shape, dtype, mode):
+    sx, sy, sz = shape
+    dims = f"{sx}^3" if sx == sy == sz else f"{sx}x{sy}x{sz}"
+    if mode == "decode":
+        return f"decompress + decompress(label=) GVox/s ({dtype} {dims})"
+    return f"compress+decompress GVox/s ({dtype} {dims})"
 
 
 def parse_args():
@@ -27,15 +50,27 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--shape", default="1024,1024,1024", help="per-GPU slab sx,sy,sz")
-    ap.add_argument("--cell", type=int, default=24)
-    ap.add_argument("--order", type=int, default=0, help="markov_model_order")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = one volume of the workload's shape z-sharded over the ranks (BASELINE configs[2]); "
+                         "weak = every rank owns a slab of the workload's shape")
+    ap.add_argument("--shape", default=None, help="override the workload's sx,sy,sz")
+    ap.add_argument("--cell", type=int, default=None)
+    ap.add_argument("--order", type=int, default=None, help="markov_model_order")
     ap.add_argument("--cpu-slices", type=int, default=128, help="z-slab size of the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the byte-parity checks of the warm-up (round trip is always checked)")
     ap.add_argument("--prof", action="store_true", help="print per-stage timings to stderr")
     ap.add_argument("--chunks", type=int, default=0, help="z-chunk pipelining: 0 = library default (host-resident volumes only), 1 = off, K = force")
-    return ap.parse_args()
+    a = ap.parse_args()
+    shape, dtype, cell, order, mode = WORKLOADS[a.workload]
+    if a.shape:
+        shape = tuple(int(v) for v in a.shape.split(","))
+    a.shape, a.dtype, a.mode = shape, dtype, mode
+    a.cell = cell if a.cell is None else a.cell
+    a.order = order if a.order is None else a.order
+    return a
 
 
 class ClockSampler:
@@ -78,7 +113,6 @@ class ClockSampler:
         rows = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= t1 + 0.12)]
         if len(rows) < 2:
             rows, window = [r for (_, r) in self.rows], "warmup+timed"
-        self.window = window
         for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
@@ -94,59 +128,97 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def ref_times(vol, order, reps):
-    """Reference CPU path (oracle/_ref, all host cores) on `vol`; returns (t_compress, t_decompress, kind, cores)."""
+def ref_times(vol, order, reps, mode="roundtrip", label=None):
+    """Reference CPU path (oracle/_ref, all host cores) on `vol`; returns (t_first, t_second, kind, cores): compress and
+    decompress times, or (mode "decode") full-decode and label-mask-decode times."""
     from oracle import oracle as O
     cores = os.cpu_count() or 1
     ref = O.ref_module()
-    tc = td = 1e30
+    ta = tb = 1e30
     if ref is not None:
         kind = "reference"
+        b = None
         for _ in range(reps):
-            t0 = time.perf_counter(); b = ref.compress(vol, False, True, order, False, True, 0, 0); t1 = time.perf_counter()
-            ref.decompress(b, 0, -1, 0, None); t2 = time.perf_counter()
-            tc, td = min(tc, t1 - t0), min(td, t2 - t1)
+            if mode == "decode":
+                if b is None:
+                    b = ref.compress(vol, False, True, order, False, True, 0, 0)
+                t0 = time.perf_counter(); ref.decompress(b, 0, -1, 0, None); t1 = time.perf_counter()
+                ref.decompress(b, 0, -1, 0, label); t2 = time.perf_counter()
+            else:
+                t0 = time.perf_counter(); b = ref.compress(vol, False, True, order, False, True, 0, 0); t1 = time.perf_counter()
+                ref.decompress(b, 0, -1, 0, None); t2 = time.perf_counter()
+            ta, tb = min(ta, t1 - t0), min(tb, t2 - t1)
     else:
         kind, cores = "port", 1
+        b = None
         for _ in range(reps):
-            t0 = time.perf_counter(); b = O.compress(vol, order); t1 = time.perf_counter()
-            O.decompress(b); t2 = time.perf_counter()
-            tc, td = min(tc, t1 - t0), min(td, t2 - t1)
-    return tc, td, kind, cores
+            if mode == "decode":
+                if b is None:
+                    b = O.compress(vol, order)
+                t0 = time.perf_counter(); O.decompress(b); t1 = time.perf_counter()
+                O.decompress(b, label=label); t2 = time.perf_counter()
+            else:
+                t0 = time.perf_counter(); b = O.compress(vol, order); t1 = time.perf_counter()
+                O.decompress(b); t2 = time.perf_counter()
+            ta, tb = min(ta, t1 - t0), min(tb, t2 - t1)
+    return ta, tb, kind, cores
 
 
-def run_reference(args, shape):
-    """--impl reference: the reference's own CPU implementation on a bounded z-slab of the same workload."""
+def np_dtype(name):
+    return np.dtype(name)
+
+
+def host_sample(args, zs):
+    """first `zs` slices of the workload as an F-ordered numpy array (GPU synth when a device is there: same integers)."""
     from crackle_b200 import synth
+    sx, sy, sz = args.shape
+    bits = 40 if args.dtype == "uint64" else 30
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError
+        t = synth.jittered_voronoi_torch((sx, sy, zs), args.cell, np_dtype(args.dtype), seed=0, id_bits=bits, device="cuda", sz_total=sz)
+        vol = np.asfortranarray(t.cpu().numpy().transpose(2, 1, 0))
+        del t
+    except Exception:
+        vol = synth.jittered_voronoi((sx, sy, zs), args.cell, np_dtype(args.dtype), seed=0, id_bits=bits, sz_total=sz)
+    return vol
+
+
+def workload_text(args, world, scaling):
+    sx, sy, sz = args.shape
+    what = ("decompress-only plus decompress(label=) mask extraction" if args.mode == "decode" else "compress then decompress")
+    shard = ""
+    if world > 1:
+        shard = (f"; ONE volume z-sharded over {world} GPUs ({sz // world} slices per rank)" if scaling == "strong"
+                 else f"; every rank owns a {sx}x{sy}x{sz} slab of a {sx}x{sy}x{sz * world} volume")
+    return (f"{sx}x{sy}x{sz} {args.dtype} jittered-Voronoi segmentation (cell {args.cell}), flat labels, markov order {args.order}; "
+            f"{what}, device-resident{shard}")
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation on a bounded z-slab of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sx, sy, sz = shape
-    zs = min(args.cpu_slices, sz)
-    try:
-        import torch
-        if torch.cuda.is_available():
-            t = synth.jittered_voronoi_torch((sx, sy, zs), args.cell, np.uint64, seed=0, id_bits=40, device="cuda", sz_total=sz)
-            vol = np.asfortranarray(t.cpu().numpy().transpose(2, 1, 0))
-            del t
-        else:
-            raise RuntimeError
-    except Exception:
-        vol = synth.jittered_voronoi((sx, sy, zs), args.cell, np.uint64, seed=0, id_bits=40, sz_total=sz)
+    sx, sy, sz = args.shape
+    zs = min(args.cpu_slices if args.dtype == "uint64" and sx <= 1024 else max(8, args.cpu_slices // 4), sz)
+    vol = host_sample(args, zs)
     V = vol.size
+    label = int(vol[sx // 2, sy // 2, zs // 2])
     times = []
     for i in range(args.warmup + args.steps):
-        tc, td, kind, cores = ref_times(vol, args.order, 1)
+        ta, tb, kind, cores = ref_times(vol, args.order, 1, args.mode, label)
         if i >= args.warmup:
-            times.append(tc + td)
+            times.append(ta + tb)
     t = float(np.mean(times))
     val = 2 * V / t / 1e9
     sample = f"{sx}x{sy}x{zs} z-slab of the {sx}x{sy}x{sz} workload"
-    line = {"metric": METRIC, "value": val, "unit": "GVox/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+    line = {"metric": metric_name(args.shape, args.dtype, args.mode), "value": val, "unit": "GVox/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": args.scaling if args.gpus > 1 else "weak",
+            "vs_baseline": None, "dtype": "u64" if args.dtype == "uint64" else "u32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"{sx}x{sy}x{sz} uint64 jittered-Voronoi segmentation (cell {args.cell}), flat labels, "
-                                   f"markov order {args.order}; compress then decompress", "sample": sample},
+            "config": {"workload": workload_text(args, 1, args.scaling).replace(", device-resident", ""), "sample": sample},
             "cpu_baseline": {"value": val, "unit": "GVox/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "GVox/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -155,13 +227,13 @@ def run_reference(args, shape):
 
 def main():
     args = parse_args()
-    shape = tuple(int(v) for v in args.shape.split(","))
     if args.impl == "reference":
-        return run_reference(args, shape)
+        return run_reference(args)
 
     import torch
     import crackle_b200 as cb
     from crackle_b200 import synth
+    from crackle_b200 import dist as cdist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -171,44 +243,100 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    sx, sy, sz = shape
-    V = sx * sy * sz
+    scaling = args.scaling if world > 1 else "weak"
+    sx, sy, sz = args.shape
+    dt = np_dtype(args.dtype)
+    width = dt.itemsize
+    tdt = getattr(torch, args.dtype)
+    bits = 40 if args.dtype == "uint64" else 30
+    if scaling == "strong":
+        sz_total = sz
+        z0, z1 = rank * sz // world, (rank + 1) * sz // world
+    else:
+        sz_total = sz * world
+        z0, z1 = rank * sz, (rank + 1) * sz
+    szl = z1 - z0
+    Vl = sx * sy * szl                 # voxels of this rank's slab
+    V = sx * sy * sz_total             # voxels of the whole job
     ctx = cb.Context(local)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     ctx.set_chunks(args.chunks)
+    job = cdist.ShardedCodec(ctx, dist) if world > 1 else None
 
-    # each rank owns a z-slab of a (sx, sy, sz*world) volume: weak scaling, per-GPU work fixed
-    vol = synth.jittered_voronoi_torch(shape, args.cell, np.uint64, seed=0, id_bits=40, device="cuda", z0=rank * sz,
-                                       sz_total=sz * world)
+    vol = synth.jittered_voronoi_torch((sx, sy, szl), args.cell, dt, seed=0, id_bits=bits, device="cuda", z0=z0, sz_total=sz_total)
     out = torch.empty_like(vol)
     torch.cuda.synchronize()
+    label = int(vol[szl // 2, sy // 2, sx // 2].item())
+    mask = torch.empty(vol.shape, dtype=torch.uint8, device="cuda") if args.mode == "decode" else None
 
-    if world > 1:
-        from crackle_b200 import dist as cdist
-        job = cdist.ShardedCodec(ctx, dist)
+    def compress_step():
+        if world > 1:
+            return job.compress(vol, z0=z0, sz_total=sz_total, markov_model_order=args.order)
+        ctx.compress_ptr(vol.data_ptr(), 1, width, sx, sy, szl, True, args.order)
+        p, n = ctx.result_device()
+        return torch.as_tensor(cdist._DevBytes(p, n), device="cuda")
+
+    def decompress_step(s, lab=None, dst=None):
+        dst = out if dst is None else dst
+        ctx.decompress_into(s.data_ptr(), 1, s.numel(), z0, z1, lab, dst.data_ptr(), 1, dst.numel() * dst.element_size())
+
+    state = {}
+    if args.mode == "decode":
+        state["s"] = compress_step().clone()          # untimed: the stream the decode-only workload starts from
 
         def step():
-            stream_t = job.compress(vol, z0=rank * sz, sz_total=sz * world, markov_model_order=args.order)
-            stream_t = job.broadcast_stream(stream_t)
-            job.decompress_shard(stream_t, rank * sz, (rank + 1) * sz, out)
-            return stream_t
+            decompress_step(state["s"])
+            decompress_step(state["s"], label, mask)
+            return state["s"]
     else:
         def step():
-            n = ctx.compress_ptr(vol.data_ptr(), 1, 8, sx, sy, sz, True, args.order)
-            p, n = ctx.result_device()
-            ctx.decompress_into(p, 1, n, 0, -1, None, out.data_ptr(), 1, out.numel() * 8)
-            return n
+            s = compress_step()
+            decompress_step(s)
+            return s
 
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
         time.sleep(0.5)                           # let nvidia-smi come up before the GPU is loaded
+    s = None
     for _ in range(max(1, args.warmup)):          # at least one untimed pass: it is also the round-trip check
-        step()
+        s = step()
     torch.cuda.synchronize()
-    assert torch.equal(out.view(torch.int64), vol.view(torch.int64)), "round trip mismatch"
-    ckl_bytes = ctx.result_device()[1] if world == 1 else None
+    assert torch.equal(out.view(torch.uint8), vol.view(torch.uint8)), "round trip mismatch"
+    if mask is not None:
+        assert torch.equal(mask.view(torch.bool), vol.view(torch.int64 if width == 8 else torch.int32) == label), "label mask mismatch"
+    ckl_bytes = int(s.numel())
+    parity = {"round_trip": "voxel-exact on every rank"}
+
+    # byte parity inside the same run: (a) a 64-slice slab against the reference compiled on this box
+    # (oracle/_ref, the checker); (b) N > 1, strong scaling: the sharded stream == a single-GPU compress of the whole volume
+    if not args.no_parity:
+        from oracle import oracle as O
+        ref = O.ref_module()
+        zs = min(64 if sx * sy <= 1024 * 1024 else 16, szl)
+        if rank == 0:
+            chk = cb.Context(local)
+            hv = np.asfortranarray(vol[:zs].cpu().numpy().transpose(2, 1, 0))
+            got = chk.compress(vol[:zs].contiguous(), args.order)
+            want = ref.compress(hv, False, True, args.order, False, True, 0, 0) if ref is not None else O.compress(hv, args.order)
+            assert got == bytes(want), "byte parity against the reference failed on the warm-up slab"
+            parity["slab"] = f"{sx}x{sy}x{zs} slab: {len(got)} bytes == {'oracle/_ref (compiled reference)' if ref is not None else 'oracle port'}"
+            if world > 1 and scaling == "strong" and args.mode == "roundtrip":
+                whole = synth.jittered_voronoi_torch((sx, sy, sz_total), args.cell, dt, seed=0, id_bits=bits, device="cuda")
+                torch.cuda.synchronize()
+                chk.compress_ptr(whole.data_ptr(), 1, width, sx, sy, sz_total, True, args.order)
+                p, n = chk.result_device()
+                mono = torch.as_tensor(cdist._DevBytes(p, n), device="cuda")
+                torch.cuda.synchronize()
+                assert n == s.numel() and torch.equal(mono, s), "sharded stream differs from the single-GPU stream"
+                parity["sharded"] = f"{world}-rank stream ({n} bytes) == single-GPU compress of the whole volume (rank 0)"
+                del whole, mono
+            chk.close()
+            del chk
+            torch.cuda.empty_cache()
+        if dist:
+            dist.barrier()
 
     ctx.prof_enable(True)
     launches0 = cb.codec.launch_count()
@@ -235,9 +363,26 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_step = ms / args.steps
-    value = 2.0 * V * world / (ms_step * 1e-3) / 1e9
+    value = 2.0 * V / (ms_step * 1e-3) / 1e9
 
-    # per-stage (CUDA events inside the library, same stream) -> roofline of the dominant kernel
+    def timed(fn):
+        """per-call time of `fn` over args.steps calls: CUDA events on the stream, barrier both sides, max over ranks"""
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.steps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        tt = a.elapsed_time(b) / args.steps
+        if dist:
+            x = torch.tensor([tt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(x, op=dist.ReduceOp.MAX)
+            tt = float(x.item())
+        return tt
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -246,108 +391,130 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured" if "hbm_gbs" in peaks else "fallback"
     stage_ms = {k: v[0] / max(1, v[1]) for k, v in prof.items()}
-    # roofline: the dominant stage (largest CUDA-event time inside the library, measured on the stream it runs on) against
-    # the algorithmic bytes of one launch (compress reads the volume and writes the stream, decompress the
-    # reverse); `traffic` = dram bytes of that stage's top kernel from the committed ncu capture (profiles/), per launch
-    # stages that are exactly ONE kernel launch (the others bundle several kernels and, on the low-priority stream, include
-    # time spent waiting for SMs): the dominant kernel is picked among these
-    one_kernel = {"edges": "k_edges<u64,16>", "trace_replay": "k_replay<0>", "d_paint": "k_paint_rows<u64,false>"}
-    cand = {k: v for k, v in stage_ms.items() if k in one_kernel}
-    dom = max(cand, key=cand.get) if cand else None
+
+    # Algorithmic bytes: compress reads the volume once and writes the stream; decompress reads the stream and
+    # writes the volume once (1 byte per voxel for a label mask).  All ranks together; the roofline peak is N x one GPU's.
+    if args.mode == "decode":
+        alg_a, alg_b = ckl_bytes * world + V * width, ckl_bytes * world + V
+        names = ("decompress", "decompress_label")
+        t_a = timed(lambda: decompress_step(state["s"]))
+        t_b = timed(lambda: decompress_step(state["s"], label, mask))
+    else:
+        alg_a, alg_b = V * width + ckl_bytes * world, ckl_bytes * world + V * width
+        names = ("compress", "decompress")
+        t_a = timed(compress_step)
+        s = compress_step()
+        t_b = timed(lambda: decompress_step(s))
     traffic_tab = {}
     try:
-        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")))
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")))
     except Exception:
         pass
-    roof = None
-    streaming = {}
-    if dom and ckl_bytes:
-        alg = V * 8 + ckl_bytes
-        ach = alg / (stage_ms[dom] * 1e-3) / 1e9
-        tr = traffic_tab.get(dom, {}) if sx * sy * sz == 1024 ** 3 else {}
-        roof = {"bound": "hbm", "kernel": one_kernel[dom], "stage": dom, "side": "decompress" if dom.startswith("d_") else "compress",
-                "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
-                "traffic": tr.get("dram_bytes"), "algorithmic_bytes_per_launch": alg, "kernel_ms": stage_ms[dom],
-                "note": ("the single-kernel stage with the largest live CUDA-event time in the timed region (events on the stream the kernel "
-                         "is launched on; other kernels run beside it on the second stream).  `achieved` = algorithmic bytes of the whole "
-                         "compress (or decompress) call / that kernel's time.  k_replay is the serial crack-graph walk, one warp per slice, "
-                         "bound by dependent shared-memory latency and not by HBM; the full-width streaming kernels are under roofline_streaming")}
-        for k in ("edges", "d_paint"):
-            if k in stage_ms:
-                a2 = alg / (stage_ms[k] * 1e-3) / 1e9
-                streaming[k] = {"achieved": a2, "frac": a2 / peak, "kernel_ms": stage_ms[k],
-                                "traffic": (traffic_tab.get(k, {}) if sx * sy * sz == 1024 ** 3 else {}).get("dram_bytes")}
+    tr = traffic_tab if (args.shape == (1024, 1024, 1024) and world == 1 and args.mode == "roundtrip" and args.order == 0) else {}
+    alg = alg_a + alg_b
+    ach = alg / (ms_step * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "whole step: every kernel of one %s + one %s call" % names, "achieved": ach, "peak": peak * world,
+            "peak_kind": peak_kind + (f" x {world} GPUs" if world > 1 else ""), "unit": "GB/s", "frac": ach / (peak * world),
+            "traffic": tr.get("step", {}).get("dram_bytes"), "algorithmic_bytes_per_step": alg,
+            names[0]: {"ms": t_a, "algorithmic_bytes": alg_a, "achieved": alg_a / (t_a * 1e-3) / 1e9, "frac": alg_a / (t_a * 1e-3) / 1e9 / (peak * world)},
+            names[1]: {"ms": t_b, "algorithmic_bytes": alg_b, "achieved": alg_b / (t_b * 1e-3) / 1e9, "frac": alg_b / (t_b * 1e-3) / 1e9 / (peak * world)},
+            "note": "whole-call fractions: algorithmic bytes of the call / its CUDA-event time / measured HBM peak.  The kernels between the two "
+                    "full-width streaming kernels work on 2 bits per voxel and are issue- or latency-bound, not HBM-bound; roofline_kernels "
+                    "lists the single-kernel stages with their OWN algorithmic bytes (rank 0, live inside the timed step)."}
+    # single-kernel stages: own algorithmic bytes of the kernel on rank 0's slab
+    own = {"edges": ("k_edges", Vl * width + Vl // 4, "hbm"), "d_paint": ("k_paint_rows", Vl * width + Vl // 8, "hbm"),
+           "trace_replay": ("k_replay", None, "shared-memory latency (serial walk per slice); not an HBM kernel")}
+    kern = {}
+    for k, (kname, b, bound) in own.items():
+        if k in stage_ms:
+            e = {"kernel": kname, "kernel_ms": stage_ms[k], "bound": bound, "traffic": tr.get(k, {}).get("dram_bytes")}
+            if b:
+                e.update({"algorithmic_bytes": b, "achieved": b / (stage_ms[k] * 1e-3) / 1e9, "frac": b / (stage_ms[k] * 1e-3) / 1e9 / peak})
+            kern[k] = e
 
-    line = {"metric": METRIC, "value": value, "unit": "GVox/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic", "impl": "b200",
-            "config": {"workload": f"{sx}x{sy}x{sz} uint64 jittered-Voronoi segmentation per GPU (cell {args.cell}, 40-bit ids), "
-                                   f"flat labels, markov order {args.order}; compress then decompress, device-resident",
-                       "l2": "inputs (8 B/voxel volume) are far larger than the 126 MB L2; no flush needed",
-                       "voxels_per_step": 2 * V * world, "ckl_bytes": ckl_bytes},
+    line = {"metric": metric_name(args.shape, args.dtype, args.mode), "value": value, "unit": "GVox/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "u64" if width == 8 else "u32", "data": "synthetic", "impl": "b200",
+            "config": {"workload": workload_text(args, world, scaling), "name": args.workload,
+                       "l2": "inputs (volume) are far larger than the 126 MB L2; no flush needed",
+                       "voxels_per_step": 2 * V, "ckl_bytes": ckl_bytes, "slices_per_rank": szl, "parity": parity},
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
-            "gpu_launches": int(launches), "clocks": clk}
-    if roof:
-        line["roofline"] = roof
-        line["roofline_streaming"] = streaming
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_kernels": kern,
+            f"{names[0]}_gvox_s": V / (t_a * 1e-3) / 1e9, f"{names[0]}_ms": t_a, f"{names[0]}_hbm_frac": roof[names[0]]["frac"],
+            f"{names[1]}_gvox_s": V / (t_b * 1e-3) / 1e9, f"{names[1]}_ms": t_b, f"{names[1]}_hbm_frac": roof[names[1]]["frac"]}
+    if job is not None:
+        line["collectives_per_compress"] = "metadata all_gather + unique-table all_gather + ONE padded all_gather of the packed blocks" + \
+                                           (" + statistics all_reduce + code-size all_gather (order > 0)" if args.order > 0 else "")
 
-    # separate compress / decompress throughput (device-resident), for the record
-    if world == 1:
-        for name, fn in (("compress", lambda: ctx.compress_ptr(vol.data_ptr(), 1, 8, sx, sy, sz, True, args.order)),
-                         ("decompress", lambda: ctx.decompress_into(*ctx.result_device()[:1], 1, ctx.result_device()[1], 0, -1, None,
-                                                                    out.data_ptr(), 1, out.numel() * 8))):
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            for _ in range(args.steps):
-                fn()
-            b.record(stream)
-            torch.cuda.synchronize()
-            t = a.elapsed_time(b) / args.steps
-            line[f"{name}_gvox_s"] = V / (t * 1e-3) / 1e9
-            line[f"{name}_ms"] = t
-            line[f"{name}_hbm_frac"] = (V * 8 + ckl_bytes) / (t * 1e-3) / 1e9 / peak
-
-    # end to end through the public host API: pinned host buffers, H2D + D2H inside the timed region
-    if not args.no_e2e and world == 1:
+    # end to end through the public host API: pinned HOST buffers, H2D + D2H inside the timed region, every rank through its
+    # own PCIe link; wall clock between barriers, max over ranks
+    if not args.no_e2e:
         hvol = torch.empty(vol.shape, dtype=vol.dtype, pin_memory=True)
         hvol.copy_(vol)
         hout = torch.empty(vol.shape, dtype=vol.dtype, pin_memory=True)
+        hmask = torch.empty(vol.shape, dtype=torch.uint8, pin_memory=True) if args.mode == "decode" else None
         hstream = torch.empty(ckl_bytes + 64, dtype=torch.uint8, pin_memory=True)
+        if args.mode == "decode":
+            hstream[:ckl_bytes].copy_(state["s"])
         torch.cuda.synchronize()
 
         def e2e_step():
-            n = ctx.compress_ptr(hvol.data_ptr(), 0, 8, sx, sy, sz, True, args.order)
+            if args.mode == "decode":
+                ctx.decompress_into(hstream.data_ptr(), 0, ckl_bytes, z0, z1, None, hout.data_ptr(), 0, hout.numel() * width)
+                ctx.decompress_into(hstream.data_ptr(), 0, ckl_bytes, z0, z1, label, hmask.data_ptr(), 0, hmask.numel())
+                return ckl_bytes
+            if world > 1:
+                st = job.compress(hvol, z0=z0, sz_total=sz_total, markov_model_order=args.order)
+                n = st.numel()
+                if rank == 0:                      # the stream is the product of compress: rank 0 delivers it to the host
+                    ctx.result_to(hstream.data_ptr(), 0, hstream.numel())
+                job.decompress_shard(st, z0, z1, hout)
+                return n
+            n = ctx.compress_ptr(hvol.data_ptr(), 0, width, sx, sy, szl, True, args.order)
             ctx.result_to(hstream.data_ptr(), 0, hstream.numel())
-            ctx.decompress_into(hstream.data_ptr(), 0, n, 0, -1, None, hout.data_ptr(), 0, hout.numel() * 8)
+            ctx.decompress_into(hstream.data_ptr(), 0, n, 0, -1, None, hout.data_ptr(), 0, hout.numel() * width)
             return n
         e2e_step()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
         t0 = time.perf_counter()
         ne = max(1, min(args.steps, 3))
         for _ in range(ne):
             n = e2e_step()
         torch.cuda.synchronize()
         te = (time.perf_counter() - t0) / ne
-        assert torch.equal(hout.view(torch.int64), hvol.view(torch.int64))
-        line["e2e"] = {"value": 2.0 * V / te / 1e9, "unit": "GVox/s", "h2d_bytes_per_step": int(V * 8 + n),
-                       "d2h_bytes_per_step": int(n + V * 8), "ms_per_step": te * 1e3,
-                       "api": "ckl_compress / ckl_decompress with pinned HOST buffers (what fastcrackle.compress/decompress bind)",
-                       "chunks": "library default: 4 z-chunks on child contexts for host-resident volumes, so H2D / D2H copies of one chunk "
-                                 "overlap the kernels of the others" if args.chunks == 0 else args.chunks}
+        if dist:
+            x = torch.tensor([te], device="cuda", dtype=torch.float64)
+            dist.all_reduce(x, op=dist.ReduceOp.MAX)
+            te = float(x.item())
+        assert torch.equal(hout.view(torch.uint8), hvol.view(torch.uint8))
+        if args.mode == "decode":
+            h2d, d2h = 2 * ckl_bytes * world, V * width + V
+        else:
+            h2d, d2h = V * width + (n if world == 1 else 0), n + V * width
+        line["e2e"] = {"value": 2.0 * V / te / 1e9, "unit": "GVox/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "ms_per_step": te * 1e3,
+                       "api": ("ckl_decompress with pinned HOST stream and output buffers" if args.mode == "decode" else
+                               "ckl_compress / ckl_decompress with pinned HOST buffers (what fastcrackle.compress/decompress bind)" if world == 1 else
+                               "ShardedCodec.compress / decompress_shard with each rank's slab in pinned HOST memory (ckl_shard_* + ckl_decompress)"),
+                       "chunks": ("library default: 4 z-chunks on child contexts for host-resident volumes, so H2D / D2H copies of one chunk "
+                                  "overlap the kernels of the others" if args.chunks == 0 else args.chunks) if world == 1 else "one slab per rank"}
         del hvol, hout, hstream
 
-    if not args.no_cpu and world == 1 and rank == 0:
-        zs = min(args.cpu_slices, sz)
+    if not args.no_cpu and rank == 0:
+        zs = min(args.cpu_slices if sx * sy <= 1024 * 1024 else max(8, args.cpu_slices // 4), szl)
         sample = np.asfortranarray(vol[:zs].cpu().numpy().transpose(2, 1, 0))
-        tc, td, kind, cores = ref_times(sample, args.order, 2)
-        line["cpu_baseline"] = {"value": 2.0 * sample.size / (tc + td) / 1e9, "unit": "GVox/s", "cores": cores, "kind": kind,
-                                "sample": f"first {zs} z-slices ({sx}x{sy}x{zs}) of the same volume, all host threads",
-                                "compress_gvox_s": sample.size / tc / 1e9, "decompress_gvox_s": sample.size / td / 1e9}
+        ta, tb, kind, cores = ref_times(sample, args.order, 2, args.mode, label)
+        line["cpu_baseline"] = {"value": 2.0 * sample.size / (ta + tb) / 1e9, "unit": "GVox/s", "cores": cores, "kind": kind,
+                                "sample": f"first {zs} z-slices ({sx}x{sy}x{zs}) of rank 0's slab, all host threads",
+                                f"{names[0]}_gvox_s": sample.size / ta / 1e9, f"{names[1]}_gvox_s": sample.size / tb / 1e9}
     if rank == 0:
         if args.prof:
             sys.stderr.write(json.dumps(stage_ms, indent=1) + "\n")
         print(json.dumps(line), flush=True)
     if dist:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -5,6 +5,8 @@ import os as _os
 # the z-chunk pipeline uses up to 2 streams per chunk: give them their own hardware work queues (read at CUDA context creation)
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
-from .codec import Context, compress, decompress, decompress_range, default_context, header  # noqa: F401
+from .codec import (Context, compress, decompress, decompress_binary_image, decompress_range, default_context,  # noqa: F401
+                    header, z_range_for_label)
 
-__all__ = ["Context", "compress", "decompress", "decompress_range", "default_context", "header"]
+__all__ = ["Context", "compress", "decompress", "decompress_binary_image", "decompress_range", "default_context", "header",
+           "z_range_for_label"]

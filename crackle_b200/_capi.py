@@ -27,6 +27,15 @@ class ShardPieces(ctypes.Structure):
     _fields_ = [("keys_bytes", u64), ("codes_bytes", u64), ("sz_local", u64)]
 
 
+class ShardCounts(ctypes.Structure):
+    _fields_ = [(n, u64) for n in ("n_unique_local", "n_components", "n_codepoints", "codes_bytes_order0", "sz_local", "runs",
+                                   "keys_bytes", "codes_bytes")]
+
+
+class ShardBlock(ctypes.Structure):
+    _fields_ = [(n, u64) for n in ("offset", "sz_local", "n_components", "keys_bytes", "codes_bytes")]
+
+
 # every symbol include/crackle_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "crackle_b200_compress": (cint, [vp, cint, u64, u64, u64, cint, cint, ctypes.POINTER(vp), ctypes.POINTER(u64),
@@ -50,6 +59,10 @@ SYMBOLS = {
     "ckl_shard_finish": (cint, [vp, vp, cint, u64, vp, cint, ctypes.POINTER(ShardPieces)]),
     "ckl_shard_model": (cint, [vp, vp, cint, u64, ctypes.POINTER(u64)]),
     "ckl_shard_fetch": (cint, [vp, vp, vp, vp, vp, vp, cint]),
+    "ckl_shard_info": (cint, [vp, ctypes.POINTER(ShardCounts)]),
+    "ckl_shard_pack": (cint, [vp, vp, u64, ctypes.POINTER(u64)]),
+    "ckl_shard_assemble": (cint, [vp, vp, ctypes.POINTER(ShardBlock), cint, vp, cint, u64, cint, cint, cint, cint, cint, u64, u64,
+                                  ctypes.POINTER(u64)]),
     "ckl_prof_enable": (cint, [vp, cint]),
     "ckl_prof_read": (cint, [vp, ctypes.c_char_p, ctypes.c_size_t]),
     "ckl_launch_count": (u64, []),

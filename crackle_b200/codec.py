@@ -5,7 +5,8 @@ decompress_range :632-687) and src/fastcrackle.cpp (compress :163-210, decompres
 through the C-ABI (libcrackle_b200.so); numpy arrays / bytes in and out like the reference, plus torch CUDA tensors
 for device-resident volumes (the benchmark's `value` path)."""
 import ctypes
-from typing import Optional
+import threading
+from typing import Optional, Tuple
 
 import numpy as np
 
@@ -13,7 +14,12 @@ from . import _capi
 
 
 class Context:
-    """One per GPU: owns the CUDA stream and the reusable device workspace (ckl_ctx)."""
+    """One per GPU: owns the CUDA stream and the reusable device workspace (ckl_ctx).
+
+    A Context (like the ckl_ctx under it) is single-threaded: one call at a time.  The module-level compress /
+    decompress functions serialise on a lock around their shared default context; use one Context per thread for
+    concurrent callers.  torch CUDA tensors are ordered against torch's CURRENT stream: the context is bound to it for
+    the call (and stays on it), so producers and consumers of the tensor need no extra synchronisation."""
 
     def __init__(self, device: int = 0):
         self._h = ctypes.c_void_p()
@@ -43,14 +49,23 @@ class Context:
                 raise ValueError(msg)
             raise RuntimeError(msg)
 
+    def bind_torch_stream(self):
+        """run on torch's current CUDA stream of this device (what produced / will consume the caller's CUDA tensors)"""
+        import torch
+        sp = torch.cuda.current_stream(self.device).cuda_stream
+        if getattr(self, "_bound_stream", None) != sp:
+            self.set_stream(sp)
+
     # -- instrumentation -----------------------------------------------------------------------------------
     def set_stream(self, cuda_stream_ptr):
         """Run on a caller-owned stream, e.g. torch.cuda.current_stream().cuda_stream (0 = legacy default stream);
         None restores the context's own stream."""
         if cuda_stream_ptr is None:
             self._check(_capi.lib().ckl_ctx_own_stream(self._h))
+            self._bound_stream = None
         else:
             self._check(_capi.lib().ckl_ctx_set_stream(self._h, ctypes.c_void_p(int(cuda_stream_ptr))))
+            self._bound_stream = int(cuda_stream_ptr)
 
     def set_chunks(self, chunks: int = 0):
         """z-chunk pipelining of compress / decompress: 0 = automatic (large volumes), 1 = off, K = always K chunks.
@@ -99,6 +114,8 @@ class Context:
         ptr, on_dev, width, (sx, sy, sz), f_order, keep = _as_fortran_volume(labels)
         if fortran_order is not None:
             f_order = fortran_order
+        if on_dev:
+            self.bind_torch_stream()
         self.compress_ptr(ptr, on_dev, width, sx, sy, sz, f_order, markov_model_order)
         del keep
         return self.result_bytes()
@@ -124,9 +141,16 @@ def launch_count() -> int:
 
 
 _default: Optional[Context] = None
+_default_lock = threading.RLock()      # the module-level API shares one context: one call at a time (ctypes drops the GIL)
 
 
 def default_context() -> Context:
+    global _default
+    with _default_lock:
+        return _default_context_locked()
+
+
+def _default_context_locked() -> Context:
     global _default
     if _default is None:
         dev = 0
@@ -191,7 +215,8 @@ def compress(labels, allow_pins: int = 0, markov_model_order: int = 0, bgcolor: 
     if allow_pins:
         raise NotImplementedError("crackle_b200: pin label formats are outside the flat-label hot path; "
                                   "use the reference for allow_pins != 0")
-    return default_context().compress(labels, markov_model_order)
+    with _default_lock:
+        return default_context().compress(labels, markov_model_order)
 
 
 def decompress_range(binary, z_start: Optional[int], z_end: Optional[int], parallel: int = 0,
@@ -205,7 +230,8 @@ def decompress_range(binary, z_start: Optional[int], z_end: Optional[int], paral
     dtype = np.dtype(f"u{h['data_width']}")
     if sx * sy * sz == 0:
         return np.zeros((0,), dtype=dtype).reshape((sx, sy, max(z_end - z_start, 0)), order=order)
-    out = default_context().decompress(binary, z_start, z_end, label)
+    with _default_lock:
+        out = default_context().decompress(binary, z_start, z_end, label)
     szr = out.size // (sx * sy)
     out = out.reshape((sx, sy, szr), order=order)
     if label is not None:
@@ -215,6 +241,61 @@ def decompress_range(binary, z_start: Optional[int], z_end: Optional[int], paral
     return out
 
 
+def z_range_for_label(binary, label: int) -> Tuple[int, int]:
+    """crackle.codec.z_range_for_label_flat (codec.py:464-520): the z-range whose slices can contain `label`, from the
+    label table alone (no voxel work); (-1, -1) when the label does not occur."""
+    h = header(binary)
+    if h["label_format"] != 0:
+        raise ValueError("Label format not supported.")
+    buf = np.frombuffer(binary, dtype=np.uint8)
+    hb = 24 if h["format_version"] == 0 else 29
+    off = hb + 4 * (h["sz"] + (0 if h["format_version"] == 0 else 1))
+    lab = buf[off: off + h["num_label_bytes"]]
+    nu = int.from_bytes(lab[:8].tobytes(), "little")
+    sw = h["stored_data_width"]
+    uniq = np.frombuffer(lab, dtype=f"<u{sw}", count=nu, offset=8)
+    if label < 0 or label > np.iinfo(uniq.dtype).max:
+        return (-1, -1)
+    idx = int(np.searchsorted(uniq, np.asarray(label, dtype=uniq.dtype)))
+    if idx >= nu or int(uniq[idx]) != int(label):
+        return (-1, -1)
+    cw = 1 if h["sx"] * h["sy"] <= 0xFF else 2 if h["sx"] * h["sy"] <= 0xFFFF else 4 if h["sx"] * h["sy"] <= 0xFFFFFFFF else 8
+    o = 8 + nu * sw
+    per_grid = np.cumsum(np.frombuffer(lab, dtype=f"<u{cw}", count=h["sz"], offset=o))
+    kw = 1 if nu <= 0xFF else 2 if nu <= 0xFFFF else 4 if nu <= 0xFFFFFFFF else 8
+    o += cw * h["sz"]
+    keys = np.frombuffer(lab, dtype=f"<u{kw}", count=(len(lab) - o) // kw, offset=o)
+    hits = np.flatnonzero(keys == idx)                 # fastcrackle.index_range
+    if hits.size == 0:
+        return (-1, -1)
+    min_cc, max_cc = int(hits[0]), int(hits[-1])
+    z_start = int(np.searchsorted(per_grid, min_cc))
+    z_end = int(np.searchsorted(per_grid, max_cc))
+    if per_grid[z_start] == min_cc:
+        z_start = min(z_start + 1, h["sz"] - 1)
+    if per_grid[z_end] == max_cc:
+        z_end = min(z_end + 1, h["sz"] - 1)
+    return (z_start, z_end + 1)
+
+
+def decompress_binary_image(binary, label: int, parallel: int = 0, crop: bool = True) -> np.ndarray:
+    """crackle.codec.decompress_binary_image (codec.py:588-614): only the z-range that can hold `label` is decoded."""
+    z_start, z_end = z_range_for_label(binary, label)
+    h = header(binary)
+    order = "F" if h["fortran_order"] else "C"
+    if z_start == -1 and z_end == -1 and crop:
+        return np.zeros([0, 0, 0], dtype=bool, order=order)
+    if (z_start == 0 and z_end == h["sz"]) or crop:
+        return decompress_range(binary, z_start, z_end, parallel, label).view(bool)
+    image = np.zeros([h["sx"], h["sy"], h["sz"]], dtype=bool, order=order)
+    if z_start == -1 and z_end == -1:
+        return image
+    image[:, :, z_start:z_end] = decompress_range(binary, z_start, z_end, parallel, label)
+    return image
+
+
 def decompress(binary, label: Optional[int] = None, parallel: int = 0, crop: bool = False) -> np.ndarray:
     """crackle.decompress (codec.py:616-630)."""
-    return decompress_range(binary, None, None, parallel, label)
+    if label is None:
+        return decompress_range(binary, None, None, parallel)
+    return decompress_binary_image(binary, label, parallel, crop=crop)

@@ -30,7 +30,10 @@ struct ShardJob {
   int permissible = 0, stored_width = 0, order = 0;
   u64 runs = 0, ncomp = 0, nuniq_local = 0, ncp = 0;
   u64 keys_bytes = 0, codes_bytes = 0;
+  u64 codes_bytes0 = 0;            // order-0 code size of the shard, known at the end of the encode stage
   int key_width = 0;
+  const u64* guniq = nullptr;      // global sorted unique table (device) the keys are written against
+  u64 nuniq_global = 0;
   bool encoded = false, finished = false;
 };
 
@@ -363,9 +366,11 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   J.nuniq_local = labels_sort_unique(c->lb, J.ncomp, stored_width, st);
   c->prof.end(st);
   CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_join, 0));     // join: everything below sees the tracer's results
+  launch_code_sizes_order0(g, c->tr, c->scal, st);        // order-0 code offsets / total: final unless a markov model re-codes them
   read_scalars(c);
   if (c->hscal[SC_ERROR]) throw CklError(CKL_ERR_CUDA, "crackle_b200: internal tracer capacity error " + std::to_string(c->hscal[SC_ERROR]));
   J.ncp = c->hscal[SC_CODEPOINTS];
+  J.codes_bytes0 = c->hscal[SC_CODE_BYTES];
   if (order > 0) {
     const u64 rows = 1ull << (2 * order);
     c->mk.stats.ensure(rows * 16);
@@ -384,9 +389,18 @@ static void shard_finish_impl(ckl_ctx* c, const u64* guniq_dev, u64 nuniq_global
   J.order = order;
   J.key_width = ckl_byte_width(nuniq_global);
   J.keys_bytes = J.ncomp * (u64)J.key_width;
+  J.guniq = guniq_dev; J.nuniq_global = nuniq_global;
   if (materialise) {
     c->keys.ensure(J.keys_bytes + 8);
     launch_write_keys(c->lb.mapping.as<u64>(), J.ncomp, guniq_dev, nuniq_global, J.key_width, c->keys.as<u8>(), st);
+  }
+  if (order == 0) {                                      // sizes and offsets were scanned at the end of the encode stage
+    J.codes_bytes = J.codes_bytes0;
+    J.finished = true;
+    if (!materialise) return;
+    c->codes.ensure(J.codes_bytes + 8);
+    launch_pack_order0(g, c->tr, c->codes.as<u8>(), st);
+    return;
   }
   if (order > 0) {
     const u64 rows = 1ull << (2 * order);
@@ -455,12 +469,12 @@ extern "C" int ckl_shard_finish(ckl_ctx* c, const uint64_t* global_unique, int u
                                 const uint32_t* global_stats, int stats_on_device, ckl_shard_pieces* pieces) {
   API_BEGIN(c)
   if (!pieces) throw CklError(CKL_ERR_ARG, "crackle_b200: null pieces");
-  const u64* gu = global_unique;
-  if (!unique_on_device) {
-    c->lb.sorted.ensure(n_unique_global * 8 + 8);
-    CUDA_CHECK(cudaMemcpyAsync(c->lb.sorted.p, global_unique, n_unique_global * 8, cudaMemcpyHostToDevice, c->st));
-    gu = c->lb.sorted.as<u64>();
-  }
+  // the context keeps its own copy of the global table: ckl_shard_pack / ckl_shard_fetch write the keys against it later
+  c->lb.sorted.ensure(n_unique_global * 8 + 8);
+  if (n_unique_global)
+    CUDA_CHECK(cudaMemcpyAsync(c->lb.sorted.p, global_unique, n_unique_global * 8,
+                               unique_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->st));
+  const u64* gu = c->lb.sorted.as<u64>();
   int order = global_stats ? c->job.order : 0;
   const u32* gs = global_stats;
   if (order > 0 && !stats_on_device) {
@@ -511,6 +525,145 @@ extern "C" int ckl_shard_fetch(ckl_ctx* c, uint8_t* keys, uint64_t* components_p
   }
   CUDA_CHECK(cudaStreamSynchronize(c->st));
   if (components_per_slice) for (u32 z = 0; z < sz; z++) components_per_slice[z] = nz[z];
+  API_END(c)
+}
+
+extern "C" int ckl_shard_info(ckl_ctx* c, ckl_shard_counts* out) {
+  API_BEGIN(c)
+  if (!out) throw CklError(CKL_ERR_ARG, "crackle_b200: null output");
+  const ShardJob& J = c->job;
+  if (!J.encoded) throw CklError(CKL_ERR_ARG, "crackle_b200: ckl_shard_info without ckl_shard_encode");
+  out->n_unique_local = J.nuniq_local; out->n_components = J.ncomp; out->n_codepoints = J.ncp;
+  out->codes_bytes_order0 = J.codes_bytes0; out->sz_local = J.g.sz; out->runs = J.runs;
+  out->codes_bytes = J.finished ? J.codes_bytes : 0; out->keys_bytes = J.finished ? J.keys_bytes : 0;
+  API_END(c)
+}
+
+// block layout of ckl_shard_pack (offsets from the block start; every section starts 4-byte aligned when the block does):
+//   N_z u32[sz] | code sizes u32[sz] | slice crcs u32[sz] | keys[keys_bytes] | codes[codes_bytes]
+static u64 shard_block_bytes(const ShardJob& J) { return 12ull * J.g.sz + J.keys_bytes + J.codes_bytes; }
+
+extern "C" int ckl_shard_pack(ckl_ctx* c, uint8_t* dst, uint64_t capacity, uint64_t* bytes) {
+  API_BEGIN(c)
+  ShardJob& J = c->job;
+  if (!J.finished) throw CklError(CKL_ERR_ARG, "crackle_b200: ckl_shard_pack without ckl_shard_finish");
+  const u64 need = shard_block_bytes(J);
+  if (bytes) *bytes = need;
+  if (dst) {
+    if (capacity < need) throw CklError(CKL_ERR_ARG, "crackle_b200: pack buffer too small");
+    if ((u64)dst & 3) throw CklError(CKL_ERR_ARG, "crackle_b200: pack buffer must be 4-byte aligned");
+    const Geom& g = J.g;
+    cudaStream_t st = c->st;
+    u32* small = reinterpret_cast<u32*>(dst);
+    CUDA_CHECK(cudaMemcpyAsync(small, c->ccl.nz.p, 4ull * g.sz, cudaMemcpyDeviceToDevice, st));
+    k_gather_stride4<<<(g.sz + 255) / 256, 256, 0, st>>>(c->tr.sliceInfo.as<u32>(), g.sz, 3, small + g.sz);
+    LAUNCH_CHECK();
+    CUDA_CHECK(cudaMemcpyAsync(small + 2ull * g.sz, c->ccl.sliceCrc.p, 4ull * g.sz, cudaMemcpyDeviceToDevice, st));
+    u8* keys = dst + 12ull * g.sz;
+    launch_write_keys(c->lb.mapping.as<u64>(), J.ncomp, J.guniq, J.nuniq_global, J.key_width, keys, st);
+    u8* codes = keys + J.keys_bytes;
+    if (J.order > 0) launch_markov_copy(g, c->tr, c->mk, codes, st);
+    else launch_pack_order0(g, c->tr, codes, st);
+  }
+  API_END(c)
+}
+
+// small per-slice arrays of up to ASM_MAX_BLOCKS gathered blocks -> their place in the stream, one launch
+#define ASM_MAX_BLOCKS 16
+struct AsmParams {
+  const u32* src[ASM_MAX_BLOCKS];     // block start: N_z | code sizes | crcs
+  u32 sz[ASM_MAX_BLOCKS], z0[ASM_MAX_BLOCKS];
+  int n, cw;
+  u8 *dst_nz, *dst_z, *dst_crc;
+};
+__global__ void __launch_bounds__(256) k_assemble_small(AsmParams P) {
+  for (int b = blockIdx.y; b < P.n; b += gridDim.y) {
+    const u32 sz = P.sz[b];
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * sz; i += gridDim.x * blockDim.x) {
+      const u32 which = i / sz, z = i - which * sz;
+      const u32 v = P.src[b][i];
+      const u64 zz = (u64)P.z0[b] + z;
+      u8* d = which == 0 ? P.dst_nz + zz * (u64)P.cw : (which == 1 ? P.dst_z : P.dst_crc) + zz * 4;
+      const int w = which == 0 ? P.cw : 4;
+      for (int k = 0; k < w; k++) d[k] = (u8)(v >> (8 * k));
+    }
+  }
+}
+
+extern "C" int ckl_shard_assemble(ckl_ctx* c, const uint8_t* gathered, const ckl_shard_block* blocks, int n_blocks,
+                                  const uint64_t* global_unique, int unique_on_device, uint64_t nu, int data_width, int stored,
+                                  int permissible, int fortran_order, int order, uint64_t sx, uint64_t sy, uint64_t* out_bytes) {
+  API_BEGIN(c)
+  if (!gathered || !blocks || n_blocks <= 0) throw CklError(CKL_ERR_ARG, "crackle_b200: ckl_shard_assemble: no blocks");
+  if (order < 0 || order > 12) throw CklError(CKL_ERR_ARG, "crackle_b200: markov_model_order must be in [0, 12]");
+  cudaStream_t st = c->st;
+  u64 sz = 0, ncomp = 0, codes_bytes = 0;
+  for (int b = 0; b < n_blocks; b++) {
+    if (blocks[b].offset & 3) throw CklError(CKL_ERR_ARG, "crackle_b200: block offsets must be 4-byte aligned");
+    sz += blocks[b].sz_local; ncomp += blocks[b].n_components; codes_bytes += blocks[b].codes_bytes;
+  }
+  if (sz > 0xFFFFFFFFull) throw CklError(CKL_ERR_ARG, "crackle_b200: dimension exceeds uint32");
+  const u64 sxy = sx * sy;
+  const int kw = ckl_byte_width(nu), cw = ckl_byte_width(sxy);
+  const u64 labels_bytes = 8 + nu * (u64)stored + sz * (u64)cw + ncomp * (u64)kw;
+  const u64 off_z = 29, off_lab = off_z + 4ull * (sz + 1), off_model = off_lab + labels_bytes;
+  const u64 off_nz = off_lab + 8 + nu * (u64)stored, off_keys = off_nz + sz * (u64)cw;
+  const u64 off_codes = off_model + model_bytes_for(order);
+  const u64 off_crcs = off_codes + codes_bytes + 4;
+  const u64 total = off_crcs + 4ull * sz;
+  c->result.ensure(total + 16);
+  c->tmp32.ensure(64);
+  u8* R = c->result.as<u8>();
+  u8 hb[29];
+  header_bytes_v1(hb, data_width, stored, permissible, fortran_order, order, (u32)sx, (u32)sy, (u32)sz, labels_bytes);
+  CUDA_CHECK(cudaMemcpyAsync(R, hb, 29, cudaMemcpyHostToDevice, st));
+  u64 z0 = 0, kpos = off_keys, cpos = off_codes;
+  for (int b0 = 0; b0 < n_blocks; b0 += ASM_MAX_BLOCKS) {
+    AsmParams P{};
+    P.n = std::min(ASM_MAX_BLOCKS, n_blocks - b0); P.cw = cw;
+    P.dst_nz = R + off_nz; P.dst_z = R + off_z; P.dst_crc = R + off_crcs;
+    u32 maxsz = 1;
+    for (int i = 0; i < P.n; i++) {
+      const ckl_shard_block& B = blocks[b0 + i];
+      if (B.keys_bytes != B.n_components * (u64)kw) throw CklError(CKL_ERR_ARG, "crackle_b200: block key bytes do not match the global key width");
+      P.src[i] = reinterpret_cast<const u32*>(gathered + B.offset);
+      P.sz[i] = (u32)B.sz_local; P.z0[i] = (u32)z0;
+      maxsz = std::max(maxsz, (u32)B.sz_local);
+      const u8* keys = gathered + B.offset + 12ull * B.sz_local;
+      if (B.keys_bytes) CUDA_CHECK(cudaMemcpyAsync(R + kpos, keys, B.keys_bytes, cudaMemcpyDeviceToDevice, st));
+      if (B.codes_bytes) CUDA_CHECK(cudaMemcpyAsync(R + cpos, keys + B.keys_bytes, B.codes_bytes, cudaMemcpyDeviceToDevice, st));
+      z0 += B.sz_local; kpos += B.keys_bytes; cpos += B.codes_bytes;
+    }
+    k_assemble_small<<<dim3((3 * maxsz + 255) / 256, P.n), 256, 0, st>>>(P);
+    LAUNCH_CHECK();
+  }
+  // z-index crc (crackle.hpp:173-185), unique table, markov model, labels crc (crackle.hpp:187, 211)
+  u32* crc_tmp = c->tmp32.as<u32>();
+  launch_crc_bytes(R + off_z, 4ull * sz, c->dtab, c->htab, crc_tmp, st);
+  k_store_bytes_u32<<<1, 1, 0, st>>>(R + off_z + 4ull * sz, crc_tmp);
+  LAUNCH_CHECK();
+  u8 nub[8];
+  for (int i = 0; i < 8; i++) nub[i] = (u8)(nu >> (8 * i));
+  CUDA_CHECK(cudaMemcpyAsync(R + off_lab, nub, 8, cudaMemcpyHostToDevice, st));
+  if (nu) {
+    const u64* gu = global_unique;
+    if (!unique_on_device) {
+      c->lb.uniq.ensure(nu * 8 + 8);
+      CUDA_CHECK(cudaMemcpyAsync(c->lb.uniq.p, global_unique, nu * 8, cudaMemcpyHostToDevice, st));
+      gu = c->lb.uniq.as<u64>();
+    }
+    launch_write_uniq(gu, nu, stored, R + off_lab + 8, st);
+  }
+  if (order > 0) {
+    if (!c->job.finished || c->job.order != order) throw CklError(CKL_ERR_ARG, "crackle_b200: ckl_shard_assemble needs this context's ckl_shard_finish for the markov model");
+    CUDA_CHECK(cudaMemcpyAsync(R + off_model, c->mk.stored.p, model_bytes_for(order), cudaMemcpyDeviceToDevice, st));
+  }
+  launch_crc_bytes(R + off_lab, labels_bytes, c->dtab, c->htab, crc_tmp + 1, st);
+  k_store_bytes_u32<<<1, 1, 0, st>>>(R + off_codes + codes_bytes, crc_tmp + 1);
+  LAUNCH_CHECK();
+  c->result_bytes = total;                     // queued on the context's stream; ckl_result_copy / ckl_decompress order after it
+  if (out_bytes) *out_bytes = total;
+  c->job.active = false;
   API_END(c)
 }
 
@@ -942,6 +1095,9 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
       throw CklError(CKL_ERR_STREAM, "crackle: grid index crc32c did not match. stored: " + std::to_string(stored) + " computed: " + std::to_string(computed));
   }
   const int order = (int)h.markov_model_order;
+  // the header field holds 0..15; the encoders (this one and, in practice, the reference: 4^order rows of statistics) stop far
+  // below 13, where the model alone would be > 80 MB of stream and the 32-bit row arithmetic of the kernels ends
+  if (order > 12) throw CklError(CKL_ERR_UNSUPPORTED, "crackle_b200: markov_model_order " + std::to_string(order) + " is not supported (maximum 12)");
   const u64 mbytes = model_bytes_for(order);
   std::vector<u64> off((u64)sz + 1);
   off[0] = hbytes + zbytes + h.num_label_bytes + mbytes;

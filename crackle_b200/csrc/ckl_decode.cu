@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(32) k_decode_slices(Geom g, const u8* __restri
                                                        const u64* __restrict__ stackOff, ull* scal) {
   __shared__ u8 smodel[DECODE_SMEM_MODEL];
   const u32 z = blockIdx.x;
-  const u32 mbytes = order > 0 ? (4u << (2 * order)) : 0u;
+  const u64 mbytes = order > 0 ? (4ull << (2 * order)) : 0ull;      // order <= 12 (checked by the caller)
   const bool msm = order > 0 && mbytes <= DECODE_SMEM_MODEL;
   if (msm) {
     for (u32 i = threadIdx.x; i < mbytes; i += blockDim.x) smodel[i] = model[i];
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(32) k_dec_markov(const DecSlice* __restrict__ 
                                                     const u8* __restrict__ model, u32* __restrict__ fields, u32* __restrict__ ncpOut) {
   __shared__ u8 smodel[DECODE_SMEM_MODEL];
   const u32 z = blockIdx.x;
-  const u32 mbytes = 4u << (2 * order);
+  const u64 mbytes = 4ull << (2 * order);      // order <= 12 (checked by the caller)
   const bool msm = mbytes <= DECODE_SMEM_MODEL;
   if (msm) {
     for (u32 i = threadIdx.x; i < mbytes; i += blockDim.x) smodel[i] = model[i];

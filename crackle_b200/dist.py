@@ -5,11 +5,16 @@ never leaves its GPU; the only exchanges are the small global couplings of the s
 (the reference's own recipe for stitching independently compressed slabs is
 crackle/operations.py:258-295 `_zstack_flat_labels` and :424-548 `zstack`):
 
-  * max label -> stored width, pixel pairs -> crack format       (all_gather of a 64-byte summary)
-  * sorted unique label table                                     (all_gather of per-shard unique sets, merge+unique)
-  * markov statistics                                             (all_reduce SUM of uint32[4^order*4], wraps mod 2^32)
-  * N_z / code sizes / slice crcs                                 (all_gather of 3 small arrays)
-  * keys + crack codes -> one stream on rank 0                    (point-to-point send/recv straight into place)
+  * max label -> stored width, pixel pairs -> crack format, counts    (ONE all_gather of an 80-byte record, after the encode:
+                                                                       every shard encodes with the crack format its own
+                                                                       statistics suggest and re-encodes in the rare case the
+                                                                       global decision differs)
+  * sorted unique label table                                          (all_gather of per-shard unique sets, merge+unique on device)
+  * markov statistics                                                  (all_reduce SUM of uint32[4^order*4], wraps mod 2^32)
+  * N_z / code sizes / slice crcs / keys / crack codes                 (ONE padded all_gather of each shard's packed block)
+
+After the last all_gather every rank holds every piece and assembles the complete, header-consistent stream on its own
+GPU (ckl_shard_assemble: no host round trip, no rank-0 bottleneck, no broadcast before a sharded decompress).
 
 The per-shard compute is behind a small backend interface so the host logic can be exercised on CPU with gloo
 (tests/test_dist_cpu.py supplies an oracle-backed fake); the product backend is `CudaShardBackend` (C-ABI)."""
@@ -57,23 +62,31 @@ def model_bytes(order: int) -> int:  # header.hpp:284-297
 
 
 class CudaShardBackend:
-    """Per-GPU shard stages through the C-ABI (ckl_shard_*)."""
+    """Per-GPU shard stages through the C-ABI (ckl_shard_*).  The context is bound to torch's current CUDA stream so the
+    library's kernels, torch ops and the NCCL collectives are ordered by the stream, not by host synchronisation."""
 
     def __init__(self, ctx):
         self.ctx = ctx
         self.L = _capi.lib()
         self.device = torch.device("cuda", ctx.device)
+        ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _check(self, rc):
         self.ctx._check(rc)
 
     def begin(self, vol):
-        """vol: CUDA tensor (sz_local, sy, sx) of an unsigned dtype."""
+        """vol: CUDA tensor (sz_local, sy, sx) of an unsigned dtype, or a pinned / pageable HOST numpy array or tensor of that
+        shape (uploaded inside the call)."""
         s = _capi.ShardSummary()
-        sz, sy, sx = vol.shape
+        if isinstance(vol, np.ndarray):
+            sz, sy, sx = vol.shape
+            ptr, on_dev, width = vol.ctypes.data, 0, vol.dtype.itemsize
+        else:
+            sz, sy, sx = vol.shape
+            ptr, on_dev, width = vol.data_ptr(), int(vol.is_cuda), vol.element_size()
         self.shape = (sx, sy, sz)
-        self.width = vol.element_size()
-        self._check(self.L.ckl_shard_begin(self.ctx._h, vol.data_ptr(), 1, self.width, sx, sy, sz, ctypes.byref(s)))
+        self.width = width
+        self._check(self.L.ckl_shard_begin(self.ctx._h, ptr, on_dev, width, sx, sy, sz, ctypes.byref(s)))
         return dict(max_label=s.max_label, pairs=s.pairs, first_voxel=s.first_voxel, last_voxel=s.last_voxel, voxels=s.voxels)
 
     def encode(self, permissible, stored_width, order):
@@ -83,6 +96,11 @@ class CudaShardBackend:
                                             ctypes.byref(nc), ctypes.byref(ncp)))
         self.n_unique_local, self.ncomp = nu.value, nc.value
         return nu.value, nc.value, ncp.value
+
+    def info(self):
+        c = _capi.ShardCounts()
+        self._check(self.L.ckl_shard_info(self.ctx._h, ctypes.byref(c)))
+        return {n: getattr(c, n) for n, _ in _capi.ShardCounts._fields_}
 
     def unique(self):
         t = torch.empty(max(self.n_unique_local, 1), dtype=torch.int64, device=self.device)
@@ -107,6 +125,29 @@ class CudaShardBackend:
         self.pieces = p
         return dict(keys_bytes=p.keys_bytes, codes_bytes=p.codes_bytes, sz_local=p.sz_local)
 
+    def pack(self, buf):
+        """this shard's block (N_z | code sizes | crcs | keys | codes) into the uint8 CUDA tensor `buf`"""
+        n = ctypes.c_uint64()
+        self._check(self.L.ckl_shard_pack(self.ctx._h, buf.data_ptr(), buf.numel(), ctypes.byref(n)))
+        return n.value
+
+    def assemble(self, gathered, blocks, guniq, data_width, stored, permissible, fortran_order, order, sx, sy):
+        """complete stream from the gathered blocks, built on this rank's GPU; returns a zero-copy uint8 view of the
+        context-owned result buffer (valid until the context's next compress)."""
+        arr = (_capi.ShardBlock * len(blocks))()
+        for i, b in enumerate(blocks):
+            arr[i].offset, arr[i].sz_local, arr[i].n_components, arr[i].keys_bytes, arr[i].codes_bytes = b
+        n = ctypes.c_uint64()
+        self._check(self.L.ckl_shard_assemble(self.ctx._h, gathered.data_ptr(), arr, len(blocks), guniq.data_ptr(), 1, guniq.numel(),
+                                              int(data_width), int(stored), int(permissible), int(bool(fortran_order)), int(order),
+                                              sx, sy, ctypes.byref(n)))
+        return self.result_view()
+
+    def result_view(self):
+        p, n = self.ctx.result_device()
+        return torch.as_tensor(_DevBytes(p, n), device=self.device)
+
+    # pieces fetched separately (kept for callers that place them themselves)
     def small_pieces(self):
         """-> (components_per_slice u64[sz], code_sizes u32[sz], slice_crcs u32[sz]) as numpy"""
         sz = int(self.pieces.sz_local)
@@ -116,12 +157,6 @@ class CudaShardBackend:
         self._check(self.L.ckl_shard_fetch(self.ctx._h, None, nz.ctypes.data, cs.ctypes.data, cr.ctypes.data, None, 0))
         return nz, cs, cr
 
-    def big_pieces(self, keys_dst, codes_dst):
-        """copies keys / codes into the given uint8 CUDA tensors (views into the final stream on rank 0)"""
-        self._check(self.L.ckl_shard_fetch(self.ctx._h, keys_dst.data_ptr() if keys_dst is not None and keys_dst.numel() else None,
-                                           None, None, None,
-                                           codes_dst.data_ptr() if codes_dst is not None and codes_dst.numel() else None, 1))
-
     def stored_model(self):
         n = ctypes.c_uint64()
         self._check(self.L.ckl_shard_model(self.ctx._h, None, 0, 0, ctypes.byref(n)))
@@ -130,28 +165,35 @@ class CudaShardBackend:
             self._check(self.L.ckl_shard_model(self.ctx._h, buf.ctypes.data, 0, n.value, ctypes.byref(n)))
         return buf[: n.value].tobytes()
 
-    def crc32c(self, t):
-        out = ctypes.c_uint32()
-        self._check(self.L.ckl_crc32c(self.ctx._h, t.data_ptr(), 1, t.numel(), ctypes.byref(out)))
-        return out.value
-
     def empty_bytes(self, n):
         return torch.empty(n, dtype=torch.uint8, device=self.device)
 
-    def to_device(self, np_bytes):
-        return torch.from_numpy(np.frombuffer(np_bytes, dtype=np.uint8).copy()).to(self.device)
+
+class _DevBytes:
+    """zero-copy __cuda_array_interface__ wrapper of a device byte range"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def block_bytes(sz_local, keys_bytes, codes_bytes):
+    """size of one shard's packed block (layout of ckl_shard_pack)"""
+    return 12 * sz_local + keys_bytes + codes_bytes
 
 
 class ShardedCodec:
-    """compress(): every rank passes its z-slab; rank 0 gets the complete .ckl stream (uint8 tensor on the backend's
-    device), byte-identical to compressing the whole volume at once.  Other ranks get None."""
+    """compress(): every rank passes its z-slab and EVERY rank gets the complete .ckl stream (uint8 tensor on the
+    backend's device), byte-identical to compressing the whole volume at once."""
+
+    META = 10      # int64 fields per rank in the one metadata all_gather
 
     def __init__(self, ctx_or_backend, dist, backend=None):
         self.dist = dist
         self.be = backend if backend is not None else CudaShardBackend(ctx_or_backend)
         self.ctx = ctx_or_backend
-        self.rank = dist.get_rank()
-        self.world = dist.get_world_size()
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.collectives = 0
 
     # -- helpers ---------------------------------------------------------------------------------------------
     def _dev(self):
@@ -159,21 +201,25 @@ class ShardedCodec:
 
     def _all_gather_i64(self, vals):
         """fixed-size all_gather of a few int64 per rank: one collective into one tensor, one device->host copy"""
+        if self.world == 1:
+            return [np.array([int(v) for v in vals], dtype=np.int64).view(np.uint64)]
         t = torch.tensor(vals, dtype=torch.int64, device=self._dev())
         out = torch.empty(self.world * t.numel(), dtype=torch.int64, device=self._dev())
         self.dist.all_gather_into_tensor(out, t)
+        self.collectives += 1
         a = out.cpu().numpy().view(np.uint64).reshape(self.world, t.numel())
         return [a[r] for r in range(self.world)]
 
-    def _all_gather_var(self, t, counts, to_host=False):
-        """all_gather of 1-D tensors of different lengths (padded to the max); to_host: numpy views of ONE host copy."""
+    def _all_gather_var(self, t, counts):
+        """all_gather of 1-D tensors of different lengths (padded to the max) -> list of device views"""
+        if self.world == 1:
+            return [t]
         m = max(max(counts), 1)
-        pad = torch.zeros(m, dtype=t.dtype, device=self._dev())
+        pad = torch.empty(m, dtype=t.dtype, device=self._dev())
         pad[: t.numel()] = t
         out = torch.empty(self.world * m, dtype=t.dtype, device=self._dev())
         self.dist.all_gather_into_tensor(out, pad)
-        if to_host:
-            out = out.cpu().numpy()
+        self.collectives += 1
         return [out[r * m: r * m + c] for r, c in enumerate(counts)]
 
     # -- compress --------------------------------------------------------------------------------------------
@@ -187,112 +233,98 @@ class ShardedCodec:
         self._marks.append((name, (t - self._t0) * 1e3))
         self._t0 = t
 
+    def _meta(self, s, sz_local):
+        be = self.be
+        info = be.info()
+        return [_i64(s["max_label"]), _i64(s["pairs"]), _i64(s["first_voxel"]), _i64(s["last_voxel"]), _i64(s["voxels"]), sz_local,
+                info["n_unique_local"], info["n_components"], info["n_codepoints"], info["codes_bytes_order0"]]
+
     def compress(self, vol, z0, sz_total, markov_model_order=0, fortran_order=True):
         be, dist, W, R = self.be, self.dist, self.world, self.rank
         self._prof = os.environ.get("CKL_DIST_PROF") == "1"
         self._marks, self._t0 = [], time.perf_counter()
         s = be.begin(vol)
-        self._mark("begin")
         sx, sy, sz_local = be.shape
         data_width = be.width
-        # (1) global scalars from the per-shard summaries
-        summ = self._all_gather_i64([_i64(s["max_label"]), _i64(s["pairs"]), _i64(s["first_voxel"]), _i64(s["last_voxel"]),
-                                     _i64(s["voxels"]), sz_local])
-        max_label = max(int(a[0]) for a in summ)
-        pairs = sum(int(a[1]) for a in summ)
-        for r in range(1, W):                      # the flat-index pair straddling each shard boundary (lib.hpp:249-256)
-            pairs += int(summ[r][2] == summ[r - 1][3])
-        voxels = sum(int(a[4]) for a in summ)
-        sz_all = [int(a[5]) for a in summ]
-        assert sum(sz_all) == sz_total, "shards do not cover the volume"
-        permissible = pairs < voxels // 2          # crackle.hpp:50-55
-        stored = byte_width(max_label)             # crackle.hpp:233-235
-        self._mark("summaries")
-        # (2) per-shard encode
-        nu_local, ncomp_local, ncp_local = be.encode(permissible, stored, markov_model_order)
-        self._mark("encode")
-        cnt = self._all_gather_i64([nu_local, ncomp_local, ncp_local])
-        nu_all = [int(c[0]) for c in cnt]
-        ncomp_all = [int(c[1]) for c in cnt]
+        # (1) encode with the crack format this shard's own statistics suggest (crackle.hpp:50-55); the global decision
+        # is checked right after the one metadata exchange
+        guess = int(s["pairs"]) < int(s["voxels"]) // 2
+        be.encode(guess, byte_width(int(s["max_label"])), markov_model_order)
+        self._mark("begin+encode")
+        redone = False
+        while True:
+            meta = self._all_gather_i64(self._meta(s, sz_local))
+            max_label = max(int(a[0]) for a in meta)
+            pairs = sum(int(a[1]) for a in meta)
+            for r in range(1, W):                  # the flat-index pair straddling each shard boundary (lib.hpp:249-256)
+                pairs += int(meta[r][2] == meta[r - 1][3])
+            voxels = sum(int(a[4]) for a in meta)
+            sz_all = [int(a[5]) for a in meta]
+            assert sum(sz_all) == sz_total, "shards do not cover the volume"
+            permissible = pairs < voxels // 2          # crackle.hpp:50-55
+            stored = byte_width(max_label)             # crackle.hpp:233-235
+            wrong = [r for r in range(W) if (int(meta[r][1]) < int(meta[r][4]) // 2) != permissible]
+            if not wrong or redone:
+                break
+            if R in wrong:                             # rare: this shard's guess differs from the global decision
+                s = be.begin(vol)
+                be.encode(permissible, stored, markov_model_order)
+            redone = True
+        nu_all = [int(a[6]) for a in meta]
+        ncomp_all = [int(a[7]) for a in meta]
         order = markov_model_order
-        if order > 0 and sum(int(c[2]) for c in cnt) == 0:
+        if order > 0 and sum(int(a[8]) for a in meta) == 0:
             order = 0                              # crackle.hpp:107-118
-        # (3) global sorted unique label table: identical merge on every rank
+        self._mark("meta")
+        # (2) global sorted unique label table: identical merge on every rank
         parts = self._all_gather_var(be.unique(), nu_all)
         guniq = be.sort_unique(torch.cat(parts) if W > 1 else parts[0].clone(), stored)
         nu = int(guniq.numel())
         self._mark("unique_merge")
-        # (4) global markov statistics
+        # (3) global markov statistics
         gstats = None
         if order > 0:
             gstats = be.stats().clone()
-            dist.all_reduce(gstats, op=dist.ReduceOp.SUM)     # int32 two's complement add == uint32 wrap (markov.hpp:210-213)
-        # (5) per-shard pieces against the global table / model
+            if W > 1:
+                dist.all_reduce(gstats, op=dist.ReduceOp.SUM)     # int32 two's complement add == uint32 wrap (markov.hpp:210-213)
+                self.collectives += 1
+        # (4) per-shard pieces against the global table / model
         pc = be.finish(guniq, gstats)
-        self._mark("finish")
-        nz, code_sizes, crcs = be.small_pieces()
-        sizes = self._all_gather_i64([pc["keys_bytes"], pc["codes_bytes"]])
-        keys_all = [int(a[0]) for a in sizes]
-        codes_all = [int(a[1]) for a in sizes]
-        small = torch.from_numpy(np.concatenate([nz.view(np.int64), code_sizes.astype(np.int64), crcs.astype(np.int64)])).to(self._dev())
-        smalls = self._all_gather_var(small, [3 * z for z in sz_all], to_host=True)
-        self._mark("small_gathers")
-        # (6) gather keys and codes on rank 0 straight into their place in the stream
-        kw, cw = byte_width(nu), byte_width(sx * sy)
-        labels_bytes = 8 + nu * stored + sz_total * cw + sum(keys_all)
-        off_lab = 29 + 4 * (sz_total + 1)
-        off_keys = off_lab + 8 + nu * stored + sz_total * cw
-        off_model = off_lab + labels_bytes
-        off_codes = off_model + model_bytes(order)
-        total = off_codes + sum(codes_all) + 4 + 4 * sz_total
-        if R == 0:
-            final = be.empty_bytes(total)
-            kpos, cpos = off_keys, off_codes
-            be.big_pieces(final[kpos:kpos + keys_all[0]], final[cpos:cpos + codes_all[0]])
-            kpos += keys_all[0]
-            cpos += codes_all[0]
-            for r in range(1, W):
-                if keys_all[r]:
-                    dist.recv(final[kpos:kpos + keys_all[r]], src=r)
-                if codes_all[r]:
-                    dist.recv(final[cpos:cpos + codes_all[r]], src=r)
-                kpos += keys_all[r]
-                cpos += codes_all[r]
-        else:
-            kt, ct = be.empty_bytes(max(keys_all[R], 1)), be.empty_bytes(max(codes_all[R], 1))
-            be.big_pieces(kt[: keys_all[R]], ct[: codes_all[R]])
-            if keys_all[R]:
-                dist.send(kt[: keys_all[R]], dst=0)
-            if codes_all[R]:
-                dist.send(ct[: codes_all[R]], dst=0)
-            return None
-        self._mark("keys_codes_gather")
-        # (7) rank 0: the small sections (crackle.hpp:171-216, labels.hpp:123-152)
-        sm_np = smalls
-        nz_g = np.concatenate([p[: z].view(np.uint64) for p, z in zip(sm_np, sz_all)])
-        cs_g = np.concatenate([p[z: 2 * z].astype(np.uint32) for p, z in zip(sm_np, sz_all)])
-        cr_g = np.concatenate([p[2 * z: 3 * z].astype(np.uint32) for p, z in zip(sm_np, sz_all)])
-        zidx = cs_g.astype("<u4").tobytes()
-        uniq_np = guniq.cpu().numpy().view(np.uint64)
-        head = header_bytes(data_width, stored, int(permissible), fortran_order, order, sx, sy, sz_total, labels_bytes)
-        zcrc = be.crc32c(be.to_device(zidx))
-        front = (head + zidx + int(zcrc).to_bytes(4, "little") + int(nu).to_bytes(8, "little") +
-                 uniq_np.astype(f"<u{stored}").tobytes() + nz_g.astype(f"<u{cw}").tobytes())
-        assert len(front) == off_keys
-        final[:off_keys] = be.to_device(front)
+        kw = byte_width(nu)
+        keys_all = [n * kw for n in ncomp_all]
         if order > 0:
-            final[off_model:off_codes] = be.to_device(be.stored_model())
-        lcrc = be.crc32c(final[off_lab:off_model])
-        tail = int(lcrc).to_bytes(4, "little") + cr_g.astype("<u4").tobytes()
-        final[total - len(tail):] = be.to_device(tail)
+            codes_all = [int(a[0]) for a in self._all_gather_i64([pc["codes_bytes"]])]
+        else:
+            codes_all = [int(a[9]) for a in meta]
+        assert pc["keys_bytes"] == keys_all[R] and pc["codes_bytes"] == codes_all[R]
+        self._mark("finish")
+        # (5) ONE padded all_gather of the packed blocks; every rank then holds every piece
+        sizes = [block_bytes(z, k, c) for z, k, c in zip(sz_all, keys_all, codes_all)]
+        P = (max(sizes) + 15) // 16 * 16
+        if W > 1:
+            gathered = be.empty_bytes(W * P)
+            mine = be.empty_bytes(P)
+            be.pack(mine)
+            dist.all_gather_into_tensor(gathered, mine)
+            self.collectives += 1
+        else:
+            gathered = be.empty_bytes(P)
+            be.pack(gathered)
+        self._mark("gather")
+        # (6) the complete stream, assembled on this rank's device (crackle.hpp:171-216, labels.hpp:123-152)
+        blocks = [(r * P, sz_all[r], ncomp_all[r], keys_all[r], codes_all[r]) for r in range(W)]
+        final = be.assemble(gathered, blocks, guniq, data_width, stored, int(permissible), fortran_order, order, sx, sy)
         self._mark("assemble")
-        if self._prof:
+        if self._prof and R == 0:
             print("CKL_DIST_PROF " + " ".join(f"{k}={v:.2f}" for k, v in self._marks), flush=True)
         return final
 
     # -- decompress ------------------------------------------------------------------------------------------
     def broadcast_stream(self, stream):
-        """rank 0's stream -> every rank (uint8 tensor on the backend's device)."""
+        """kept for callers that hold the stream on rank 0 only (e.g. read from storage): rank 0's stream -> every rank.
+        compress() already leaves the stream on every rank, so a compress -> decompress pipeline does not need it."""
+        if self.world == 1:
+            return stream
         n = torch.tensor([stream.numel() if self.rank == 0 else 0], dtype=torch.int64, device=self._dev())
         self.dist.broadcast(n, src=0)
         if self.rank != 0:
@@ -301,6 +333,10 @@ class ShardedCodec:
         return stream
 
     def decompress_shard(self, stream, z_start, z_end, out, label=None):
-        """every rank decodes its own z-range of the (replicated) stream into its own output shard; no collective."""
-        self.ctx.decompress_into(stream.data_ptr(), 1, stream.numel(), z_start, z_end, label, out.data_ptr(), 1,
-                                 out.numel() * out.element_size())
+        """every rank decodes its own z-range of the (replicated) stream into its own output shard; no collective.
+        out: CUDA tensor, or a HOST numpy array / tensor (downloaded inside the call)."""
+        if isinstance(out, np.ndarray):
+            optr, on_dev, nbytes = out.ctypes.data, 0, out.nbytes
+        else:
+            optr, on_dev, nbytes = out.data_ptr(), int(out.is_cuda), out.numel() * out.element_size()
+        self.ctx.decompress_into(stream.data_ptr(), 1, stream.numel(), z_start, z_end, label, optr, on_dev, nbytes)

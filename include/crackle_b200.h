@@ -135,6 +135,34 @@ CKL_API int ckl_shard_model(ckl_ctx* ctx, uint8_t* dst, int dst_on_device, uint6
 CKL_API int ckl_shard_fetch(ckl_ctx* ctx, uint8_t* keys, uint64_t* components_per_slice, uint32_t* code_sizes,
                     uint32_t* slice_crcs, uint8_t* codes, int dst_on_device);
 
+/* Local counts of the shard after ckl_shard_encode (codes_bytes / keys_bytes are valid after ckl_shard_finish;
+ * codes_bytes_order0 is the order-0 code size, known right after the encode stage). */
+typedef struct ckl_shard_counts {
+  uint64_t n_unique_local, n_components, n_codepoints, codes_bytes_order0;
+  uint64_t sz_local, runs, keys_bytes, codes_bytes;
+} ckl_shard_counts;
+CKL_API int ckl_shard_info(ckl_ctx* ctx, ckl_shard_counts* out);
+
+/* One-collective exchange: ckl_shard_pack writes ALL of this shard's pieces into one 4-byte-aligned DEVICE buffer
+ *     N_z u32[sz_local] | code sizes u32[sz_local] | slice crcs u32[sz_local] | keys[keys_bytes] | codes[codes_bytes]
+ * (dst == NULL: only *bytes is returned) so the ranks can exchange them with a single padded all-gather
+ * (torch.distributed.all_gather_into_tensor over NCCL).  ckl_shard_assemble then builds the complete .ckl stream
+ * -- header, z index + crc, label table, N_z, keys, markov model, crack codes, labels crc, slice crcs
+ * (src/crackle.hpp:171-216, src/labels.hpp:123-152) -- on the device from the gathered blocks, on every rank
+ * alike, without a host round trip; the result is fetched with ckl_result_copy / ckl_result_device.  This is the
+ * device-side equivalent of operations.zstack for slabs encoded against one global label table
+ * (crackle/operations.py:424-548).  For markov_model_order > 0 the stored model is the one this context built in
+ * ckl_shard_finish from the global statistics. */
+typedef struct ckl_shard_block {
+  uint64_t offset;           /* byte offset of the rank's block inside the gathered buffer (multiple of 4) */
+  uint64_t sz_local, n_components, keys_bytes, codes_bytes;
+} ckl_shard_block;
+CKL_API int ckl_shard_pack(ckl_ctx* ctx, uint8_t* dst_device, uint64_t capacity, uint64_t* bytes);
+CKL_API int ckl_shard_assemble(ckl_ctx* ctx, const uint8_t* gathered_device, const ckl_shard_block* blocks, int n_blocks,
+                       const uint64_t* global_unique, int unique_on_device, uint64_t n_unique_global,
+                       int data_width, int stored_width, int permissible, int fortran_order, int markov_model_order,
+                       uint64_t sx, uint64_t sy, uint64_t* out_bytes);
+
 /* ---- instrumentation and small device utilities ---------------------------------------------------------- */
 /* Per-stage CUDA-event timing on the context's stream.  ckl_prof_read formats "stage=ms_total:calls;..." */
 CKL_API int ckl_prof_enable(ckl_ctx* ctx, int on);

@@ -1,5 +1,6 @@
 """multi-GPU parity check (run under torchrun): z-sharded compress == single-GPU compress of the whole volume,
-orders 0 and 5; every rank decodes its own z-range of the broadcast stream."""
+orders 0 and 5, checked on EVERY rank (each holds the complete stream after the one padded all-gather); every rank then
+decodes its own z-range of its own copy."""
 import os
 import sys
 
@@ -19,8 +20,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = cb.Context(local)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     job = ShardedCodec(ctx, dist)
+    mono = cb.Context(local)
     ok = True
     for shape, cell, dt, bits in (((256, 192, 8 * world + 3), 20, np.uint64, 40), ((130, 97, 2 * world), 12, np.uint16, 15)):
         sx, sy, szt = shape
@@ -28,11 +29,12 @@ def main():
         z0 = rank * per
         z1 = szt if rank == world - 1 else z0 + per
         vol = synth.jittered_voronoi_torch((sx, sy, z1 - z0), cell, dt, seed=1, id_bits=bits, z0=z0, sz_total=szt)
-        whole = synth.jittered_voronoi_torch(shape, cell, dt, seed=1, id_bits=bits) if rank == 0 else None
+        whole = synth.jittered_voronoi_torch(shape, cell, dt, seed=1, id_bits=bits)
+        torch.cuda.synchronize()
         for order in (0, 5):
             s = job.compress(vol, z0, szt, order)
-            if rank == 0:
-                want = ctx.compress(whole, order)
+            if True:
+                want = mono.compress(whole, order)
                 got = bytes(s.cpu().numpy().tobytes())
                 same = got == want
                 print(f"shape {shape} {np.dtype(dt).name} order {order}: sharded == monolithic: {same} ({len(got)} bytes)", flush=True)
@@ -49,7 +51,6 @@ def main():
                             else:
                                 i = next((j for j in range(min(len(sg[k]), len(sw[k]))) if sg[k][j] != sw[k][j]), -1)
                                 print(f"  section {k}: len {len(sg[k])} vs {len(sw[k])}, first diff at {i}: {bytes(sg[k][i:i+16]).hex()} vs {bytes(sw[k][i:i+16]).hex()}", flush=True)
-            s = job.broadcast_stream(s)
             out = torch.empty_like(vol)
             try:
                 job.decompress_shard(s, z0, z1, out)

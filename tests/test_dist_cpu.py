@@ -57,28 +57,42 @@ class OracleShardBackend:
         self.codes = b"".join(self.sec["codes"])
         return dict(keys_bytes=len(self.keys), codes_bytes=len(self.codes), sz_local=self.shape[2])
 
-    def small_pieces(self):
-        cs = np.array([len(c) for c in self.sec["codes"]], dtype=np.uint32)
-        cr = np.frombuffer(self.sec["slice_crcs"], dtype="<u4").astype(np.uint32)
-        return self.nz.copy(), cs, cr
+    def info(self):
+        cs = sum(len(c) for c in self.sec["codes"])
+        return dict(n_unique_local=len(self.uniq), n_components=len(self.mapping), n_codepoints=cs, codes_bytes_order0=cs,
+                    sz_local=self.shape[2], runs=0, keys_bytes=0, codes_bytes=0)
 
-    def big_pieces(self, keys_dst, codes_dst):
-        if keys_dst is not None and keys_dst.numel():
-            keys_dst.copy_(torch.from_numpy(np.frombuffer(self.keys, dtype=np.uint8).copy()))
-        if codes_dst is not None and codes_dst.numel():
-            codes_dst.copy_(torch.from_numpy(np.frombuffer(self.codes, dtype=np.uint8).copy()))
+    def pack(self, buf):
+        """layout of ckl_shard_pack: N_z u32[sz] | code sizes u32[sz] | crcs u32[sz] | keys | codes"""
+        cs = np.array([len(c) for c in self.sec["codes"]], dtype="<u4")
+        cr = np.frombuffer(self.sec["slice_crcs"], dtype="<u4")
+        blob = self.nz.astype("<u4").tobytes() + cs.tobytes() + cr.tobytes() + self.keys + self.codes
+        buf[: len(blob)] = torch.from_numpy(np.frombuffer(blob, dtype=np.uint8).copy())
+        return len(blob)
 
-    def stored_model(self):
-        return b""
-
-    def crc32c(self, t):
-        return O.crc32c(t.numpy().tobytes())
+    def assemble(self, gathered, blocks, guniq, data_width, stored, permissible, fortran_order, order, sx, sy):
+        """numpy restatement of ckl_shard_assemble (crackle.hpp:171-216, labels.hpp:123-152)"""
+        from crackle_b200.dist import header_bytes, byte_width
+        G = gathered.numpy().tobytes()
+        nz, cs, cr, keys, codes = b"", b"", b"", b"", b""
+        cw = byte_width(sx * sy)
+        sz = 0
+        for off, szl, ncomp, kb, cb in blocks:
+            small = np.frombuffer(G[off:off + 12 * szl], dtype="<u4")
+            nz += small[:szl].astype(f"<u{cw}").tobytes()
+            cs += small[szl:2 * szl].tobytes()
+            cr += small[2 * szl:].tobytes()
+            keys += G[off + 12 * szl: off + 12 * szl + kb]
+            codes += G[off + 12 * szl + kb: off + 12 * szl + kb + cb]
+            sz += szl
+        g = guniq.numpy().view(np.uint64)
+        labels = len(g).to_bytes(8, "little") + g.astype(f"<u{stored}").tobytes() + nz + keys
+        head = header_bytes(data_width, stored, permissible, fortran_order, order, sx, sy, sz, len(labels))
+        out = (head + cs + O.crc32c(cs).to_bytes(4, "little") + labels + codes + O.crc32c(labels).to_bytes(4, "little") + cr)
+        return torch.from_numpy(np.frombuffer(out, dtype=np.uint8).copy())
 
     def empty_bytes(self, n):
         return torch.zeros(n, dtype=torch.uint8)
-
-    def to_device(self, b):
-        return torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy())
 
 
 def _volume(kind):
@@ -103,10 +117,7 @@ def _worker(rank, world, port, kind, split, q):
         z0, z1 = bounds[rank], bounds[rank + 1]
         codec = ShardedCodec(None, dist, backend=OracleShardBackend())
         out = codec.compress(np.asfortranarray(vol[:, :, z0:z1]), z0, vol.shape[2], 0)
-        if rank == 0:
-            q.put(bytes(out.numpy().tobytes()))
-        stream = codec.broadcast_stream(out)
-        assert stream.numel() > 29
+        q.put((rank, bytes(out.numpy().tobytes()), codec.collectives))      # EVERY rank holds the complete stream
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -128,11 +139,15 @@ def test_two_rank_sharded_compress_is_byte_identical(kind, split):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, kind, split, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=120)
+    got = [q.get(timeout=120) for _ in range(2)]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert got == O.compress(_volume(kind), 0)
+    want = O.compress(_volume(kind), 0)
+    assert sorted(r for r, _, _ in got) == [0, 1]
+    for _, stream, ncoll in got:
+        assert stream == want
+        assert ncoll == 3            # metadata, unique tables, packed blocks: no per-peer send/recv, no broadcast
 
 
 def test_header_helper_matches_oracle():

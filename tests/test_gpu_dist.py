@@ -90,16 +90,30 @@ class ThreadGroup:
         return V()
 
 
+def _mixed_volume(shape, world):
+    """rank 0's slab is 60 % noise (its own statistics say PERMISSIBLE), the rest is blocky: the global decision is
+    IMPERMISSIBLE, so rank 0 must re-encode after the metadata exchange"""
+    sx, sy, sz = shape
+    g = torch.Generator().manual_seed(5)
+    vol = (torch.arange(sz)[:, None, None] // 2 * 7 + torch.arange(sy)[None, :, None] // 16 * 3 + torch.arange(sx)[None, None, :] // 16 + 1)
+    vol = vol.to(torch.int64).contiguous()
+    per = sz // world
+    noise = torch.randint(1, 1 << 30, (per, sy, sx), generator=g, dtype=torch.int64)
+    m = torch.rand((per, sy, sx), generator=g) < 0.6
+    vol[:per][m] = noise[m]
+    return vol.view(torch.uint64).cuda()
+
+
 @pytest.mark.parametrize("order", [0, 5])
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_equals_monolithic_threads(order, world):
+@pytest.mark.parametrize("world,kind", [(2, "voronoi"), (3, "voronoi"), (2, "mixed"), (3, "mixed")])
+def test_sharded_equals_monolithic_threads(order, world, kind):
     import crackle_b200 as cb
     from crackle_b200 import synth
     from crackle_b200.dist import ShardedCodec
     from oracle import oracle as O
     shape = (160, 128, 4 * world + 1)
     szt = shape[2]
-    whole = synth.jittered_voronoi_torch(shape, 14, np.uint64, seed=8, id_bits=40)
+    whole = synth.jittered_voronoi_torch(shape, 14, np.uint64, seed=8, id_bits=40) if kind == "voronoi" else _mixed_volume(shape, world)
     want = cb.default_context().compress(whole, order)
     assert want == O.compress(np.asfortranarray(whole.cpu().numpy().transpose(2, 1, 0)), order)
     group = ThreadGroup(world)
@@ -108,16 +122,14 @@ def test_sharded_equals_monolithic_threads(order, world):
     def run(rank):
         try:
             ctx = cb.Context(0)
-            ctx.set_stream(0)
             per = szt // world
             z0 = rank * per
             z1 = szt if rank == world - 1 else z0 + per
             vol = whole[z0:z1].contiguous()
             job = ShardedCodec(ctx, group.view(rank))
             s = job.compress(vol, z0, szt, order)
-            if rank == 0:
-                results["stream"] = bytes(s.cpu().numpy().tobytes())
-            s = job.broadcast_stream(s)
+            results["stream", rank] = bytes(s.cpu().numpy().tobytes())     # every rank holds the complete stream
+            results["collectives", rank] = job.collectives
             out = torch.empty_like(vol)
             job.decompress_shard(s, z0, z1, out)
             torch.cuda.synchronize()
@@ -135,7 +147,10 @@ def test_sharded_equals_monolithic_threads(order, world):
     for t in ts:
         t.join(timeout=180)
     assert not errors, errors
-    assert results["stream"] == want
+    for r in range(world):
+        assert results["stream", r] == want
+        # metadata (+1 when a shard re-encodes), unique tables, packed blocks; order > 0 adds statistics + code sizes
+        assert results["collectives", r] == 3 + (kind == "mixed") + 2 * (order > 0)
     assert all(results[r] for r in range(world))
 
 

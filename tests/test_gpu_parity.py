@@ -291,3 +291,93 @@ def test_config3_slab_1024x1024_u64_bytes_vs_oracle(ctx):
     v = np.asfortranarray(t.cpu().numpy().transpose(2, 1, 0))
     for order in (0, 5):
         assert ctx.compress(t, order) == O.compress(v, order)
+
+
+@pytest.mark.parametrize("order", [0, 5])
+def test_config2_and_config4_full_size_bytes_vs_compiled_reference(ctx, order):
+    # BASELINE.json configs[1] / configs[3] at FULL size: the 512^3 uint64 stream is byte-identical to the stream of the
+    # unmodified reference compiled on this box (oracle/_ref, parallel=0 = all host threads); the order-5 model depends on
+    # the statistics of the whole volume, so no slab test can stand in for this one.
+    from oracle import oracle as O
+    from crackle_b200 import synth
+    ref = O.ref_module()
+    if ref is None:
+        pytest.skip("oracle/_ref (compiled reference) is not present on this box")
+    t = synth.jittered_voronoi_torch((512, 512, 512), 24, np.uint64, seed=0, id_bits=40)
+    v = np.asfortranarray(t.cpu().numpy().transpose(2, 1, 0))
+    got = ctx.compress(t, order)
+    want = bytes(ref.compress(v, False, True, order, False, True, 0, 0))
+    assert len(got) == len(want)
+    assert got == want
+
+
+def _craft_long_escape_run(stream, z=0, pairs=20):
+    """Stream surgery: slice z's first chain gets `pairs` x (UP, DOWN) = 'b' followed by `pairs` x (DOWN, UP) = 't' in front
+    of its moves -- branches that are pushed and popped without a move, so the cracks (and every crc) stay the same, but
+    the code now holds a run of opposite moves far longer than a 16-codepoint word, which the encoders never produce."""
+    from oracle import oracle as O
+    sec, h = O.sections(stream), O.header(stream)
+    assert h["order"] == 0
+    code = sec["codes"][z]
+    isz = 4 + int.from_bytes(code[:4], "little")
+    boc, body = code[:isz], np.frombuffer(code[isz:], dtype=np.uint8)
+    bits = np.unpackbits(body, bitorder="little").reshape(-1, 2)
+    moves = np.cumsum(bits[:, 0] + 2 * bits[:, 1]) % 4
+    new = np.concatenate([np.array([0, 2] * pairs + [2, 0] * pairs), moves])
+    diffs = (np.diff(np.concatenate([[0], new]).astype(np.int64)) % 4).astype(np.uint8)
+    nb = np.stack([diffs & 1, diffs >> 1], 1).astype(np.uint8).reshape(-1)
+    codes = list(sec["codes"])
+    codes[z] = boc + np.packbits(nb, bitorder="little").tobytes()
+    zi = np.array([len(c) for c in codes], dtype="<u4").tobytes()
+    return (sec["header"] + zi + O.crc32c(zi).to_bytes(4, "little") + sec["labels"] + sec["model"] + b"".join(codes) +
+            sec["labels_crc"] + sec["slice_crcs"])
+
+
+def test_crafted_stream_takes_the_serial_decoder(ctx):
+    # a valid stream no encoder emits: an opposite-move run longer than a word makes the scan-parallel decoder hand the
+    # call to the serial per-slice decoder (k_decode_slices); result identical to the oracle's and the reference's decode
+    from oracle import oracle as O
+    from crackle_b200 import synth
+    import crackle_b200 as cb
+    v = synth.jittered_voronoi((96, 80, 3), 16, np.uint32, seed=2, id_bits=20)
+    b = O.compress(v, 0)
+    for z in (0, 2):
+        crafted = _craft_long_escape_run(b, z)
+        assert crafted != b and len(crafted) == len(b) + 20
+        assert np.array_equal(O.decompress(crafted), v)
+        if O.ref_module() is not None:
+            assert np.array_equal(O.ref_decompress(crafted), v)
+        assert np.array_equal(cb.decompress(crafted).reshape(v.shape), v)
+        assert np.array_equal(cb.decompress_range(crafted, z, z + 1), v[:, :, z:z + 1])
+    lab = int(v[40, 40, 0])
+    assert np.array_equal(cb.decompress(_craft_long_escape_run(b, 0), label=lab), v == lab)
+
+
+def test_label_crop_and_z_range_for_label(ctx):
+    # crackle.decompress(binary, label, crop=True) (codec.py:588-614): only the z-range that holds the label is returned
+    import crackle_b200 as cb
+    v = np.zeros((40, 30, 12), dtype=np.uint16, order="F")
+    v[5:20, 5:20, 3:7] = 7
+    v[22:30, 2:9, 6:11] = 9
+    b = cb.compress(v)
+    assert cb.z_range_for_label(b, 7) == (3, 7)
+    assert cb.z_range_for_label(b, 9) == (6, 11)
+    assert cb.z_range_for_label(b, 8) == (-1, -1) and cb.z_range_for_label(b, 1 << 20) == (-1, -1)
+    m = cb.decompress(b, label=7, crop=True)
+    assert m.shape == (40, 30, 4) and np.array_equal(m, v[:, :, 3:7] == 7)
+    assert cb.decompress(b, label=8, crop=True).shape == (0, 0, 0)
+    full = cb.decompress(b, label=9)
+    assert full.shape == v.shape and np.array_equal(full, v == 9)
+    assert not cb.decompress(b, label=8).any()
+
+
+def test_decoder_rejects_markov_orders_it_cannot_hold(ctx):
+    import crackle_b200 as cb
+    from oracle import oracle as O
+    v = np.ones((8, 8, 2), dtype=np.uint8, order="F")
+    b = bytearray(O.compress(v, 0))
+    fmt = int.from_bytes(b[5:7], "little") | (13 << 9)
+    b[5:7] = fmt.to_bytes(2, "little")
+    b[28] = O.lib().ckl_oracle_crc8((ctypes.c_char * 23).from_buffer(b, 5), 23)
+    with pytest.raises(RuntimeError, match="markov_model_order 13"):
+        cb.decompress(bytes(b))
