@@ -136,6 +136,19 @@ class Context:
         return out
 
 
+    def label_stats(self, binary, z_start=0, z_end=-1):
+        """ckl_label_stats: (labels u64[n], counts u64[n], sums u64[n,3], bbox u32[n,6]) for slices [z_start, z_end),
+        indexed like the stream's sorted unique label table -- computed from the runs, no volume is painted."""
+        buf = np.frombuffer(binary, dtype=np.uint8)
+        n = num_labels(binary)
+        labels, counts = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+        sums, bbox = np.zeros((n, 3), dtype=np.uint64), np.zeros((n, 6), dtype=np.uint32)
+        nu = ctypes.c_uint64()
+        self._check(_capi.lib().ckl_label_stats(self._h, buf.ctypes.data, 0, buf.size, int(z_start), int(z_end), labels.ctypes.data,
+                                                counts.ctypes.data, sums.ctypes.data, bbox.ctypes.data, 0, n, ctypes.byref(nu)))
+        return labels, counts, sums, bbox
+
+
 def launch_count() -> int:
     return int(_capi.lib().ckl_launch_count())
 
@@ -239,6 +252,94 @@ def decompress_range(binary, z_start: Optional[int], z_end: Optional[int], paral
     if h["is_signed"]:
         out = out.view(np.dtype(f"i{h['data_width']}"))
     return out
+
+
+def _labels_section(binary):
+    h = header(binary)
+    buf = np.frombuffer(binary, dtype=np.uint8)
+    hb = 24 if h["format_version"] == 0 else 29
+    off = hb + 4 * (h["sz"] + (0 if h["format_version"] == 0 else 1))
+    return h, buf[off: off + h["num_label_bytes"]]
+
+
+def num_labels(binary) -> int:
+    """crackle.num_labels (codec.py:82-96), flat label format"""
+    h, lab = _labels_section(binary)
+    if h["sx"] * h["sy"] * h["sz"] == 0:
+        return 0
+    return int.from_bytes(lab[:8].tobytes(), "little")
+
+
+def labels(binary) -> np.ndarray:
+    """crackle.labels (codec.py:17-80): the sorted unique labels of the stream"""
+    h, lab = _labels_section(binary)
+    if h["sx"] * h["sy"] * h["sz"] == 0:
+        return np.zeros((0,), dtype=np.dtype(f"u{h['data_width']}"))
+    n = int.from_bytes(lab[:8].tobytes(), "little")
+    return np.frombuffer(lab, dtype=f"<u{h['stored_data_width']}", count=n, offset=8).astype(np.dtype(f"u{h['data_width']}"))
+
+
+def contains(binary, label: int) -> bool:
+    """crackle.contains (codec.py:98-132)"""
+    u = labels(binary)
+    if label < 0 or u.size == 0 or label > int(u[-1]):
+        return False
+    i = int(np.searchsorted(u, np.asarray(label, dtype=u.dtype)))
+    return i < u.size and int(u[i]) == int(label)
+
+
+def _stats_range(binary, label):
+    if label is None:
+        return 0, -1
+    if not contains(binary, label):
+        raise ValueError(f"Label {label} not contained in image.")
+    return z_range_for_label(binary, label)
+
+
+def voxel_counts(binary, label: Optional[int] = None, parallel: int = 0):
+    """crackle.voxel_counts (codec.py:949-982 -> operations.hpp:321-371): {label: voxels} (an int when `label` is given)."""
+    z_start, z_end = _stats_range(binary, label)
+    if num_labels(binary) == 1:
+        h = header(binary)
+        vcts = {int(labels(binary)[0]): h["sx"] * h["sy"] * h["sz"]}
+    else:
+        with _default_lock:
+            lab, cnt, _, _ = default_context().label_stats(binary, z_start, z_end)
+        keep = cnt > 0
+        vcts = dict(zip(lab[keep].tolist(), cnt[keep].tolist()))
+    return vcts[label] if label is not None else vcts
+
+
+def centroids(binary, label: Optional[int] = None, parallel: int = 0):
+    """crackle.centroids (codec.py:984-1007 -> operations.hpp:421-491): {label: [x, y, z]} (float64, sums / count)."""
+    z_start, z_end = _stats_range(binary, label)
+    with _default_lock:
+        lab, cnt, sums, _ = default_context().label_stats(binary, z_start, z_end)
+    keep = cnt > 0
+    cen = sums[keep].astype(np.float64) / cnt[keep].astype(np.float64)[:, None]
+    out = {int(k): [float(v[0]), float(v[1]), float(v[2])] for k, v in zip(lab[keep], cen)}
+    return out[label] if label is not None else out
+
+
+def bounding_boxes(binary, label: Optional[int] = None, parallel: int = 0, no_slice_conversion: bool = False):
+    """crackle.bounding_boxes (codec.py:1009-1065 -> operations.hpp:541-617): {label: [xmin,ymin,zmin,xmax,ymax,zmax]} or
+    slices.  Like the reference, every label of the stream has an entry; one that is absent from the decoded z-range keeps
+    the initial (2^32-1, 2^32-1, 2^32-1, 0, 0, 0)."""
+    z_start, z_end = _stats_range(binary, label)
+    if num_labels(binary) == 1:
+        h = header(binary)
+        boxes = {int(labels(binary)[0]): np.array([0, 0, 0, h["sx"], h["sy"], h["sz"]], dtype=np.uint32)}
+    else:
+        with _default_lock:
+            lab, _, _, bbox = default_context().label_stats(binary, z_start, z_end)
+        boxes = {int(k): bbox[i].copy() for i, k in enumerate(lab)}
+    if no_slice_conversion:
+        return boxes[label] if label is not None else boxes
+    if label is not None:
+        boxes = {label: boxes[label]}
+    boxes = {k: (slice(int(b[0]), int(b[3]) + 1), slice(int(b[1]), int(b[4]) + 1), slice(int(b[2]), int(b[5]) + 1))
+             for k, b in boxes.items()}
+    return boxes[label] if label is not None else boxes
 
 
 def z_range_for_label(binary, label: int) -> Tuple[int, int]:

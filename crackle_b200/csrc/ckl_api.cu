@@ -1049,8 +1049,11 @@ __global__ void k_crc_compare(const u32* __restrict__ computed, const u8* __rest
 }
 
 // hbin: host view of the stream (may be null), dbin: device view (may be null -> uploaded); at least one is given.
+// stats != nullptr: no paint -- the per-label tables of ckl_label_stats are produced instead (out / label are unused)
+struct StatsOut { u64 *labels, *counts, *sums; u32* bbox; int on_device; u64 capacity; u64 n_unique; };
 static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t num_bytes, int64_t z_start, int64_t z_end,
-                            int has_label, uint64_t label, void* out, int out_on_device, uint64_t out_capacity) {
+                            int has_label, uint64_t label, void* out, int out_on_device, uint64_t out_capacity,
+                            StatsOut* stats = nullptr) {
   cudaStream_t st = c->st;
   timeline_base(c);
   if (num_bytes < 29) throw CklError(CKL_ERR_STREAM, "crackle: Input too small to be a valid stream. Bytes: " + std::to_string(num_bytes));
@@ -1083,7 +1086,7 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
   if (voxels == 0) return;
   if (sxy >= (1ull << 30)) throw CklError(CKL_ERR_ARG, "crackle_b200: slice too large (sx*sy must be < 2^30)");
   const int ow = has_label ? 1 : (int)h.data_width;
-  if (out_capacity < voxels * (u64)ow) throw CklError(CKL_ERR_ARG, "crackle_b200: output buffer too small");
+  if (!stats && out_capacity < voxels * (u64)ow) throw CklError(CKL_ERR_ARG, "crackle_b200: output buffer too small");
   const u64 hbytes = h.format_version == 0 ? 24 : 29;
   const u64 zbytes = 4ull * (h.sz + (h.format_version == 0 ? 0 : 1));
   if (hbytes + zbytes > num_bytes) throw CklError(CKL_ERR_STREAM, "crackle: get_crack_code_offsets: Unable to read past end of buffer.");
@@ -1158,7 +1161,7 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
   // Large Fortran-order outputs: K z-chunks on child contexts (each a z-range decode into its own part of the output),
   // so one chunk's decode chains / CCL overlap another chunk's paint and, for host outputs, its device->host copy.
   {
-    const int K = h.fortran_order ? pick_chunks(c, sxy, szr, (u64)ow, !out_on_device) : 1;
+    const int K = (h.fortran_order && !stats) ? pick_chunks(c, sxy, szr, (u64)ow, !out_on_device) : 1;
     if (K > 1) {
       ensure_kids(c, K);
       GridMultScope fine_grids;
@@ -1262,6 +1265,7 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
   launch_unpack_le(dsrc.uniq, sw, nu, D.uniq64.as<u64>(), st);
   launch_unpack_le(dsrc.keys, kw, n_keys, D.keys64.as<u64>(), st);
   dsrc.uniq64 = D.uniq64.as<u64>(); dsrc.keys64 = D.keys64.as<u64>();
+  dsrc.keys_only = stats != nullptr;
   STAGE(c, "d_ccl_finish", launch_ccl_finish(g, c->ccl, runs, c->dtab, init_term, &dsrc, st));
   if (h.format_version > 0) {   // crackle.hpp:599-611
     k_crc_compare<<<(g.sz + 255) / 256, 256, 0, st>>>(c->ccl.sliceCrc.as<u32>(), dstream + num_bytes - 4ull * h.sz + 4ull * (u64)z_start, g.sz, c->scal);
@@ -1277,6 +1281,25 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
                                          std::to_string(computed) + " stored: " + std::to_string(stored));
     }
   }
+  if (stats) {      // operations.hpp:321-665: per-label voxel counts, coordinate sums and bounding boxes, straight from the runs
+    stats->n_unique = nu;
+    if (stats->capacity < nu) throw CklError(CKL_ERR_ARG, "crackle_b200: statistics buffers hold fewer entries than the stream has labels");
+    c->out_dev.ensure(nu * (8 + 24 + 24) + 64);
+    ull* d_counts = c->out_dev.as<ull>();
+    ull* d_sums = d_counts + nu;
+    u32* d_bbox = reinterpret_cast<u32*>(d_sums + 3 * nu);
+    STAGE(c, "d_stats", launch_run_stats(g, (u32)z_start, c->ccl, runs, D.runLabel.as<u64>(), nu, d_counts, d_sums, d_bbox, st));
+    const cudaMemcpyKind k = stats->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (nu) {
+      if (stats->labels) CUDA_CHECK(cudaMemcpyAsync(stats->labels, D.uniq64.p, nu * 8, k, st));
+      if (stats->counts) CUDA_CHECK(cudaMemcpyAsync(stats->counts, d_counts, nu * 8, k, st));
+      if (stats->sums) CUDA_CHECK(cudaMemcpyAsync(stats->sums, d_sums, nu * 24, k, st));
+      if (stats->bbox) CUDA_CHECK(cudaMemcpyAsync(stats->bbox, d_bbox, nu * 24, k, st));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (!c->is_kid) c->prof.collect();
+    return;
+  }
   void* dout = out;
   if (!out_on_device) { c->out_dev.ensure(voxels * (u64)ow); dout = c->out_dev.p; }
   STAGE(c, "d_paint", launch_paint(g, c->DV.as<u32>(), c->ccl, D.runLabel.as<u64>(), ow, has_label, label, (int)h.fortran_order, dout, st));
@@ -1290,6 +1313,19 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   API_BEGIN(c)
   decompress_impl(c, binary_on_device ? nullptr : (const u8*)binary, binary_on_device ? (const u8*)binary : nullptr, num_bytes, z_start, z_end,
                   has_label, label, out, out_on_device, out_capacity);
+  API_END(c)
+}
+
+extern "C" int ckl_label_stats(ckl_ctx* c, const void* binary, int binary_on_device, uint64_t num_bytes, int64_t z_start, int64_t z_end,
+                               uint64_t* labels, uint64_t* counts, uint64_t* sums, uint32_t* bbox, int out_on_device,
+                               uint64_t capacity_entries, uint64_t* n_unique) {
+  API_BEGIN(c)
+  StatsOut so{labels, counts, sums, bbox, out_on_device, capacity_entries, 0};
+  try {
+    decompress_impl(c, binary_on_device ? nullptr : (const u8*)binary, binary_on_device ? (const u8*)binary : nullptr, num_bytes, z_start, z_end,
+                    0, 0, nullptr, 1, 0, &so);
+  } catch (...) { if (n_unique) *n_unique = so.n_unique; throw; }       // the label count is reported even when the buffers are too small
+  if (n_unique) *n_unique = so.n_unique;
   API_END(c)
 }
 

@@ -35,10 +35,14 @@ void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, c
 // second half: per-run component ranks, per-slice CRCs and (compress) component first pixels / (decompress, `decode`
 // non-null) the label of every run
 struct CclDecodeSrc { const u8* uniq; const u8* keys; u64 n_uniq, n_keys; int sw, kw; const u64* keyBase; u64* runLabel;
-                      const u64* uniq64 = nullptr; const u64* keys64 = nullptr; };   // aligned copies (launch_unpack_le), optional
+                      const u64* uniq64 = nullptr; const u64* keys64 = nullptr;      // aligned copies (launch_unpack_le), optional
+                      bool keys_only = false; };                                      // runLabel receives the key (unique-table index), not the label
 void launch_unpack_le(const u8* src, int width, u64 n, u64* dst, cudaStream_t st);
 void launch_ccl_finish(const Geom& g, CclBufs& B, u64 total_runs, const CrcTables* d_tables, u32 crc_init_term,
                        const CclDecodeSrc* decode, cudaStream_t st);
+// compressed-domain statistics: per-run reduction into tables indexed like the sorted unique label table
+void launch_run_stats(const Geom& g, u32 z_first, const CclBufs& B, u64 total_runs, const u64* runKey, u64 nu, ull* counts, ull* sums,
+                      u32* bbox, cudaStream_t st);
 // generic device CRC-32C of a byte buffer: result (finalised) written to *d_out
 void launch_crc_bytes(const u8* d, u64 n, const CrcTables* d_tables, const CrcTables& h_tables, u32* d_out, cudaStream_t st);
 // finalise per-slice raw registers into standard CRCs (in place)

@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(256) k_run_finish(Geom g, const u32* __restric
     if (lo >= n) continue;
     const u32 hi = min(n, lo + L);
     const u64 cb = compBase[z];
-    const u64 kb = MODE == 1 ? src.keyBase[z] : 0;
+    const u64 kb = MODE != 0 ? src.keyBase[z] : 0;
     u32 carry = lo ? rank[uf_find(par, lo - 1)] : 0u;             // component of the run before the range (warp-uniform)
     u32 x = 0;
     for (u32 i0 = lo; i0 < hi; i0 += 32) {
@@ -560,7 +560,12 @@ __global__ void __launch_bounds__(256) k_run_finish(Geom g, const u32* __restric
         const u32 root = uf_find(par, i);
         c = rank[root];
         if (MODE == 0) { if (root == i) compPix[cb + c] = runStart[gb + i]; }
-        else {
+        else if (MODE == 2) {                                   // compressed-domain statistics: the run's index into the unique table
+          const u64 ki = kb + c;
+          u64 key = ~0ull;
+          if (ki < src.n_keys) key = src.keys64 ? src.keys64[ki] : ld_le_dev(src.keys + ki * (u64)src.kw, src.kw);
+          src.runLabel[gb + i] = key;
+        } else {
           const u64 ki = kb + c;
           u64 label = 0;
           if (ki < src.n_keys) {
@@ -659,7 +664,14 @@ void launch_ccl_finish(const Geom& g, CclBufs& B, u64 total_runs, const CrcTable
     if (gx < 1) gx = 1;
     const dim3 grid(gx, g.sz < 65535u ? g.sz : 65535u);
     RunLabelSrc src{};
-    if (decode) {
+    if (decode && decode->keys_only) {
+      src.uniq = decode->uniq; src.keys = decode->keys; src.n_uniq = decode->n_uniq; src.n_keys = decode->n_keys;
+      src.sw = decode->sw; src.kw = decode->kw; src.keyBase = decode->keyBase; src.runLabel = decode->runLabel;
+      src.uniq64 = decode->uniq64; src.keys64 = decode->keys64;
+      k_run_finish<2><<<grid, 256, 0, st>>>(g, B.parent.as<u32>(), B.sliceRuns.as<u32>(), B.runBase.as<u64>(), B.compRank.as<u32>(),
+                                           B.runStart.as<u32>(), B.compBase.as<u64>(), B.crcH.as<u32>(), d_tables, B.compPix.as<u32>(),
+                                           src, B.sliceCrc.as<u32>());
+    } else if (decode) {
       src.uniq = decode->uniq; src.keys = decode->keys; src.n_uniq = decode->n_uniq; src.n_keys = decode->n_keys;
       src.sw = decode->sw; src.kw = decode->kw; src.keyBase = decode->keyBase; src.runLabel = decode->runLabel;
       src.uniq64 = decode->uniq64; src.keys64 = decode->keys64;
@@ -724,5 +736,61 @@ void launch_crc_bytes(const u8* d, u64 n, const CrcTables* d_tables, const CrcTa
   k_crc_bytes<<<grid_for(nchunks ? nchunks : 1, 256, 8), 256, 0, st>>>(d, n, d_tables, d_out);
   LAUNCH_CHECK();
   k_not<<<1, 1, 0, st>>>(d_out);
+  LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Compressed-domain statistics (src/operations.hpp:321-665 voxel_counts / centroids / bounding_boxes): the reference
+// paints the slice's component image and loops over its pixels; here every RUN contributes its length, coordinate sums
+// and extent to the tables of its label (index into the sorted unique table) -- no full-width image exists.
+// counts u64[nu]; sums u64[nu][3] (x, y, z); bbox u32[nu][6] (xmin, ymin, zmin, xmax, ymax, zmax)
+__global__ void __launch_bounds__(256) k_stats_init(u64 nu, ull* counts, ull* sums, u32* bbox) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nu * 6; i += stride) {
+    if (i < nu) counts[i] = 0;
+    if (i < nu * 3) sums[i] = 0;
+    bbox[i] = (i % 6) < 3 ? 0xFFFFFFFFu : 0u;
+  }
+}
+__global__ void __launch_bounds__(256) k_run_stats(Geom g, u32 z_first, const u32* __restrict__ sliceRuns, const u64* __restrict__ runBase,
+                                                    const u32* __restrict__ runStart, const u64* __restrict__ runKey, u64 nu,
+                                                    ull* counts, ull* sums, u32* bbox) {
+  for (u32 z = blockIdx.y; z < g.sz; z += gridDim.y) {
+    const u32 n = sliceRuns[z];
+    const u64 gb = runBase[z];
+    const u32 zabs = z_first + z;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const u64 key = runKey[gb + i];
+      if (key >= nu) continue;                                   // corrupt key: the reference would read out of bounds
+      const u32 start = runStart[gb + i];
+      const u32 end = i + 1 < n ? runStart[gb + i + 1] : (u32)g.sxy;   // runs tile the slice in raster order, one row each
+      const u32 len = end - start;
+      const u32 y = start / g.sx, x0 = start - y * g.sx, x1 = x0 + len - 1;
+      atomicAdd(counts + key, (ull)len);
+      atomicAdd(sums + key * 3 + 0, (ull)len * x0 + (ull)len * (len - 1) / 2);
+      atomicAdd(sums + key * 3 + 1, (ull)len * y);
+      atomicAdd(sums + key * 3 + 2, (ull)len * zabs);
+      u32* b = bbox + key * 6;                                   // a plain read first: most runs do not extend the box
+      if (x0 < __ldcg(b + 0)) atomicMin(b + 0, x0);
+      if (y < __ldcg(b + 1)) atomicMin(b + 1, y);
+      if (zabs < __ldcg(b + 2)) atomicMin(b + 2, zabs);
+      if (x1 > __ldcg(b + 3)) atomicMax(b + 3, x1);
+      if (y > __ldcg(b + 4)) atomicMax(b + 4, y);
+      if (zabs > __ldcg(b + 5)) atomicMax(b + 5, zabs);
+    }
+  }
+}
+void launch_run_stats(const Geom& g, u32 z_first, const CclBufs& B, u64 total_runs, const u64* runKey, u64 nu, ull* counts, ull* sums,
+                      u32* bbox, cudaStream_t st) {
+  if (!nu) return;
+  k_stats_init<<<grid_for(nu * 6, 256, 8), 256, 0, st>>>(nu, counts, sums, bbox);
+  LAUNCH_CHECK();
+  if (!total_runs) return;
+  const u64 per_slice = (total_runs + g.sz - 1) / g.sz;
+  u32 gx = (u32)((per_slice + 255) / 256);
+  if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
+  k_run_stats<<<dim3(gx, g.sz < 65535u ? g.sz : 65535u), 256, 0, st>>>(g, z_first, B.sliceRuns.as<u32>(), B.runBase.as<u64>(),
+                                                                        B.runStart.as<u32>(), runKey, nu, counts, sums, bbox);
   LAUNCH_CHECK();
 }

@@ -20,6 +20,7 @@ The per-shard compute is behind a small backend interface so the host logic can 
 (tests/test_dist_cpu.py supplies an oracle-backed fake); the product backend is `CudaShardBackend` (C-ABI)."""
 import ctypes
 import os
+import sys
 import time
 
 import numpy as np
@@ -316,7 +317,7 @@ class ShardedCodec:
         final = be.assemble(gathered, blocks, guniq, data_width, stored, int(permissible), fortran_order, order, sx, sy)
         self._mark("assemble")
         if self._prof and R == 0:
-            print("CKL_DIST_PROF " + " ".join(f"{k}={v:.2f}" for k, v in self._marks), flush=True)
+            sys.stderr.write("CKL_DIST_PROF " + " ".join(f"{k}={v:.2f}" for k, v in self._marks) + "\n")
         return final
 
     # -- decompress ------------------------------------------------------------------------------------------

@@ -94,6 +94,19 @@ CKL_API int ckl_decompress(ckl_ctx* ctx, const void* binary, int binary_on_devic
                    int64_t z_start, int64_t z_end, int has_label, uint64_t label,
                    void* out, int out_on_device, uint64_t out_capacity);
 
+/* Compressed-domain statistics -- voxel_counts, centroids and bounding_boxes of src/operations.hpp:321-665 (the
+ * consumers of for_each_z_parallel, :89-182) -- for slices [z_start, z_end) without ever painting the volume: crack
+ * decode, per-slice CCL and label map as in ckl_decompress, then every horizontal run adds its length, coordinate sums
+ * and extent to its label's entry.  Entries are indexed like the stream's sorted unique label table:
+ *   labels u64[n]  counts u64[n]  sums u64[n][3] = (sum x, sum y, sum z)  bbox u32[n][6] = (xmin,ymin,zmin,xmax,ymax,zmax)
+ * (centroid = sums / count; a label absent from the z-range keeps count 0, mins 0xFFFFFFFF, maxs 0 like the
+ * reference's freshly initialised boxes).  Each output may be NULL; capacity_entries >= the stream's label count
+ * (crackle_b200_header + the u64 at the start of the labels section, or call once with all outputs NULL and
+ * capacity 0 ... which fails with CKL_ERR_ARG but still reports *n_unique). */
+CKL_API int ckl_label_stats(ckl_ctx* ctx, const void* binary, int binary_on_device, uint64_t num_bytes,
+                    int64_t z_start, int64_t z_end, uint64_t* labels, uint64_t* counts, uint64_t* sums, uint32_t* bbox,
+                    int out_on_device, uint64_t capacity_entries, uint64_t* n_unique);
+
 /* ---- z-sharded multi-GPU compress (one context per GPU; the caller moves the small blobs between ranks,
  *      e.g. with torch.distributed all_gather over NCCL).  Mirrors what operations.zstack /
  *      _zstack_flat_labels (crackle/operations.py:258-295, 424-548) do for independently compressed slabs. --- */

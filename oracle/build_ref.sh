@@ -12,6 +12,16 @@ if [ ! -f "$REF/src/fastcrackle.cpp" ]; then
   echo "reference sources not found at $REF; keeping any prebuilt oracle/_ref" >&2
   exit 0
 fi
+# The reference's pure-Python package and its own test file are staged next to the compiled module (git-ignored like it;
+# nothing of the reference enters the history): tests/test_reference_suite.py runs the reference's automated_test.py through
+# the reference's Python layer with the B200 library underneath (INTEGRATION.md Option B).
+PKG="$OUT/refpkg"
+if [ -d "$REF/crackle" ]; then
+  rm -rf "$PKG"; mkdir -p "$PKG"
+  cp -r "$REF/crackle" "$PKG/crackle"
+  cp "$REF/automated_test.py" "$PKG/automated_test.py"
+  find "$PKG" -name "__pycache__" -type d -prune -exec rm -rf {} +
+fi
 EXT="$(python3 -c "import sysconfig;print(sysconfig.get_config_var('EXT_SUFFIX'))")"
 TARGET="$OUT/_fastcrackle_ref$EXT"
 if [ -f "$TARGET" ] && [ "$TARGET" -nt "$REF/src/fastcrackle.cpp" ] && [ "${1:-}" != "--force" ]; then
