@@ -136,6 +136,13 @@ class Context:
         return out
 
 
+    def reencode(self, binary, markov_model_order: int) -> bytes:
+        """ckl_reencode: the same stream with its crack codes re-coded at another markov order (no voxel decode)"""
+        buf = np.frombuffer(binary, dtype=np.uint8)
+        n = ctypes.c_uint64()
+        self._check(_capi.lib().ckl_reencode(self._h, buf.ctypes.data, 0, buf.size, int(markov_model_order), ctypes.byref(n)))
+        return self.result_bytes()
+
     def label_stats(self, binary, z_start=0, z_end=-1):
         """ckl_label_stats: (labels u64[n], counts u64[n], sums u64[n,3], bbox u32[n,6]) for slices [z_start, z_end),
         indexed like the stream's sorted unique label table -- computed from the runs, no volume is painted."""
@@ -252,6 +259,14 @@ def decompress_range(binary, z_start: Optional[int], z_end: Optional[int], paral
     if h["is_signed"]:
         out = out.view(np.dtype(f"i{h['data_width']}"))
     return out
+
+
+def reencode(binary, markov_model_order: int, parallel: int = 0) -> bytes:
+    """crackle.codec.reencode (codec.py:877-881)"""
+    if header(binary)["markov_model_order"] == markov_model_order:
+        return binary
+    with _default_lock:
+        return default_context().reencode(binary, markov_model_order)
 
 
 def _labels_section(binary):

@@ -16,6 +16,11 @@
 
 void launch_exscan_u32_u64(const u32* in, u32 n, u32 stride, u64* out, ull* total_out, u64 add_each, cudaStream_t st);
 void launch_markov_copy(const Geom& g, TraceBufs& T, MarkovBufs& M, u8* dst, cudaStream_t st);
+void launch_markov_copy_body(const Geom& g, TraceBufs& T, MarkovBufs& M, u8* dst, cudaStream_t st);
+void launch_reencode_codepoints(const Geom& g, const u8* stream, int order, DecodeBufs& D, u64 total_events, u32* sliceInfo, cudaStream_t st);
+void launch_reencode_unpack(const Geom& g, DecodeBufs& D, const u32* sliceInfo, const u64* cpOff, u8* cp, u64 total_words, cudaStream_t st);
+void launch_reencode_emit(const Geom& g, const u8* stream, DecodeBufs& D, const u32* sliceInfo, const u64* cpOff, const u8* cp,
+                          const u64* codeOff, int pack0, u8* dst, cudaStream_t st);
 bool launch_trace_nodes(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes, cudaStream_t st);
 void launch_trace_paths(const Geom& g, TraceBufs& T, ull* scal, u32 max_nodes, cudaStream_t st);
 void launch_trace_replay(const Geom& g, TraceBufs& T, ull* scal, u32 max_nodes, cudaStream_t st);
@@ -1049,6 +1054,7 @@ __global__ void k_crc_compare(const u32* __restrict__ computed, const u8* __rest
 }
 
 // hbin: host view of the stream (may be null), dbin: device view (may be null -> uploaded); at least one is given.
+static std::vector<u8> decode_stored_model(const u8* ms, u64 mbytes, int order);
 // stats != nullptr: no paint -- the per-label tables of ckl_label_stats are produced instead (out / label are unused)
 struct StatsOut { u64 *labels, *counts, *sums; u32* bbox; int on_device; u64 capacity; u64 n_unique; };
 static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t num_bytes, int64_t z_start, int64_t z_end,
@@ -1134,23 +1140,7 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
   }
   // markov model: symbol of rank per context row (markov.hpp:382-420)
   std::vector<u8> model;
-  if (order > 0) {
-    u8 lut[24]; int k = 0;
-    for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) for (int cc = 0; cc < 4; cc++) for (int d = 0; d < 4; d++) {
-      if (a == b || a == cc || a == d || b == cc || b == d || cc == d) continue;
-      lut[k++] = (u8)(a | b << 2 | cc << 4 | d << 6);
-    }
-    const u64 rows = 1ull << (2 * order);
-    model.resize(rows * 4);
-    const u8* ms = fetch(lab_off + h.num_label_bytes, mbytes, buf_model);
-    for (u64 r = 0; r < rows; r++) {
-      const u64 bit = r * 5;
-      u32 v = ms[bit >> 3];
-      if ((bit >> 3) + 1 < mbytes) v |= (u32)ms[(bit >> 3) + 1] << 8;
-      const u8 packed = lut[((v >> (bit & 7)) & 31) % 24];
-      for (int q = 0; q < 4; q++) model[r * 4 + q] = (packed >> (2 * q)) & 3;
-    }
-  }
+  if (order > 0) model = decode_stored_model(fetch(lab_off + h.num_label_bytes, mbytes, buf_model), mbytes, order);
   // device copies
   const u8* dstream = dbin;
   if (!dstream) {
@@ -1326,6 +1316,156 @@ extern "C" int ckl_label_stats(ckl_ctx* c, const void* binary, int binary_on_dev
                     0, 0, nullptr, 1, 0, &so);
   } catch (...) { if (n_unique) *n_unique = so.n_unique; throw; }       // the label count is reported even when the buffers are too small
   if (n_unique) *n_unique = so.n_unique;
+  API_END(c)
+}
+
+// symbol of rank per context row from the stored model (markov.hpp:382-420)
+static std::vector<u8> decode_stored_model(const u8* ms, u64 mbytes, int order) {
+  u8 lut[24]; int k = 0;
+  for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) for (int cc = 0; cc < 4; cc++) for (int d = 0; d < 4; d++) {
+    if (a == b || a == cc || a == d || b == cc || b == d || cc == d) continue;
+    lut[k++] = (u8)(a | b << 2 | cc << 4 | d << 6);
+  }
+  const u64 rows = 1ull << (2 * order);
+  std::vector<u8> model(rows * 4);
+  for (u64 r = 0; r < rows; r++) {
+    const u64 bit = r * 5;
+    u32 v = ms[bit >> 3];
+    if ((bit >> 3) + 1 < mbytes) v |= (u32)ms[(bit >> 3) + 1] << 8;
+    const u8 packed = lut[((v >> (bit & 7)) & 31) % 24];
+    for (int q = 0; q < 4; q++) model[r * 4 + q] = (packed >> (2 * q)) & 3;
+  }
+  return model;
+}
+
+// crackle::reencode_with_markov_order (src/crackle.hpp:860-984): same stream, crack codes re-coded with another context
+// model order.  Labels section, labels crc and slice crcs are carried over verbatim (so every label format is accepted);
+// the crack codes go codepoints -> (statistics -> model -> bitstreams | 2-bit packing) on the device.
+extern "C" int ckl_reencode(ckl_ctx* c, const void* binary, int binary_on_device, uint64_t num_bytes, int new_order, uint64_t* out_bytes) {
+  API_BEGIN(c)
+  cudaStream_t st = c->st;
+  const u8* hbin = binary_on_device ? nullptr : (const u8*)binary;
+  const u8* dbin = binary_on_device ? (const u8*)binary : nullptr;
+  if (num_bytes < 29) throw CklError(CKL_ERR_STREAM, "crackle: Input too small to be a valid stream. Bytes: " + std::to_string(num_bytes));
+  if (new_order < 0 || new_order > 12) throw CklError(CKL_ERR_ARG, "crackle_b200: markov_model_order must be in [0, 12]");
+  std::vector<u8> buf_head, buf_z, buf_model;
+  auto fetch = [&](u64 offset, u64 n, std::vector<u8>& buf) -> const u8* {
+    if (hbin) return hbin + offset;
+    buf.resize(n ? n : 1);
+    if (n) { CUDA_CHECK(cudaMemcpyAsync(buf.data(), dbin + offset, n, cudaMemcpyDeviceToHost, st)); CUDA_CHECK(cudaStreamSynchronize(st)); }
+    return buf.data();
+  };
+  const u8* hhead = fetch(0, 29, buf_head);
+  ckl_header_info h;
+  std::string perr;
+  int rc = parse_header(hhead, num_bytes, &h, perr);
+  if (rc) throw CklError(rc, perr);
+  const int order = (int)h.markov_model_order;
+  if (order > 12) throw CklError(CKL_ERR_UNSUPPORTED, "crackle_b200: markov_model_order " + std::to_string(order) + " is not supported (maximum 12)");
+  const u8* dstream = dbin;
+  if (!dstream) {
+    c->stream_dev.ensure(num_bytes + 8);
+    CUDA_CHECK(cudaMemcpyAsync(c->stream_dev.p, hbin, num_bytes, cudaMemcpyHostToDevice, st));
+    dstream = c->stream_dev.as<u8>();
+  }
+  const u64 sxy = (u64)h.sx * h.sy;
+  if (order == new_order || sxy * h.sz == 0) {                     // crackle.hpp:888-890: a copy
+    c->result.ensure(num_bytes + 16);
+    CUDA_CHECK(cudaMemcpyAsync(c->result.p, dstream, num_bytes, cudaMemcpyDeviceToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    c->result_bytes = num_bytes;
+    if (out_bytes) *out_bytes = num_bytes;
+    return CKL_OK;
+  }
+  if (sxy >= (1ull << 30)) throw CklError(CKL_ERR_ARG, "crackle_b200: slice too large (sx*sy must be < 2^30)");
+  const bool v1 = h.format_version > 0;
+  const u64 sz = h.sz;
+  const u64 hbytes = v1 ? 29 : 24, zbytes = 4ull * (sz + (v1 ? 1 : 0));
+  if (hbytes + zbytes > num_bytes) throw CklError(CKL_ERR_STREAM, "crackle: get_crack_code_offsets: Unable to read past end of buffer.");
+  const u8* hz = fetch(hbytes, zbytes, buf_z);
+  const u64 mbytes = model_bytes_for(order), mbytes_new = model_bytes_for(new_order);
+  std::vector<u64> codeOff(sz + 1), wordOff(sz + 1);
+  codeOff[0] = hbytes + zbytes + h.num_label_bytes + mbytes;
+  u64 tw = 0;
+  for (u64 z = 0; z < sz; z++) {
+    const u64 clen = le_host(hz + 4 * z, 4);
+    codeOff[z + 1] = codeOff[z] + clen;
+    const u64 cap = order == 0 ? clen * 4 : clen * 8;
+    if (cap >= (1ull << 30)) throw CklError(CKL_ERR_ARG, "crackle_b200: crack code of a slice is too large");
+    wordOff[z] = tw;
+    tw += (cap + 15) / 16 + 1;
+  }
+  wordOff[sz] = tw;
+  const u64 tail = v1 ? 4 + 4 * sz : 0;
+  if (codeOff[sz] + tail > num_bytes) throw CklError(CKL_ERR_STREAM, "crackle: get_crack_codes: Unable to read past end of buffer.");
+  Geom g;
+  g.sx = h.sx; g.sy = h.sy; g.sz = (u32)sz; g.W = (u32)((g.sx + 31) / 32); g.sxy = sxy;
+  DecodeBufs& D = c->dc;
+  D.codeOff.ensure((sz + 1) * 8); D.wordOff.ensure((sz + 1) * 8); D.slices.ensure(sz * sizeof(DecSlice));
+  CUDA_CHECK(cudaMemcpyAsync(D.codeOff.p, codeOff.data(), (sz + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(D.wordOff.p, wordOff.data(), (sz + 1) * 8, cudaMemcpyHostToDevice, st));
+  std::vector<u8> model;
+  if (order > 0) {
+    model = decode_stored_model(fetch(hbytes + zbytes + h.num_label_bytes, mbytes, buf_model), mbytes, order);
+    D.model.ensure(model.size());
+    CUDA_CHECK(cudaMemcpyAsync(D.model.p, model.data(), model.size(), cudaMemcpyHostToDevice, st));
+  }
+  CUDA_CHECK(cudaMemsetAsync(c->scal, 0, SC_COUNT * sizeof(ull), st));
+  launch_decode_slices_init(g, dstream, D.codeOff.as<u64>(), D.wordOff.as<u64>(), D.slices.as<DecSlice>(), c->scal, st);
+  launch_decode_classify(g, dstream, order, D.model.as<u8>(), D, tw, c->scal, st);
+  read_scalars(c);
+  if (c->hscal[SC_ERROR]) throw CklError(CKL_ERR_STREAM, "crackle: crack code index is larger than its slice's code.");
+  if (c->hscal[SC_FIRST]) throw CklError(CKL_ERR_UNSUPPORTED, "crackle_b200: crack code holds an escape run no encoder emits; re-encode it with the reference");
+  TraceBufs& T = c->tr;
+  const u64 n1 = sz + 1;
+  T.sliceInfo.ensure(sz * 16); T.offs.ensure(n1 * 8 * 4); T.codeOff.ensure(n1 * 8);
+  launch_reencode_codepoints(g, dstream, order, D, c->hscal[SC_LAST], T.sliceInfo.as<u32>(), st);
+  u64* cpOff = T.offs.as<u64>() + 3 * n1;
+  launch_exscan_u32_u64(T.sliceInfo.as<u32>(), g.sz, 4, cpOff, &c->scal[SC_CODEPOINTS], 0, st);
+  T.cp.ensure(tw * 16 + 16);                                         // upper bound of the codepoint total, known without a read-back
+  launch_reencode_unpack(g, D, T.sliceInfo.as<u32>(), cpOff, T.cp.as<u8>(), tw, st);
+  if (new_order > 0) {                                               // markov.hpp:166-266, :422-489
+    const u64 rows = 1ull << (2 * new_order);
+    c->mk.stats.ensure(rows * 16); c->mk.model.ensure(rows * 4); c->mk.stored.ensure(mbytes_new + 16);
+    launch_markov_stats(g, T, new_order, c->mk.stats.as<u32>(), st);
+    launch_markov_model(new_order, c->mk.stats.as<u32>(), c->mk.model.as<u8>(), c->mk.stored.as<u8>(), mbytes_new, st);
+    launch_markov_sizes(g, T, new_order, c->mk.model.as<u8>(), c->mk, c->scal, st);
+    const u64 scratch_words = (3 * tw * 16) / 32 + 3ull * g.sz + 64;
+    c->mk.scratch.ensure(scratch_words * 4);
+    CUDA_CHECK(cudaMemsetAsync(c->mk.scratch.p, 0, scratch_words * 4, st));
+    launch_markov_encode(g, T, new_order, c->mk.model.as<u8>(), c->mk, nullptr, st);
+  }
+  launch_code_sizes_order0(g, T, c->scal, st);
+  read_scalars(c);
+  const u64 codes_bytes = c->hscal[SC_CODE_BYTES];
+  const u64 off_z = hbytes, off_lab = off_z + zbytes, off_model = off_lab + h.num_label_bytes, off_codes = off_model + mbytes_new;
+  const u64 total = off_codes + codes_bytes + tail;
+  c->result.ensure(total + 16);
+  u8* R = c->result.as<u8>();
+  u8 hb[29];
+  memcpy(hb, hhead, hbytes);
+  const u32 fmt = ((u32)le_host(hb + 5, 2) & ~(15u << 9)) | ((u32)new_order << 9);
+  hb[5] = (u8)fmt; hb[6] = (u8)(fmt >> 8);
+  if (v1) hb[28] = crc8_header(hb + 5, 23);
+  CUDA_CHECK(cudaMemcpyAsync(R, hb, hbytes, cudaMemcpyHostToDevice, st));
+  c->tmp32.ensure(sz * 4 + 16);
+  k_gather_stride4<<<(g.sz + 255) / 256, 256, 0, st>>>(T.sliceInfo.as<u32>(), g.sz, 3, c->tmp32.as<u32>());
+  LAUNCH_CHECK();
+  launch_write_le_u32(c->tmp32.as<u32>(), sz, 4, R + off_z, st);
+  if (v1) {
+    u32* crc_tmp = c->tmp32.as<u32>() + sz;
+    launch_crc_bytes(R + off_z, 4 * sz, c->dtab, c->htab, crc_tmp, st);
+    k_store_bytes_u32<<<1, 1, 0, st>>>(R + off_z + 4 * sz, crc_tmp);
+    LAUNCH_CHECK();
+  }
+  CUDA_CHECK(cudaMemcpyAsync(R + off_lab, dstream + off_lab, h.num_label_bytes, cudaMemcpyDeviceToDevice, st));
+  if (new_order > 0) CUDA_CHECK(cudaMemcpyAsync(R + off_model, c->mk.stored.p, mbytes_new, cudaMemcpyDeviceToDevice, st));
+  launch_reencode_emit(g, dstream, D, T.sliceInfo.as<u32>(), cpOff, T.cp.as<u8>(), T.codeOff.as<u64>(), new_order == 0, R + off_codes, st);
+  if (new_order > 0) launch_markov_copy_body(g, T, c->mk, R + off_codes, st);
+  if (tail) CUDA_CHECK(cudaMemcpyAsync(R + off_codes + codes_bytes, dstream + codeOff[sz], tail, cudaMemcpyDeviceToDevice, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  c->result_bytes = total;
+  if (out_bytes) *out_bytes = total;
   API_END(c)
 }
 

@@ -791,3 +791,129 @@ void launch_paint(const Geom& g, const u32* DV, const CclBufs& B, const u64* run
 #undef PAINTR
   LAUNCH_CHECK();
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Re-encoding with another markov order (crackle::reencode_with_markov_order, src/crackle.hpp:860-984): the codepoints
+// of every slice are recovered with the scan-parallel front end above (moves Mw, event list) and handed to the
+// encoder's packers; nothing is decoded to voxels.
+//
+// Exact codepoint count of a slice: codes end with padding (up to 3 fields at order 0, up to 7 bits at order > 0).  The
+// symbols end when the last chain of the beginning-of-chain index closes; every chain opens with one branch, a 'b' adds
+// one and a 't' removes one, so the end is the first event at which (#t - #b) reaches the number of chains.
+__global__ void __launch_bounds__(256) k_reenc_ncp(Geom g, const DecSlice* __restrict__ ds, const u8* __restrict__ stream, int order,
+                                                    const u32* __restrict__ ncpIn, const u64* __restrict__ evOff,
+                                                    const u32* __restrict__ evIdx, u32* __restrict__ sliceInfo) {
+  __shared__ u32 sm[33];
+  __shared__ u32 s_nch, s_best;
+  const int xw = ckl_byte_width((u64)g.sx + 1), yw = ckl_byte_width((u64)g.sy + 1);
+  for (u32 z = blockIdx.x; z < g.sz; z += gridDim.x) {
+    const DecSlice d = ds[z];
+    if (threadIdx.x == 0) {
+      u32 nch = 0;
+      if (d.isz >= (u32)(4 + yw)) {
+        const u8* p = stream + d.code;
+        u64 idx = 4;
+        const u32 ny = (u32)ld_le(p + idx, yw); idx += yw;
+        for (u32 r = 0; r < ny && idx + yw + xw <= d.isz; r++) {
+          idx += yw;
+          const u32 nx = (u32)ld_le(p + idx, xw);
+          idx += xw + (u64)nx * xw;
+          nch += nx;
+        }
+      }
+      s_nch = nch; s_best = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    const u32 nch = s_nch;
+    const u64 e0 = evOff[z];
+    const u32 nev = (u32)(evOff[z + 1] - e0);
+    const u32 cap = order > 0 ? ncpIn[z] : d.blen * 4u;
+    int carry = 0;
+    for (u32 j0 = 0; j0 < nev && nch; j0 += blockDim.x) {
+      const u32 j = j0 + threadIdx.x;
+      int v = 0;
+      u32 e = 0;
+      if (j < nev) { e = evIdx[e0 + j]; const u32 m = e >> 30; v = (m == 0 || m == 3) ? 1 : -1; }      // 't' : 'b'
+      u32 tot;
+      const int incl = carry + (int)block_excl_scan((u32)v, sm, tot) + v;
+      if (j < nev && v == 1 && incl == (int)nch) atomicMin(&s_best, j);
+      carry += (int)tot;
+      __syncthreads();
+      if (s_best != 0xFFFFFFFFu) break;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u32 ncp = 0;
+      if (nch) ncp = s_best != 0xFFFFFFFFu ? (evIdx[e0 + s_best] & 0x3FFFFFFFu) + 1u : cap;
+      sliceInfo[(u64)z * 4 + 0] = ncp;
+      sliceInfo[(u64)z * 4 + 1] = nch;
+      sliceInfo[(u64)z * 4 + 2] = d.isz;                          // the index is carried over verbatim
+      sliceInfo[(u64)z * 4 + 3] = d.isz + (ncp + 3) / 4;          // order-0 size; the markov encoder overwrites it
+    }
+    __syncthreads();
+  }
+}
+// absolute moves, 16 per word -> one byte per codepoint at the encoder's codepoint offsets
+__global__ void __launch_bounds__(256) k_reenc_unpack(Geom g, const DecSlice* __restrict__ ds, const u32* __restrict__ Mw,
+                                                       const u32* __restrict__ sliceInfo, const u64* __restrict__ cpOff, u8* __restrict__ cp) {
+  for (u32 z = blockIdx.y; z < g.sz; z += gridDim.y) {
+    const u32 ncp = sliceInfo[(u64)z * 4 + 0];
+    const u32 nwords = (ncp + 15) / 16;
+    const u32* M = Mw + ds[z].wordOff;
+    u8* out = cp + cpOff[z];
+    for (u32 w = blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += gridDim.x * blockDim.x) {
+      const u32 m = M[w];
+      const u32 n = min(16u, ncp - w * 16);
+      for (u32 k = 0; k < n; k++) out[w * 16 + k] = (u8)((m >> (2 * k)) & 3u);
+    }
+  }
+}
+// beginning-of-chain index of every slice copied from the source stream; order 0 also packs the difference fields
+__global__ void __launch_bounds__(256) k_reenc_emit(Geom g, const DecSlice* __restrict__ ds, const u8* __restrict__ stream,
+                                                     const u32* __restrict__ sliceInfo, const u64* __restrict__ cpOff,
+                                                     const u8* __restrict__ cp, const u64* __restrict__ codeOff, int pack0,
+                                                     u8* __restrict__ dst) {
+  for (u32 z = blockIdx.x; z < g.sz; z += gridDim.x) {
+    const DecSlice d = ds[z];
+    u8* out = dst + codeOff[z];
+    for (u32 b = threadIdx.x; b < d.isz; b += blockDim.x) out[b] = stream[d.code + b];
+    if (!pack0) continue;
+    const u32 ncp = sliceInfo[(u64)z * 4 + 0];
+    const u8* c = cp + cpOff[z];
+    for (u32 b = threadIdx.x; b < (ncp + 3) / 4; b += blockDim.x) {
+      u32 last = b ? c[4 * b - 1] : 0, acc = 0;                    // differences carry across chains, initial 0
+      for (u32 k = 0; k < 4; k++) {
+        const u32 i = 4 * b + k;
+        if (i < ncp) { const u32 v = c[i]; acc |= ((v - last) & 3u) << (2 * k); last = v; }
+      }
+      out[d.isz + b] = (u8)acc;
+    }
+  }
+}
+
+// front end: events of every slice (after launch_decode_classify + the host knows total_events)
+void launch_reencode_codepoints(const Geom& g, const u8* stream, int order, DecodeBufs& D, u64 total_events, u32* sliceInfo,
+                                cudaStream_t st) {
+  const DecSlice* ds = D.slices.as<DecSlice>();
+  D.evIdx.ensure(total_events * 4 + 16);
+  if (total_events) {
+    k_dec_compact<<<dec_grid(g.sz, 1, 8), 256, 0, st>>>(ds, g.sz, order, D.ncp.as<u32>(), D.Mw.as<u32>(), D.Sw.as<u32>(), D.evOff.as<u64>(),
+                                                        D.evIdx.as<u32>(), D.evBaseW.as<u32>());
+    LAUNCH_CHECK();
+  }
+  k_reenc_ncp<<<dec_grid(g.sz, 1, 8), 256, 0, st>>>(g, ds, stream, order, D.ncp.as<u32>(), D.evOff.as<u64>(), D.evIdx.as<u32>(), sliceInfo);
+  LAUNCH_CHECK();
+}
+void launch_reencode_unpack(const Geom& g, DecodeBufs& D, const u32* sliceInfo, const u64* cpOff, u8* cp, u64 total_words, cudaStream_t st) {
+  const u64 per_slice = (total_words + g.sz - 1) / g.sz;
+  u32 gx = (u32)((per_slice + 255) / 256);
+  if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
+  k_reenc_unpack<<<dim3(gx, g.sz < 65535u ? g.sz : 65535u), 256, 0, st>>>(g, D.slices.as<DecSlice>(), D.Mw.as<u32>(), sliceInfo, cpOff, cp);
+  LAUNCH_CHECK();
+}
+void launch_reencode_emit(const Geom& g, const u8* stream, DecodeBufs& D, const u32* sliceInfo, const u64* cpOff, const u8* cp,
+                          const u64* codeOff, int pack0, u8* dst, cudaStream_t st) {
+  k_reenc_emit<<<dec_grid(g.sz, 1, 8), 256, 0, st>>>(g, D.slices.as<DecSlice>(), stream, sliceInfo, cpOff, cp, codeOff, pack0, dst);
+  LAUNCH_CHECK();
+}

@@ -191,6 +191,12 @@ __global__ void __launch_bounds__(256) k_markov_copy(Geom g, const u32* __restri
     for (u32 b = threadIdx.x; b < total - boc; b += blockDim.x) out[b] = src[b];
   }
 }
+// bitstreams only (the caller places the beginning-of-chain indices itself)
+void launch_markov_copy_body(const Geom& g, TraceBufs& T, MarkovBufs& M, u8* dst, cudaStream_t st) {
+  k_markov_copy<<<grid_slices(g.sz, 8), 256, 0, st>>>(g, T.sliceInfo.as<u32>(), T.codeOff.as<u64>(), M.scratchOff.as<u64>(),
+                                                      M.scratch.as<u32>(), dst);
+  LAUNCH_CHECK();
+}
 void launch_markov_copy(const Geom& g, TraceBufs& T, MarkovBufs& M, u8* dst, cudaStream_t st) {
   launch_write_boc_only(g, T, dst, st);
   k_markov_copy<<<grid_slices(g.sz, 8), 256, 0, st>>>(g, T.sliceInfo.as<u32>(), T.codeOff.as<u64>(), M.scratchOff.as<u64>(),

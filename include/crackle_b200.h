@@ -107,6 +107,13 @@ CKL_API int ckl_label_stats(ckl_ctx* ctx, const void* binary, int binary_on_devi
                     int64_t z_start, int64_t z_end, uint64_t* labels, uint64_t* counts, uint64_t* sums, uint32_t* bbox,
                     int out_on_device, uint64_t capacity_entries, uint64_t* n_unique);
 
+/* Re-code a stream's crack codes with another markov model order without decoding to voxels
+ * (crackle::reencode_with_markov_order, src/crackle.hpp:860-984; fastcrackle.reencode_markov src/fastcrackle.cpp:643).
+ * Labels, labels crc and slice crcs are carried over verbatim; the result is left in the context's result buffer
+ * (ckl_result_copy / ckl_result_device). */
+CKL_API int ckl_reencode(ckl_ctx* ctx, const void* binary, int binary_on_device, uint64_t num_bytes, int markov_model_order,
+                 uint64_t* out_bytes);
+
 /* ---- z-sharded multi-GPU compress (one context per GPU; the caller moves the small blobs between ranks,
  *      e.g. with torch.distributed all_gather over NCCL).  Mirrors what operations.zstack /
  *      _zstack_flat_labels (crackle/operations.py:258-295, 424-548) do for independently compressed slabs. --- */
