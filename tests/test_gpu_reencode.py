@@ -50,9 +50,9 @@ def test_reencode_v0_stream_and_device_pointers():
     got = cb.reencode(v0, 4)
     assert cb.header(got)["format_version"] == 0 and cb.header(got)["markov_model_order"] == 4
     assert got == to_v0(O.compress(v, 4))
-    ref = O.ref_module()
-    if ref is not None:
-        assert got == bytes(ref.reencode_markov(v0, 4, 1))
+    # (the reference itself writes a 29-byte version-1 header layout under version byte 0 here -- header.tobytes() has one
+    # size, header.hpp:269-273 -- which its own decoder then misreads; the v0 result is therefore pinned by the v0 form of
+    # a fresh encode, not by the reference's output)
     # 1024x1024 slab of the bench volume, stream resident on the device
     ctx = cb.Context(0)
     t = synth.jittered_voronoi_torch((1024, 1024, 8), 24, np.uint64, seed=0, id_bits=40, sz_total=1024)
