@@ -54,6 +54,8 @@ SYMBOLS = {
     "ckl_decompress": (cint, [vp, vp, cint, u64, i64, i64, cint, u64, vp, cint, u64]),
     "ckl_label_stats": (cint, [vp, vp, cint, u64, i64, i64, vp, vp, vp, vp, cint, u64, ctypes.POINTER(u64)]),
     "ckl_reencode": (cint, [vp, vp, cint, u64, cint, ctypes.POINTER(u64)]),
+    "ckl_zstack": (cint, [vp, cint, ctypes.POINTER(vp), ctypes.POINTER(u64), cint, ctypes.POINTER(u64)]),
+    "ckl_zslice": (cint, [vp, vp, cint, u64, u64, u64, ctypes.POINTER(u64)]),
     "ckl_shard_begin": (cint, [vp, vp, cint, cint, u64, u64, u64, ctypes.POINTER(ShardSummary)]),
     "ckl_shard_encode": (cint, [vp, cint, cint, cint, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(u64)]),
     "ckl_shard_unique": (cint, [vp, vp, cint]),

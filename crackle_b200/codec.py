@@ -143,6 +143,22 @@ class Context:
         self._check(_capi.lib().ckl_reencode(self._h, buf.ctypes.data, 0, buf.size, int(markov_model_order), ctypes.byref(n)))
         return self.result_bytes()
 
+    def zstack(self, binaries) -> bytes:
+        """ckl_zstack: flat-label, order-0 streams stacked along z on the device"""
+        bufs = [np.frombuffer(b, dtype=np.uint8) for b in binaries]
+        ptrs = (ctypes.c_void_p * len(bufs))(*[b.ctypes.data for b in bufs])
+        sizes = (ctypes.c_uint64 * len(bufs))(*[b.size for b in bufs])
+        n = ctypes.c_uint64()
+        self._check(_capi.lib().ckl_zstack(self._h, len(bufs), ptrs, sizes, 0, ctypes.byref(n)))
+        return self.result_bytes()
+
+    def zslice(self, binary, z_start: int, z_end: int) -> bytes:
+        """ckl_zslice: the stream of slices [z_start, z_end) with its own label table"""
+        buf = np.frombuffer(binary, dtype=np.uint8)
+        n = ctypes.c_uint64()
+        self._check(_capi.lib().ckl_zslice(self._h, buf.ctypes.data, 0, buf.size, int(z_start), int(z_end), ctypes.byref(n)))
+        return self.result_bytes()
+
     def label_stats(self, binary, z_start=0, z_end=-1):
         """ckl_label_stats: (labels u64[n], counts u64[n], sums u64[n,3], bbox u32[n,6]) for slices [z_start, z_end),
         indexed like the stream's sorted unique label table -- computed from the runs, no volume is painted."""
@@ -267,6 +283,47 @@ def reencode(binary, markov_model_order: int, parallel: int = 0) -> bytes:
         return binary
     with _default_lock:
         return default_context().reencode(binary, markov_model_order)
+
+
+def zstack(images) -> bytes:
+    """crackle.zstack (operations.py:424-548): arrays or streams of equal width and height stacked along z into one
+    stream, without decoding the streams.  Arrays are compressed first, streams re-coded to markov order 0 first."""
+    binaries = []
+    for img in images:
+        if img is None:
+            continue
+        if isinstance(img, np.ndarray):
+            b = compress(img)
+        else:
+            b = reencode(bytes(getattr(img, "binary", img)), 0)
+        if header(b)["sx"] * header(b)["sy"] * header(b)["sz"] == 0:
+            continue
+        binaries.append(b)
+    if len(binaries) == 1:
+        return binaries[0]
+    with _default_lock:
+        return default_context().zstack(binaries)
+
+
+def zsplit(binary, z: int):
+    """crackle.zsplit (operations.py:617-640): (before, middle, after) streams around slice z; an empty side is b''."""
+    sz = header(binary)["sz"]
+    if z < 0 or z >= sz:
+        raise ValueError(f"{z} is outside the range 0 to {sz}.")
+    if sz == 1:
+        return (b"", binary, b"")
+    with _default_lock:
+        ctx = default_context()
+        return (ctx.zslice(binary, 0, z) if z > 0 else b"", ctx.zslice(binary, z, z + 1),
+                ctx.zslice(binary, z + 1, sz) if z + 1 < sz else b"")
+
+
+def zshatter(binary):
+    """crackle.zshatter (operations.py:642-662): one stream per slice."""
+    sz = header(binary)["sz"]
+    with _default_lock:
+        ctx = default_context()
+        return [ctx.zslice(binary, z, z + 1) for z in range(sz)]
 
 
 def _labels_section(binary):

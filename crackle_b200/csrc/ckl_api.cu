@@ -1469,6 +1469,213 @@ extern "C" int ckl_reencode(ckl_ctx* c, const void* binary, int binary_on_device
   API_END(c)
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// zstack / z-range extraction of streams without decoding (crackle/operations.py:424-548 zstack, :258-295
+// _zstack_flat_labels, :551-662 zsplit / zshatter): label tables are merged / re-derived on the device (sort + unique,
+// binary-search keys), crack codes, N_z, z-index entries and slice crcs are byte copies.
+struct FlatStreamView {              // host-side description of one flat-label, order-0, version-1 stream
+  ckl_header_info h;
+  u64 nbytes, nu, n_keys, codes_bytes;
+  u64 off_z, off_lab, off_uniq, off_nz, off_keys, off_codes, off_crcs;
+  int sw, kw, cw;
+  std::vector<u64> code_off;         // sz + 1 offsets relative to off_codes
+  std::vector<u64> key_base;         // sz + 1 prefix of components per slice
+  const u8* dev;                     // device view
+};
+static void ensure_copy(ckl_ctx* c, std::vector<u8>& dst, const u8* hbin, const u8* dbin, u64 off, u64 n) {
+  dst.resize(n ? n : 1);
+  if (!n) return;
+  if (hbin) memcpy(dst.data(), hbin + off, n);
+  else { CUDA_CHECK(cudaMemcpyAsync(dst.data(), dbin + off, n, cudaMemcpyDeviceToHost, c->st)); CUDA_CHECK(cudaStreamSynchronize(c->st)); }
+}
+static FlatStreamView view_flat_stream(ckl_ctx* c, const u8* hbin, const u8* dbin, u64 nbytes, const char* who) {
+  FlatStreamView v;
+  v.nbytes = nbytes; v.dev = dbin;
+  if (nbytes < 29) throw CklError(CKL_ERR_STREAM, "crackle: Input too small to be a valid stream. Bytes: " + std::to_string(nbytes));
+  std::vector<u8> head, zi, small;
+  ensure_copy(c, head, hbin, dbin, 0, 29);
+  std::string perr;
+  int rc = parse_header(head.data(), nbytes, &v.h, perr);
+  if (rc) throw CklError(rc, perr);
+  const ckl_header_info& h = v.h;
+  if (h.format_version != 1) throw CklError(CKL_ERR_UNSUPPORTED, std::string("crackle_b200: ") + who + " needs format version 1 streams");
+  if (h.label_format != 0) throw CklError(CKL_ERR_UNSUPPORTED, std::string("crackle_b200: ") + who + " covers the flat label format; use the reference for pins");
+  if (h.markov_model_order != 0) throw CklError(CKL_ERR_ARG, std::string("crackle_b200: ") + who + " needs markov order 0 streams (ckl_reencode first, like operations.zstack does)");
+  const u64 sz = h.sz, sxy = (u64)h.sx * h.sy;
+  v.off_z = 29; v.off_lab = 29 + 4 * (sz + 1);
+  if (v.off_lab + 8 > nbytes || h.num_label_bytes < 8) throw CklError(CKL_ERR_STREAM, "crackle: labels section too small.");
+  ensure_copy(c, zi, hbin, dbin, v.off_z, 4 * sz);
+  v.code_off.resize(sz + 1);
+  v.code_off[0] = 0;
+  for (u64 z = 0; z < sz; z++) v.code_off[z + 1] = v.code_off[z] + le_host(zi.data() + 4 * z, 4);
+  v.codes_bytes = v.code_off[sz];
+  ensure_copy(c, small, hbin, dbin, v.off_lab, 8);
+  v.nu = le_host(small.data(), 8);
+  v.sw = (int)h.stored_data_width; v.kw = ckl_byte_width(v.nu); v.cw = ckl_byte_width(sxy);
+  v.off_uniq = v.off_lab + 8; v.off_nz = v.off_uniq + v.nu * (u64)v.sw; v.off_keys = v.off_nz + (u64)v.cw * sz;
+  v.off_codes = v.off_lab + h.num_label_bytes; v.off_crcs = v.off_codes + v.codes_bytes + 4;
+  if (v.nu > h.num_label_bytes || v.off_keys > v.off_codes || v.off_crcs + 4 * sz > nbytes)
+    throw CklError(CKL_ERR_STREAM, "crackle: labels section is inconsistent with the header.");
+  v.n_keys = (v.off_codes - v.off_keys) / (u64)v.kw;
+  std::vector<u8> nz;
+  ensure_copy(c, nz, hbin, dbin, v.off_nz, (u64)v.cw * sz);
+  v.key_base.resize(sz + 1);
+  v.key_base[0] = 0;
+  for (u64 z = 0; z < sz; z++) v.key_base[z + 1] = v.key_base[z] + le_host(nz.data() + (u64)v.cw * z, v.cw);
+  if (v.key_base[sz] > v.n_keys) throw CklError(CKL_ERR_STREAM, "crackle: labels section is inconsistent with the header.");
+  return v;
+}
+__global__ void __launch_bounds__(256) k_keys_to_labels(const u64* __restrict__ keys64, u64 n, const u64* __restrict__ uniq64, u64 nu,
+                                                         u64* __restrict__ out) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) { const u64 k = keys64[i]; out[i] = k < nu ? uniq64[k] : 0; }
+}
+// labels of components [k0, k1) of stream v into dst (u64 each)
+static void stream_component_labels(ckl_ctx* c, const FlatStreamView& v, u64 k0, u64 k1, DBuf& uniq64, DBuf& keys64, u64* dst) {
+  const u64 n = k1 - k0;
+  if (!n) return;
+  uniq64.ensure(v.nu * 8 + 8); keys64.ensure(n * 8 + 8);
+  launch_unpack_le(v.dev + v.off_uniq, v.sw, v.nu, uniq64.as<u64>(), c->st);
+  launch_unpack_le(v.dev + v.off_keys + k0 * (u64)v.kw, v.kw, n, keys64.as<u64>(), c->st);
+  k_keys_to_labels<<<(u32)std::min<u64>((n + 255) / 256, 148 * 16), 256, 0, c->st>>>(keys64.as<u64>(), n, uniq64.as<u64>(), v.nu, dst);
+  LAUNCH_CHECK();
+}
+// tail of a stream under construction: header, z-index crc, unique table, labels crc (everything else is already in place)
+static void finish_flat_stream(ckl_ctx* c, u8* R, const ckl_header_info& h0, u32 sz, int data_width, int stored, u64 nu, const u64* guniq,
+                               u64 labels_bytes, u64 off_codes, u64 codes_bytes) {
+  cudaStream_t st = c->st;
+  u8 hb[29];
+  header_bytes_v1(hb, data_width, stored, (int)h0.crack_format, (int)h0.fortran_order, 0, h0.sx, h0.sy, sz, labels_bytes);
+  u32 fmt = (u32)le_host(hb + 5, 2) | ((u32)h0.is_signed << 8) | ((u32)(h0.is_sorted ? 0 : 1) << 13);
+  hb[5] = (u8)fmt; hb[6] = (u8)(fmt >> 8);
+  hb[28] = crc8_header(hb + 5, 23);
+  CUDA_CHECK(cudaMemcpyAsync(R, hb, 29, cudaMemcpyHostToDevice, st));
+  const u64 off_z = 29, off_lab = off_z + 4ull * (sz + 1);
+  c->tmp32.ensure(64);
+  u32* crc_tmp = c->tmp32.as<u32>();
+  launch_crc_bytes(R + off_z, 4ull * sz, c->dtab, c->htab, crc_tmp, st);
+  k_store_bytes_u32<<<1, 1, 0, st>>>(R + off_z + 4ull * sz, crc_tmp);
+  LAUNCH_CHECK();
+  u8 nub[8];
+  for (int i = 0; i < 8; i++) nub[i] = (u8)(nu >> (8 * i));
+  CUDA_CHECK(cudaMemcpyAsync(R + off_lab, nub, 8, cudaMemcpyHostToDevice, st));
+  launch_write_uniq(guniq, nu, stored, R + off_lab + 8, st);
+  launch_crc_bytes(R + off_lab, labels_bytes, c->dtab, c->htab, crc_tmp + 1, st);
+  k_store_bytes_u32<<<1, 1, 0, st>>>(R + off_codes + codes_bytes, crc_tmp + 1);
+  LAUNCH_CHECK();
+}
+static u64 read_max_label(ckl_ctx* c, const u64* guniq, u64 nu) {
+  u64 m = 0;
+  if (nu) { CUDA_CHECK(cudaMemcpyAsync(&m, guniq + nu - 1, 8, cudaMemcpyDeviceToHost, c->st)); CUDA_CHECK(cudaStreamSynchronize(c->st)); }
+  return m;
+}
+
+extern "C" int ckl_zstack(ckl_ctx* c, int n, const void* const* binaries, const uint64_t* sizes, int on_device, uint64_t* out_bytes) {
+  API_BEGIN(c)
+  if (n <= 0 || !binaries || !sizes) throw CklError(CKL_ERR_ARG, "crackle_b200: ckl_zstack: no inputs");
+  cudaStream_t st = c->st;
+  std::vector<FlatStreamView> V;
+  std::vector<DBuf> up(on_device ? 0 : n);
+  u64 sz = 0, ncomp = 0, nloc = 0, codes = 0;
+  int data_width = 1;
+  for (int i = 0; i < n; i++) {
+    const u8* hb = on_device ? nullptr : (const u8*)binaries[i];
+    const u8* db = on_device ? (const u8*)binaries[i] : nullptr;
+    if (!on_device) {
+      up[i].ensure(sizes[i] + 8);
+      CUDA_CHECK(cudaMemcpyAsync(up[i].p, hb, sizes[i], cudaMemcpyHostToDevice, st));
+      db = up[i].as<u8>();
+    }
+    V.push_back(view_flat_stream(c, hb, db, sizes[i], "zstack"));
+    V.back().dev = db;
+    const ckl_header_info &h = V.back().h, &f = V[0].h;
+    if (h.sx != f.sx || h.sy != f.sy)                         // operations.py:471-475
+      throw CklError(CKL_ERR_ARG, "All images must have the same width and height. Expected sx=" + std::to_string(f.sx) + " sy=" +
+                                      std::to_string(f.sy) + " ; Got: sx=" + std::to_string(h.sx) + " sy=" + std::to_string(h.sy));
+    if (h.crack_format != f.crack_format) throw CklError(CKL_ERR_ARG, "All crack formats must match.");
+    if (h.is_signed != f.is_signed) throw CklError(CKL_ERR_ARG, "All binaries must have the same sign.");
+    data_width = std::max(data_width, (int)h.data_width);
+    sz += h.sz; ncomp += V.back().key_base[h.sz]; nloc += V.back().nu; codes += V.back().codes_bytes;
+  }
+  if (sz > 0xFFFFFFFFull) throw CklError(CKL_ERR_ARG, "crackle_b200: dimension exceeds uint32");
+  // merged sorted unique table (operations.py:494-497)
+  c->lb.mapping.ensure(std::max(nloc, ncomp) * 8 + 8);
+  u64 o = 0;
+  for (auto& v : V) { launch_unpack_le(v.dev + v.off_uniq, v.sw, v.nu, c->lb.mapping.as<u64>() + o, st); o += v.nu; }
+  const u64 nu = labels_sort_unique(c->lb, nloc, 8, st);
+  const u64* guniq = c->lb.uniq.as<u64>();
+  const int stored = ckl_byte_width(read_max_label(c, guniq, nu));
+  const int kw = ckl_byte_width(nu), cw = V[0].cw;
+  const u64 labels_bytes = 8 + nu * (u64)stored + sz * (u64)cw + ncomp * (u64)kw;
+  const u64 off_z = 29, off_lab = off_z + 4 * (sz + 1), off_nz = off_lab + 8 + nu * (u64)stored, off_keys = off_nz + sz * (u64)cw;
+  const u64 off_codes = off_lab + labels_bytes, off_crcs = off_codes + codes + 4, total = off_crcs + 4 * sz;
+  c->result.ensure(total + 16);
+  u8* R = c->result.as<u8>();
+  u64 z0 = 0, k0 = 0, c0 = 0;
+  for (auto& v : V) {
+    const u64 szi = v.h.sz, nk = v.key_base[szi];
+    if (szi) {
+      CUDA_CHECK(cudaMemcpyAsync(R + off_z + 4 * z0, v.dev + v.off_z, 4 * szi, cudaMemcpyDeviceToDevice, st));
+      CUDA_CHECK(cudaMemcpyAsync(R + off_nz + z0 * (u64)cw, v.dev + v.off_nz, szi * (u64)cw, cudaMemcpyDeviceToDevice, st));
+      CUDA_CHECK(cudaMemcpyAsync(R + off_crcs + 4 * z0, v.dev + v.off_crcs, 4 * szi, cudaMemcpyDeviceToDevice, st));
+    }
+    if (v.codes_bytes) CUDA_CHECK(cudaMemcpyAsync(R + off_codes + c0, v.dev + v.off_codes, v.codes_bytes, cudaMemcpyDeviceToDevice, st));
+    if (nk) {
+      stream_component_labels(c, v, 0, nk, c->dc.uniq64, c->dc.keys64, c->lb.mapping.as<u64>());
+      launch_write_keys(c->lb.mapping.as<u64>(), nk, guniq, nu, kw, R + off_keys + k0 * (u64)kw, st);
+    }
+    z0 += szi; k0 += nk; c0 += v.codes_bytes;
+  }
+  finish_flat_stream(c, R, V[0].h, (u32)sz, data_width, stored, nu, guniq, labels_bytes, off_codes, codes);
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  c->result_bytes = total;
+  if (out_bytes) *out_bytes = total;
+  API_END(c)
+}
+
+// the stream of slices [z_start, z_end) of `binary`: its own sorted unique table and keys (operations.py:551-615 _zsplit_helper)
+extern "C" int ckl_zslice(ckl_ctx* c, const void* binary, int on_device, uint64_t num_bytes, uint64_t z_start, uint64_t z_end,
+                          uint64_t* out_bytes) {
+  API_BEGIN(c)
+  cudaStream_t st = c->st;
+  const u8* hb = on_device ? nullptr : (const u8*)binary;
+  const u8* db = on_device ? (const u8*)binary : nullptr;
+  if (!on_device) {
+    c->stream_dev.ensure(num_bytes + 8);
+    CUDA_CHECK(cudaMemcpyAsync(c->stream_dev.p, hb, num_bytes, cudaMemcpyHostToDevice, st));
+    db = c->stream_dev.as<u8>();
+  }
+  FlatStreamView v = view_flat_stream(c, hb, db, num_bytes, "zsplit");
+  v.dev = db;
+  if (z_start >= z_end || z_end > v.h.sz) throw CklError(CKL_ERR_ARG, "crackle_b200: ckl_zslice: z-range outside the stream");
+  const u64 sz = z_end - z_start, k0 = v.key_base[z_start], k1 = v.key_base[z_end], nk = k1 - k0;
+  const u64 codes = v.code_off[z_end] - v.code_off[z_start];
+  c->lb.mapping.ensure(nk * 8 + 8);
+  DBuf& labs = c->dc.runLabel;                                 // component labels of the range (kept while mapping is sorted)
+  labs.ensure(nk * 8 + 8);
+  stream_component_labels(c, v, k0, k1, c->dc.uniq64, c->dc.keys64, labs.as<u64>());
+  if (nk) CUDA_CHECK(cudaMemcpyAsync(c->lb.mapping.p, labs.p, nk * 8, cudaMemcpyDeviceToDevice, st));
+  const u64 nu = labels_sort_unique(c->lb, nk, 8, st);
+  const u64* guniq = c->lb.uniq.as<u64>();
+  const int stored = ckl_byte_width(read_max_label(c, guniq, nu));
+  const int kw = ckl_byte_width(nu), cw = v.cw;
+  const u64 labels_bytes = 8 + nu * (u64)stored + sz * (u64)cw + nk * (u64)kw;
+  const u64 off_z = 29, off_lab = off_z + 4 * (sz + 1), off_nz = off_lab + 8 + nu * (u64)stored, off_keys = off_nz + sz * (u64)cw;
+  const u64 off_codes = off_lab + labels_bytes, off_crcs = off_codes + codes + 4, total = off_crcs + 4 * sz;
+  c->result.ensure(total + 16);
+  u8* R = c->result.as<u8>();
+  CUDA_CHECK(cudaMemcpyAsync(R + off_z, v.dev + v.off_z + 4 * z_start, 4 * sz, cudaMemcpyDeviceToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(R + off_nz, v.dev + v.off_nz + z_start * (u64)cw, sz * (u64)cw, cudaMemcpyDeviceToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(R + off_crcs, v.dev + v.off_crcs + 4 * z_start, 4 * sz, cudaMemcpyDeviceToDevice, st));
+  if (codes) CUDA_CHECK(cudaMemcpyAsync(R + off_codes, v.dev + v.off_codes + v.code_off[z_start], codes, cudaMemcpyDeviceToDevice, st));
+  launch_write_keys(labs.as<u64>(), nk, guniq, nu, kw, R + off_keys, st);
+  finish_flat_stream(c, R, v.h, (u32)sz, (int)v.h.data_width, stored, nu, guniq, labels_bytes, off_codes, codes);
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  c->result_bytes = total;
+  if (out_bytes) *out_bytes = total;
+  API_END(c)
+}
+
 // z-chunk pipelining of the single-GPU paths: 0 = automatic (large volumes), 1 = off, K = always K chunks
 extern "C" int ckl_ctx_set_chunks(ckl_ctx* c, int chunks) {
   if (!c || chunks < 0) return CKL_ERR_ARG;

@@ -114,6 +114,16 @@ CKL_API int ckl_label_stats(ckl_ctx* ctx, const void* binary, int binary_on_devi
 CKL_API int ckl_reencode(ckl_ctx* ctx, const void* binary, int binary_on_device, uint64_t num_bytes, int markov_model_order,
                  uint64_t* out_bytes);
 
+/* Stream surgery on the device, no voxel decode (crackle/operations.py:424-548 zstack with :258-295
+ * _zstack_flat_labels; :551-662 zsplit / zshatter through _zsplit_helper): flat-label, markov order 0, format
+ * version 1 streams of equal sx, sy and crack format.  ckl_zstack: the stream of the inputs stacked along z (merged
+ * sorted unique table, keys re-derived by binary search, crack codes / N_z / z-index entries / slice crcs copied).
+ * ckl_zslice: the stream of slices [z_start, z_end) of one input with its own unique table (zsplit(b, z) is the three
+ * ranges [0,z), [z,z+1), [z+1,sz); zshatter one range per slice).  Result: ckl_result_copy / ckl_result_device. */
+CKL_API int ckl_zstack(ckl_ctx* ctx, int n, const void* const* binaries, const uint64_t* sizes, int on_device, uint64_t* out_bytes);
+CKL_API int ckl_zslice(ckl_ctx* ctx, const void* binary, int on_device, uint64_t num_bytes, uint64_t z_start, uint64_t z_end,
+               uint64_t* out_bytes);
+
 /* ---- z-sharded multi-GPU compress (one context per GPU; the caller moves the small blobs between ranks,
  *      e.g. with torch.distributed all_gather over NCCL).  Mirrors what operations.zstack /
  *      _zstack_flat_labels (crackle/operations.py:258-295, 424-548) do for independently compressed slabs. --- */
