@@ -9,6 +9,8 @@
 //   paint                                            src/crackle.hpp:617-656
 // The voxel connectivity graph is kept as two crack bit-planes instead of a byte per pixel: the CCL only reads the
 // "-x" and "-y" passable bits, which are exactly "no vertical crack at column x" / "no horizontal crack above y".
+#include <cstdlib>
+
 #include "ckl_internal.cuh"
 
 static u32 grid1(u64 n, u32 bs, u32 cap_blocks) {
@@ -426,7 +428,7 @@ __device__ __forceinline__ int2 disp_before(const u32* __restrict__ Mz, const u3
 // pass below reads and then overwrites with the segment's start position) and Q at the segment's first codepoint
 __global__ void __launch_bounds__(256) k_dec_evsum(const DecSlice* __restrict__ ds, u32 sz, const u32* __restrict__ Mw, const u32* __restrict__ Sw,
                                                     const int2* __restrict__ Qw, const u64* __restrict__ evOff, const u32* __restrict__ evIdx,
-                                                    int2* __restrict__ segStart, int2* __restrict__ segQ) {
+                                                    int2* __restrict__ segStart, int2* __restrict__ segQ, int2* __restrict__ segSum) {
   for (u32 z = blockIdx.y; z < sz; z += gridDim.y) {
     const DecSlice d = ds[z];
     const u64 e0 = evOff[z];
@@ -439,7 +441,8 @@ __global__ void __launch_bounds__(256) k_dec_evsum(const DecSlice* __restrict__ 
       const u32 first = j ? (evIdx[e0 + j - 1] & 0x3FFFFFFFu) + 1 : 0u;
       const int2 qf = disp_before(Mz, Sz, Qz, first);
       const int2 ql = disp_before(Mz, Sz, Qz, ei - 1);       // the codepoint before an event is the dropped first-of-pair
-      segStart[e0 + j] = make_int2(ql.x - qf.x, ql.y - qf.y);
+      const int2 sum = make_int2(ql.x - qf.x, ql.y - qf.y);
+      segSum[e0 + j] = sum;
       segQ[e0 + j] = qf;
     }
   }
@@ -457,15 +460,19 @@ __device__ __forceinline__ int2 dec_lds64(u32 a) {
   return v;
 }
 __device__ __forceinline__ void dec_sts64(u32 a, int2 v) { asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
-__global__ void __launch_bounds__(32) k_dec_chain(Geom g, const DecSlice* __restrict__ ds, const u8* __restrict__ stream,
+// Serial form of the chain pass: the fallback for slices the warp-parallel kernel below hands back (`redo[z]`; the segment
+// sums it needs are kept in segSum).
+__global__ void __launch_bounds__(32) k_dec_chain_serial(Geom g, const DecSlice* __restrict__ ds, const u8* __restrict__ stream,
                                                    const u32* __restrict__ Mw, const u32* __restrict__ Sw, const int2* __restrict__ Qw,
                                                    const u64* __restrict__ evOff, const u32* __restrict__ evIdx,
                                                    int2* __restrict__ segStart, int2* __restrict__ segQ, int2* __restrict__ gstack,
-                                                   u32* __restrict__ nevUsed, ull* scal) {
+                                                   u32* __restrict__ nevUsed, const u32* __restrict__ redo, const int2* __restrict__ segSum,
+                                                   ull* scal) {
   __shared__ int2 sstack[DEC_STACK];
   __shared__ int2 s_sum[32], s_start[32];
   __shared__ u32 s_used;
   const u32 z = blockIdx.x, lane = threadIdx.x;
+  if (!redo[z]) return;
   const DecSlice d = ds[z];
   const u64 e0 = evOff[z];
   const u32 nev = (u32)(evOff[z + 1] - e0);
@@ -491,13 +498,13 @@ __global__ void __launch_bounds__(32) k_dec_chain(Geom g, const DecSlice* __rest
   // the next batch's inputs are loaded before the serial pass over the current one (one coalesced load each)
   int2 nsum = make_int2(0, 0);
   u32 nev_w = 0;
-  if (lane < nev) { nsum = segStart[e0 + lane]; nev_w = evIdx[e0 + lane]; }
+  if (lane < nev) { nsum = segSum[e0 + lane]; nev_w = evIdx[e0 + lane]; }
   for (u32 base = 0; base < nev; base += 32) {
     const u32 j = base + lane;
     const int2 csum = nsum;
     const u32 m = nev_w >> 30;
     const bool is_t = j < nev && (m == 0 || m == 3);
-    if (j + 32 < nev) { nsum = segStart[e0 + j + 32]; nev_w = evIdx[e0 + j + 32]; }
+    if (j + 32 < nev) { nsum = segSum[e0 + j + 32]; nev_w = evIdx[e0 + j + 32]; }
     s_sum[lane] = csum;
     const u32 tmask = __ballot_sync(FULL_MASK, is_t);
     __syncwarp();
@@ -535,6 +542,118 @@ __global__ void __launch_bounds__(32) k_dec_chain(Geom g, const DecSlice* __rest
     __syncwarp();
   }
   if (lane == 0) nevUsed[z] = s_used;
+}
+
+// Warp-parallel chain pass.  The serial dependency of the pass is the revisit stack: after a 't' the position is the one
+// its matching 'b' pushed.  32 events at a time: bracket matching inside the batch (the match of a 't' is the event after the
+// nearest earlier event whose depth is not above the depth after the 't'; deeper pops come from the stack the batch was
+// entered with), which makes every event's position "the position after some earlier event (+ its own segment)" -- a
+// forest of depth <= 32, resolved with five rounds of pointer jumping through shuffles.  'b's left open at the end of the
+// batch go onto the stack.  A chain ends at the 't' that finds the stack empty; the batch is split there and the next start
+// vertex read from the beginning-of-chain index.  The reference's push quirk (a position with x == sx is stored as (0, y+1),
+// crackcodes.hpp:772,850) is not linear: a slice where it occurs is handed to the serial kernel (`redo`).
+#define DCH_SMEM 3072           // stack entries held in shared memory (deeper entries live in global memory)
+#define DCH_ROOT 32u
+#define DCH_ABS 33u
+__global__ void __launch_bounds__(32) k_dec_chain(Geom g, const DecSlice* __restrict__ ds, const u8* __restrict__ stream,
+                                                   const u64* __restrict__ evOff, const u32* __restrict__ evIdx,
+                                                   int2* __restrict__ segStart, const int2* __restrict__ segSum, int2* __restrict__ gstack,
+                                                   u32* __restrict__ nevUsed, u32* __restrict__ redo, ull* scal, const bool force_serial) {
+  __shared__ int2 sstack[DCH_SMEM];
+  const u32 z = blockIdx.x, lane = threadIdx.x;
+  const DecSlice d = ds[z];
+  const u64 e0 = evOff[z];
+  const u32 nev = (u32)(evOff[z + 1] - e0);
+  const int xw = ckl_byte_width((u64)g.sx + 1), yw = ckl_byte_width((u64)g.sy + 1);
+  BocIter it;
+  {
+    const u8* code = stream + d.code;
+    it.p = code; it.idx = 4; it.end = d.isz; it.xw = xw; it.yw = yw; it.sxe = g.sx + 1;
+    it.ny = d.isz >= (u32)(4 + yw) ? (u32)ld_le(code + 4, yw) : 0u; it.idx += yw; it.yi = 0; it.nx = 0; it.y = 0; it.x = 0;
+  }
+  int2* gst = gstack + e0;
+  int curx = 0, cury = 0;
+  u32 sp = 0, used = nev;
+  bool open = false, quirk = false;
+  for (u32 base = 0; base < nev && used == nev; base += 32) {
+    const u32 j = base + lane;
+    const bool valid = j < nev;
+    const u32 m = valid ? evIdx[e0 + j] >> 30 : 1u;
+    const bool isT = valid && (m == 0 || m == 3), isB = valid && !isT;
+    const int2 sum = valid ? segSum[e0 + j] : make_int2(0, 0);
+    u32 lo = 0;
+    while (lo < 32 && base + lo < nev) {
+      if (!open) {                                         // next chain: start vertex from the BOC index (lane 0 reads it)
+        u32 vx = 0, vy = 0, ok = 0;
+        if (lane == 0) ok = it.next(vx, vy) ? 1u : 0u;
+        ok = __shfl_sync(FULL_MASK, ok, 0); vx = __shfl_sync(FULL_MASK, vx, 0); vy = __shfl_sync(FULL_MASK, vy, 0);
+        if (!ok || vx > g.sx || vy > g.sy) {
+          if (ok && lane == 0) atomicExch(&scal[SC_ERROR], 11ull);
+          used = base + lo;
+          break;
+        }
+        curx = (int)vx; cury = (int)vy; sp = 0; open = true;
+      }
+      const bool act = valid && lane >= lo;
+      const u32 bm = __ballot_sync(FULL_MASK, isB && act), tm = __ballot_sync(FULL_MASK, isT && act);
+      const u32 upto = ((2u << lane) - 1u) & ~((1u << lo) - 1u);
+      const int v = (int)__popc(bm & upto) - (int)__popc(tm & upto);          // depth after this event, relative to the batch entry
+      const u32 endm = __ballot_sync(FULL_MASK, act && isT && (int)sp + v < 0); // a 't' that finds the stack empty ends the chain
+      const u32 hi = endm ? (u32)__ffs(endm) - 1u : 31u;
+      const bool on = act && lane <= hi;
+      // nearest earlier active event whose depth is <= this one's (brute force over the 31 distances)
+      int found = -1;
+#pragma unroll
+      for (u32 step = 1; step < 32; step++) {
+        const int c = __shfl_up_sync(FULL_MASK, v, step);
+        if (found < 0 && lane >= lo + step && c <= v) found = (int)(lane - step);
+      }
+      u32 par = DCH_ABS;
+      int offx = 0, offy = 0;
+      u32 mlane = 32;                                      // the in-batch 'b' a 't' returns to
+      if (on && isB) { par = lane == lo ? DCH_ROOT : lane - 1; offx = sum.x; offy = sum.y; }
+      else if (on && isT) {
+        if (found >= 0) mlane = (u32)found + 1u;
+        else if (v >= 0) mlane = lo;
+        if (mlane < 32) par = mlane;
+        else if ((int)sp + v >= 0) {                       // from the stack the batch was entered with
+          const u32 si = sp + (u32)v;
+          const int2 q = si < DCH_SMEM ? sstack[si] : gst[si - DCH_SMEM];
+          offx = q.x; offy = q.y;
+        }
+      }
+      if (on && isT && endm && lane == hi) { par = DCH_ABS; mlane = 32; }       // the chain-ending 't': its position is not used
+      const u32 matched = __reduce_or_sync(FULL_MASK, mlane < 32 ? 1u << mlane : 0u);
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        const u32 src = par & 31u;
+        const int px = __shfl_sync(FULL_MASK, offx, src), py = __shfl_sync(FULL_MASK, offy, src);
+        const u32 pp = __shfl_sync(FULL_MASK, par, src);
+        if (par < 32) { offx += px; offy += py; par = pp; }
+      }
+      const int ax = (par == DCH_ROOT ? curx : 0) + offx, ay = (par == DCH_ROOT ? cury : 0) + offy;    // position after the event
+      // the push quirk: a pushed position with x == sx would come back as (0, y + 1)
+      if (__any_sync(FULL_MASK, on && isB && ax == (int)g.sx)) { quirk = true; break; }
+      int bx = __shfl_up_sync(FULL_MASK, ax, 1), by = __shfl_up_sync(FULL_MASK, ay, 1);
+      if (lane == lo) { bx = curx; by = cury; }
+      if (on) segStart[e0 + j] = make_int2(bx, by);
+      __syncwarp();                                        // stack reads above, stack writes below
+      if (on && isB && !((matched >> lane) & 1u)) {        // still open at the end of the batch
+        const u32 si = sp + (u32)v - 1u;
+        if (si < DCH_SMEM) sstack[si] = make_int2(ax, ay); else gst[si - DCH_SMEM] = make_int2(ax, ay);
+      }
+      __syncwarp();
+      if (endm) { open = false; sp = 0; lo = hi + 1; }
+      else {
+        const u32 last = min(31u, nev - 1u - base);        // last valid lane of the batch
+        sp = (u32)((int)sp + __shfl_sync(FULL_MASK, v, last));
+        curx = __shfl_sync(FULL_MASK, ax, last); cury = __shfl_sync(FULL_MASK, ay, last);
+        lo = 32;
+      }
+    }
+    if (quirk) break;
+  }
+  if (lane == 0) { nevUsed[z] = used; redo[z] = (quirk || force_serial) ? 1u : 0u; }
 }
 
 // marking: one thread per 16-codepoint word (uniform work).  Position at the word start = start of the segment the
@@ -667,6 +786,8 @@ void launch_decode_mark(const Geom& g, const u8* stream, int order, DecodeBufs& 
   D.segQ.ensure(total_events * 8 + 16);
   D.segStart.ensure(total_events * 8 + 16);
   D.gstack.ensure(total_events * 8 + 16);
+  D.segSum.ensure(total_events * 8 + 16);
+  D.redo.ensure((u64)g.sz * 4 + 16);
   const DecSlice* ds = D.slices.as<DecSlice>();
   k_dec_compact<<<dec_grid(g.sz, 1, 8), 256, 0, st>>>(ds, g.sz, order, D.ncp.as<u32>(), D.Mw.as<u32>(), D.Sw.as<u32>(), D.evOff.as<u64>(),
                                                       D.evIdx.as<u32>(), D.evBaseW.as<u32>());
@@ -678,11 +799,19 @@ void launch_decode_mark(const Geom& g, const u8* stream, int order, DecodeBufs& 
     if (gx < 1) gx = 1;
     k_dec_evsum<<<dim3(gx, g.sz < 65535u ? g.sz : 65535u), 256, 0, st>>>(ds, g.sz, D.Mw.as<u32>(), D.Sw.as<u32>(), D.Qw.as<int2>(),
                                                                           D.evOff.as<u64>(), D.evIdx.as<u32>(), D.segStart.as<int2>(),
-                                                                          D.segQ.as<int2>());
+                                                                          D.segQ.as<int2>(), D.segSum.as<int2>());
     LAUNCH_CHECK();
   }
-  k_dec_chain<<<g.sz, 32, 0, st>>>(g, ds, stream, D.Mw.as<u32>(), D.Sw.as<u32>(), D.Qw.as<int2>(), D.evOff.as<u64>(), D.evIdx.as<u32>(),
-                                   D.segStart.as<int2>(), D.segQ.as<int2>(), D.gstack.as<int2>(), D.nevUsed.as<u32>(), scal);
+  // k_dec_evsum left the segment sums in segSum; the chain pass turns them into segment start positions
+  static int force_env = -1;      // test hook: every slice takes the serial fallback (tests/test_gpu_parity.py)
+  if (force_env < 0) { const char* e = getenv("CKL_TEST_SERIAL_CHAIN"); force_env = (e && atoi(e) > 0) ? 1 : 0; }
+  const bool force_serial = force_env == 1;
+  k_dec_chain<<<g.sz, 32, 0, st>>>(g, ds, stream, D.evOff.as<u64>(), D.evIdx.as<u32>(), D.segStart.as<int2>(), D.segSum.as<int2>(),
+                                   D.gstack.as<int2>(), D.nevUsed.as<u32>(), D.redo.as<u32>(), scal, force_serial);
+  LAUNCH_CHECK();
+  k_dec_chain_serial<<<g.sz, 32, 0, st>>>(g, ds, stream, D.Mw.as<u32>(), D.Sw.as<u32>(), D.Qw.as<int2>(), D.evOff.as<u64>(), D.evIdx.as<u32>(),
+                                          D.segStart.as<int2>(), D.segQ.as<int2>(), D.gstack.as<int2>(), D.nevUsed.as<u32>(), D.redo.as<u32>(),
+                                          D.segSum.as<int2>(), scal);
   LAUNCH_CHECK();
   const u64 per_slice = (total_words + g.sz - 1) / g.sz;
   u32 gx = (u32)((per_slice + 255) / 256);

@@ -110,7 +110,8 @@ struct DecodeBufs {
   DBuf fields;      // order > 0: packed 2-bit difference fields (u32 per 16)
   DBuf Mw, Sw, Qw, evBaseW;   // per 16-codepoint word: absolute moves, event mask, displacement prefix, events before
   DBuf nev, ncp, evOff, nevUsed;   // per slice
-  DBuf evIdx, segQ, segStart, gstack;   // per event
+  DBuf evIdx, segQ, segStart, gstack, segSum;   // per event
+  DBuf redo;        // per slice: the chain pass must be redone by the serial kernel
   DBuf codeOff;     // u64 x (szr+1): absolute offsets of each decoded slice's crack code inside the stream
   DBuf keyBase;     // u64 x szr: first key index of each decoded slice
   DBuf storedNz;    // u32 x szr

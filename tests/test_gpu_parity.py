@@ -381,3 +381,23 @@ def test_decoder_rejects_markov_orders_it_cannot_hold(ctx):
     b[28] = O.lib().ckl_oracle_crc8((ctypes.c_char * 23).from_buffer(b, 5), 23)
     with pytest.raises(RuntimeError, match="markov_model_order 13"):
         cb.decompress(bytes(b))
+
+
+def test_serial_chain_fallback_of_the_decoder():
+    # the warp-parallel chain pass hands a slice back to the serial kernel when the reference's push quirk (x == sx) occurs,
+    # which no encoder-made stream triggers: the test hook sends every slice down that path (fresh process: read once)
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = ("import numpy as np, crackle_b200 as cb\n"
+            "from crackle_b200 import synth\n"
+            "from oracle import oracle as O\n"
+            "for v in (synth.jittered_voronoi((192, 160, 6), 20, np.uint64, seed=11), synth.random_blobs((61, 47, 6), 9, np.uint16, seed=3),\n"
+            "          np.asfortranarray(np.random.default_rng(1).integers(0, 30, (70, 50, 3)).astype(np.uint8))):\n"
+            "    for order in (0, 4):\n"
+            "        assert np.array_equal(cb.decompress(O.compress(v, order)).reshape(v.shape), v)\n"
+            "print('SERIAL CHAIN OK')\n")
+    env = dict(os.environ, CKL_TEST_SERIAL_CHAIN="1", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0 and "SERIAL CHAIN OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
