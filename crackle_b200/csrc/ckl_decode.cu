@@ -310,6 +310,152 @@ __global__ void __launch_bounds__(32) k_dec_markov(const DecSlice* __restrict__ 
   ncpOut[z] = (u32)n;
 }
 
+// ---- order > 0, parallel form -------------------------------------------------------------------------------
+// The code 0 / 10 / 110 / 111 (ranks 0..3, markov.hpp:444-458) is self-synchronising: a 0 bit always ends a code, and ones
+// after a boundary are consumed three at a time, so the parser state at any bit position is (length of the run of ones
+// right before it, not reaching below bit 2) mod 3 -- a local computation.  Pass 1 (k_mk_scan): per 32-bit word of a
+// slice's bitstream, entry state and number of codes that START in the word; a block scan numbers the symbols.  Pass 2
+// (k_mk_decode): 256 threads per slice decode disjoint word ranges.  The context chain (symbol -> context -> model row ->
+// next symbol) is the one truly serial thing: every thread first guesses its entry context by decoding a warm-up stretch
+// before its range, then the guesses are checked against the exit context of the thread before and wrong ones redone until
+// all agree -- the result is exactly the serial decode (markov.hpp:268-323), whatever the guesses were.
+struct MkCursor {
+  u64 wi;            // next word to fetch
+  u32 cur, nxt, bp;  // window = (nxt : cur) >> bp
+};
+__device__ __forceinline__ void mk_seek(MkCursor& c, const DecSlice& d, const u8* __restrict__ stream, u32 pos) {
+  const u64 w = pos >> 5;
+  c.cur = dec_word(d, stream, nullptr, 0, w); c.nxt = dec_word(d, stream, nullptr, 0, w + 1); c.wi = w + 2; c.bp = pos & 31u;
+}
+// length and rank of the code at the cursor: 0 -> (1, 0); 10 -> (2, 1); 110 -> (3, 2); 111 -> (3, 3)
+__device__ __forceinline__ void mk_peek(const MkCursor& c, u32& len, u32& rank) {
+  const u32 v2 = (__funnelshift_r(c.cur, c.nxt, c.bp) & 7u) * 2u;
+  len = (0xD9D9u >> v2) & 3u; rank = (0xC484u >> v2) & 3u;
+}
+__device__ __forceinline__ void mk_skip(MkCursor& c, const DecSlice& d, const u8* __restrict__ stream, u32 len) {
+  c.bp += len;
+  if (c.bp >= 32) { c.bp -= 32; c.cur = c.nxt; c.nxt = dec_word(d, stream, nullptr, 0, c.wi++); }
+}
+// parser state at the start of word w (w >= 1): run of ones ending at bit 32 w - 1, not reaching below bit 2
+__device__ __forceinline__ u32 mk_entry_state(const DecSlice& d, const u8* __restrict__ stream, u64 w) {
+  u32 run = 0;
+  for (u64 q = w; q > 0;) {
+    q--;
+    u32 x = dec_word(d, stream, nullptr, 0, q);
+    if (q == 0) x &= ~3u;                                       // the two raw bits of the first symbol are a boundary
+    const u32 ones = __clz(~x);                                 // leading (most significant = latest) ones of the word
+    run += ones;
+    if (ones < 32) break;
+  }
+  return run % 3u;
+}
+#define MK_WORD_STATE_SHIFT 30
+__global__ void __launch_bounds__(256) k_mk_scan(const DecSlice* __restrict__ ds, u32 sz, const u8* __restrict__ stream,
+                                                  u32* __restrict__ wordSym, u32* __restrict__ ncpOut) {
+  __shared__ u32 sm[33];
+  for (u32 z = blockIdx.x; z < sz; z += gridDim.x) {
+    const DecSlice d = ds[z];
+    const u32 nbits = d.blen * 8u;
+    const u32 nW = (d.blen + 3u) / 4u;
+    u32* ws = wordSym + d.wordOff;
+    u32 carry = 0;
+    for (u32 w0 = 0; w0 < nW; w0 += blockDim.x) {
+      const u32 w = w0 + threadIdx.x;
+      u32 cnt = 0, st = 0;
+      if (w < nW) {
+        u32 pos = 2;
+        if (w > 0) { st = mk_entry_state(d, stream, w); pos = 32u * w - st; }
+        MkCursor c;
+        mk_seek(c, d, stream, pos);
+        u32 len, rank;
+        if (w > 0 && st > 0) { mk_peek(c, len, rank); mk_skip(c, d, stream, len); pos += len; }      // the code straddling in from the word before
+        const u32 end = min(32u * (w + 1u), nbits);
+        while (pos < end) { mk_peek(c, len, rank); mk_skip(c, d, stream, len); pos += len; cnt++; }
+      }
+      u32 tot;
+      const u32 ex = carry + block_excl_scan(cnt, sm, tot);
+      if (w < nW) ws[w] = ex | (st << MK_WORD_STATE_SHIFT);
+      carry += tot;
+    }
+    if (threadIdx.x == 0) ncpOut[z] = d.blen ? carry + 1u : 0u;      // + the first symbol (two raw bits)
+    __syncthreads();
+  }
+}
+
+// codes that start in words [a, b) of the slice, decoded from entry context ctx4 (pre-multiplied by 4); returns the exit context
+template <bool WRITE>
+__device__ __forceinline__ u32 mk_run(const DecSlice& d, const u8* __restrict__ stream, const u32* __restrict__ ws, u32 a, u32 b, u32 nbits,
+                                      u32 ctx4, const u8* mdl, u32 top2, u32* __restrict__ out) {
+  if (a >= b) return ctx4;
+  u32 pos = 2, st = 0;
+  if (a > 0) { st = ws[a] >> MK_WORD_STATE_SHIFT; pos = 32u * a - st; }
+  MkCursor c;
+  mk_seek(c, d, stream, pos);
+  u32 len, rank;
+  if (a > 0 && st > 0) { mk_peek(c, len, rank); mk_skip(c, d, stream, len); pos += len; }
+  const u32 end = min(32u * b, nbits);
+  u32 idx = 1u + (ws[a] & ((1u << MK_WORD_STATE_SHIFT) - 1u));
+  u32 acc = 0, accw = idx >> 4;
+  while (pos < end) {
+    mk_peek(c, len, rank);
+    const u32 dsym = mdl[ctx4 + rank];
+    ctx4 = ((ctx4 >> 2) & ~3u) + (dsym << top2);
+    if (WRITE) {
+      if ((idx >> 4) != accw) { if (acc) atomicOr(out + accw, acc); acc = 0; accw = idx >> 4; }
+      acc |= dsym << (2u * (idx & 15u));
+    }
+    idx++;
+    mk_skip(c, d, stream, len);
+    pos += len;
+  }
+  if (WRITE && acc) atomicOr(out + accw, acc);
+  return ctx4;
+}
+#define MK_WARM 3u            // words of warm-up before a thread's range (about 60 symbols)
+__global__ void __launch_bounds__(256) k_mk_decode(const DecSlice* __restrict__ ds, u32 sz, const u8* __restrict__ stream, int order,
+                                                    const u8* __restrict__ model, const u32* __restrict__ wordSym, u32* __restrict__ fields) {
+  __shared__ u8 smodel[DECODE_SMEM_MODEL];
+  __shared__ u32 s_end[256];
+  const u64 mbytes = 4ull << (2 * order);      // order <= 12 (checked by the caller)
+  const bool msm = mbytes <= DECODE_SMEM_MODEL;
+  if (msm) for (u32 i = threadIdx.x; i < mbytes; i += blockDim.x) smodel[i] = model[i];
+  __syncthreads();
+  const u8* mdl = msm ? smodel : model;
+  const u32 top2 = 2 * (order - 1) + 2;
+  const u32 t = threadIdx.x;
+  for (u32 z = blockIdx.x; z < sz; z += gridDim.x) {
+    const DecSlice d = ds[z];
+    const u32 nbits = d.blen * 8u;
+    const u32 nW = (d.blen + 3u) / 4u;
+    const u32* ws = wordSym + d.wordOff;
+    u32* out = fields + d.wordOff;
+    if (nW) {
+      const u32 first = dec_word(d, stream, nullptr, 0, 0) & 3u;      // first symbol: two raw bits; it seeds the context
+      const u32 ctx0 = first << top2;
+      if (t == 0) atomicOr(out, first);
+      const u32 wpt = (nW + blockDim.x - 1) / blockDim.x;
+      const u32 a = min(nW, t * wpt), b = min(nW, a + wpt);
+      // entry context: exact for the thread that starts the stream, a warm-up guess for the others
+      u32 start = ctx0;
+      if (a > 0) {
+        const u32 aw = a > MK_WARM ? a - MK_WARM : 0u;
+        start = mk_run<false>(d, stream, ws, aw, a, nbits, aw == 0 ? ctx0 : 0u, mdl, top2, nullptr);
+      }
+      u32 endc = mk_run<false>(d, stream, ws, a, b, nbits, start, mdl, top2, nullptr);
+      for (;;) {                                                      // settle: entry context == exit context of the thread before
+        s_end[t] = endc;
+        __syncthreads();
+        const u32 want = t == 0 ? ctx0 : s_end[t - 1];
+        const bool redo = want != start;
+        if (redo) { start = want; endc = mk_run<false>(d, stream, ws, a, b, nbits, start, mdl, top2, nullptr); }
+        if (!__syncthreads_or(redo ? 1 : 0)) break;
+      }
+      mk_run<true>(d, stream, ws, a, b, nbits, start, mdl, top2, out);
+    }
+    __syncthreads();
+  }
+}
+
 // displacement of the non-event fields [0, nf) of a word (moves: 0 up, 1 right, 2 down, 3 left), packed dy * 65536 + dx
 __device__ __forceinline__ int word_disp(u32 M, u32 S, u32 nf) {
   u32 rm = L5 & ~S;
@@ -767,7 +913,11 @@ void launch_decode_classify(const Geom& g, const u8* stream, int order, const u8
   const DecSlice* ds = D.slices.as<DecSlice>();
   if (order > 0) {
     D.fields.ensure(total_words * 4 + 16);
-    k_dec_markov<<<g.sz, 32, 0, st>>>(ds, g.sz, stream, order, model, D.fields.as<u32>(), D.ncp.as<u32>());
+    // evBaseW is free until k_dec_compact: it holds the per-word symbol numbering of the bitstreams meanwhile
+    CUDA_CHECK(cudaMemsetAsync(D.fields.p, 0, total_words * 4, st));
+    k_mk_scan<<<dec_grid(g.sz, 1, 8), 256, 0, st>>>(ds, g.sz, stream, D.evBaseW.as<u32>(), D.ncp.as<u32>());
+    LAUNCH_CHECK();
+    k_mk_decode<<<dec_grid(g.sz, 1, 8), 256, 0, st>>>(ds, g.sz, stream, order, model, D.evBaseW.as<u32>(), D.fields.as<u32>());
     LAUNCH_CHECK();
   }
   k_dec_classify<<<dec_grid(g.sz, 1, 8), 256, 0, st>>>(ds, g.sz, stream, D.fields.as<u32>(), order, D.ncp.as<u32>(), D.Mw.as<u32>(),
