@@ -118,6 +118,123 @@ __global__ void __launch_bounds__(256) k_edges(const T* __restrict__ L, Geom g, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TMA-staged form of the edge kernel (sx a multiple of 256, uint32 / uint64): a warp owns a band of 256 pixels and walks
+// down a range of rows.  Rows arrive through the bulk-copy engine -- one cp.async.bulk of 2 KB (+ 16 bytes before the band,
+// which holds the left neighbour of its first pixel) per row into a per-warp ring of EDT_STAGES shared-memory stages, each
+// with its own mbarrier -- so the bytes in flight (stages x 2 KB per warp, ~190 KB per SM) do not occupy registers and no
+// lane computes a load address.  The consumer side is lane <-> pixel: conflict-free ld.shared of the pixel and of its left
+// neighbour (no shuffles), ballots against the previous row held in registers, and the band's 8 + 8 plane words of a row
+// leave as two 32-byte stores.  The warp is its own producer: after a row has been compared its stage is re-armed with the
+// row EDT_STAGES further down.
+#define EDT_WORDS 8
+#define EDT_STAGES 6
+#define EDT_ROWS 256
+#define EDT_WARPS 4
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+template <typename T> __device__ __forceinline__ T lds_t(u32 a) {
+  if constexpr (sizeof(T) == 8) { ull v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return (T)v; }
+  else { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return (T)v; }
+}
+template <typename T>
+__global__ void __launch_bounds__(32 * EDT_WARPS) k_edges_tma(const T* __restrict__ L, Geom g, u32* __restrict__ DV, u32* __restrict__ DH, ull* scal) {
+  constexpr u32 ROWB = 32 * EDT_WORDS * sizeof(T), STAGEB = ROWB + 16;
+  extern __shared__ __align__(128) u8 edt_smem[];
+  __shared__ __align__(8) u64 bars[EDT_WARPS][EDT_STAGES];
+  const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const u32 ring = (u32)__cvta_generic_to_shared(edt_smem) + wib * (EDT_STAGES * STAGEB);
+  const u32 bar0 = (u32)__cvta_generic_to_shared(&bars[wib][0]);
+  if (lane == 0)
+    for (u32 s0 = 0; s0 < EDT_STAGES; s0++) mbar_init(bar0 + 8 * s0, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  const u64 nwarps = (u64)gridDim.x * EDT_WARPS;
+  const u32 nband = g.sx / (32 * EDT_WORDS), nrange = (g.sy + EDT_ROWS - 1) / EDT_ROWS;
+  const u64 items = (u64)g.sz * nrange * nband;
+  u64 orall = 0, pairs = 0;
+  u32 n = 0;                                               // rows consumed by this warp so far: stage = n % STAGES, parity = (n / STAGES) & 1
+  for (u64 it = (u64)blockIdx.x * EDT_WARPS + wib; it < items; it += nwarps) {
+    const u32 band = (u32)(it % nband);
+    const u64 t2 = it / nband;
+    const u32 range = (u32)(t2 % nrange), z = (u32)(t2 / nrange);
+    const u32 y0 = range * EDT_ROWS, y1 = min(g.sy, y0 + EDT_ROWS);
+    const u32 w0 = band * EDT_WORDS;
+    const T* col = L + (u64)z * g.sxy + (u64)w0 * 32;
+    // producer: row y of the band into stage (n + (y - y0)) % STAGES; the 16 bytes before the band come along (not for flat index 0)
+    auto issue = [&](u32 y, u32 slot) {
+      const u32 st = slot % EDT_STAGES;
+      const bool first = (w0 | y | z) == 0;
+      const T* src = col + (u64)y * g.sx;
+      const u32 bytes = first ? ROWB : STAGEB;
+      mbar_expect_tx(bar0 + 8 * st, bytes);
+      bulk_g2s(ring + st * STAGEB + (first ? 16u : 0u), first ? (const void*)src : (const void*)((const u8*)src - 16), bytes, bar0 + 8 * st);
+    };
+    if (lane == 0)
+      for (u32 k = 0; k < EDT_STAGES && y0 + k < y1; k++) issue(y0 + k, n + k);
+    T up[EDT_WORDS];
+#pragma unroll
+    for (int j = 0; j < EDT_WORDS; j++) up[j] = y0 > 0 ? col[(u64)(y0 - 1) * g.sx + 32 * j + lane] : (T)0;
+    u32 neq = 0;
+    for (u32 y = y0; y < y1; y++, n++) {
+      const u32 st = n % EDT_STAGES;
+      mbar_wait(bar0 + 8 * st, (n / EDT_STAGES) & 1u);
+      const u32 base = ring + st * STAGEB + 16 + lane * (u32)sizeof(T);
+      const bool has_prev = (w0 | y | z) != 0;
+      u32 mydv = 0, mydh = 0;
+#pragma unroll
+      for (int j = 0; j < EDT_WORDS; j++) {
+        const T v = lds_t<T>(base + j * 32 * (u32)sizeof(T));
+        const T l = lds_t<T>(base + j * 32 * (u32)sizeof(T) - (u32)sizeof(T));
+        u32 vb = __ballot_sync(FULL_MASK, v != l);
+        u32 hb = __ballot_sync(FULL_MASK, v != up[j]);
+        if (j == 0 && !has_prev) vb |= 1u;                  // flat index 0 has no predecessor: not an equal pair (its pad is stale)
+        neq += __popc(vb);
+        if (j == 0 && w0 == 0) vb &= ~1u;                   // column 0 has no left neighbour inside its row
+        if (y == 0) hb = 0;
+        if (lane == (u32)j) mydv = vb;
+        if (lane == (u32)j + EDT_WORDS) mydh = hb;
+        orall |= (u64)v;
+        up[j] = v;
+      }
+      const u64 o = ((u64)z * g.sy + y) * g.W + w0;
+      if (lane < EDT_WORDS) DV[o + lane] = mydv;
+      else if (lane < 2 * EDT_WORDS) DH[o + lane - EDT_WORDS] = mydh;
+      __syncwarp();                                         // every lane has consumed the stage (the values above are in use)
+      if (lane == 0 && y + EDT_STAGES < y1) issue(y + EDT_STAGES, n + EDT_STAGES);
+    }
+    pairs += (u64)(32 * EDT_WORDS) * (y1 - y0) - neq;       // warp-uniform
+  }
+  __shared__ u64 s_or[EDT_WARPS], s_pr[EDT_WARPS];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) orall |= (u64)__shfl_xor_sync(FULL_MASK, (ull)orall, o);
+  if (lane == 0) { s_or[wib] = orall; s_pr[wib] = pairs; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (u32 i = 1; i < EDT_WARPS; i++) { orall |= s_or[i]; pairs += s_pr[i]; }
+    atomicOr(&scal[SC_MAX], (ull)orall);
+    atomicAdd(&scal[SC_PAIRS], (ull)pairs);
+  }
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -141,6 +258,21 @@ void launch_edges(const void* labels, int width, const Geom& g, u32* DV, u32* DH
   // (250 registers); CKL_EDGES_VARIANT = 1 / 2 / 3 selects 8 rows x 256, 16 rows x 128, 8 rows x 128 threads for re-tuning
   static int variant = -1;
   if (variant < 0) { const char* e = getenv("CKL_EDGES_VARIANT"); variant = e ? atoi(e) : 0; }
+  if (variant == 0 && g.sx % (32 * EDT_WORDS) == 0 && width >= 4 && ((u64)labels & 15) == 0) {
+    const u64 items = (u64)g.sz * ((g.sy + EDT_ROWS - 1) / EDT_ROWS) * (g.sx / (32 * EDT_WORDS));
+    const size_t smem = (size_t)EDT_WARPS * EDT_STAGES * (32 * EDT_WORDS * width + 16);
+    const u32 per_sm = (u32)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024)));
+    const u32 grid = grid_for(items, EDT_WARPS, per_sm);
+    if (width == 4) {
+      if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_edges_tma<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_edges_tma<u32><<<grid, 32 * EDT_WARPS, smem, st>>>((const u32*)labels, g, DV, DH, scal);
+    } else {
+      if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_edges_tma<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_edges_tma<u64><<<grid, 32 * EDT_WARPS, smem, st>>>((const u64*)labels, g, DV, DH, scal);
+    }
+    LAUNCH_CHECK();
+    return;
+  }
   const int rs = (variant == 1 || variant == 3) ? 8 : 16;                    // default: 16-row strips, 256 threads
   const u32 threads = (variant == 2 || variant == 3) ? 128u : 256u;
   const u64 items = (u64)g.sz * ((g.sy + rs - 1) / rs);
