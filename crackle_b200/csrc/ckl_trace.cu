@@ -310,6 +310,7 @@ __device__ __forceinline__ bool nib_step(const u32* __restrict__ vn, u32 S, u32&
 // grid = (chunks, slices); a lane takes the next slot of its warp's chunk as soon as its current path reaches a node
 // (the refill reads the node's static adjacency nibble, so slots without an edge cost one byte load).
 #define SE_UNSET 0xFEFEFEFEu
+#define WALK_REFILL 8           // idle lanes that trigger a refill of the walkers (k_path_walk, k_expand)
 // Small chunks = many warps per slice = few slices in flight at once: the vertex words the walkers chase (541 KB per
 // 1024^2 slice) then stay L2-resident instead of streaming from DRAM once per step.
 #define PW_CHUNK 128u
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(256) k_path_walk(TraceParams P) {
       u32 pos = 0, kk = 0, len = 0, slot = 0;
       for (;;) {
         const u32 idle = __ballot_sync(FULL_MASK, !active);
-        if (idle) {
+        if ((__popc(idle) >= WALK_REFILL && next < end) || idle == FULL_MASK) {      // refill in batches: the refill code is as long as the step itself
           const u32 i = next + __popc(idle & ltmask);
           if (!active && i < end) {
             const u32 node = i >> 1, k0 = (i & 1u) * 2u + PASS;      // pass 0: right, down; pass 1: left, up
@@ -811,7 +812,7 @@ __global__ void __launch_bounds__(256) k_expand(TraceParams P) {
       u8* o = nullptr;
       for (;;) {
         const u32 idle = __ballot_sync(FULL_MASK, left == 0);
-        if (idle) {
+        if ((__popc(idle) >= WALK_REFILL && next < end) || idle == FULL_MASK) {
           const u32 i = next + __popc(idle & ltmask);
           if (left == 0 && i < end) {
             const uint4 r = __ldg(recs + i);
