@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) k_edges(const T* __restrict__ L, Geom g, 
 // leave as two 32-byte stores.  The warp is its own producer: after a row has been compared its stage is re-armed with the
 // row EDT_STAGES further down.
 #define EDT_WORDS 8
-#define EDT_STAGES 6
+#define EDT_STAGES 4
 #define EDT_ROWS 256
 #define EDT_WARPS 4
 __device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
