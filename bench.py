@@ -422,7 +422,9 @@ def main():
                     "full-width streaming kernels work on 2 bits per voxel and are issue- or latency-bound, not HBM-bound; roofline_kernels "
                     "lists the single-kernel stages with their OWN algorithmic bytes (rank 0, live inside the timed step)."}
     # single-kernel stages: own algorithmic bytes of the kernel on rank 0's slab
-    own = {"edges": ("k_edges", Vl * width + Vl // 4, "hbm"), "d_paint": ("k_paint_rows", Vl * width + Vl // 8, "hbm"),
+    own = {"edges": ("k_edges_tma (cp.async.bulk staged)" if sx % 256 == 0 and width >= 4 else "k_edges", Vl * width + Vl // 4, "hbm"),
+           "d_paint": ("k_paint_tma (cp.async.bulk stores)" if width == 4 and sx % 256 == 0 else "k_paint_band" if sx % 256 == 0 else "k_paint_rows",
+                       Vl * width + Vl // 8, "hbm"),
            "trace_replay": ("k_replay", None, "shared-memory latency (serial walk per slice); not an HBM kernel")}
     kern = {}
     for k, (kname, b, bound) in own.items():
