@@ -1133,6 +1133,49 @@ static void paint_tma(const Geom& g, const u32* DV, const CclBufs& B, const u64*
   LAUNCH_CHECK();
 }
 
+// C-order paint (out[z + sz * (y + sy * x)], crackle.hpp:649-654) as a tiled transpose: a block takes a tile of ZT slices x 32
+// pixels of one row y.  Reading is lane <-> x (one warp per slice: the run-label gather is as coalesced as in the Fortran
+// paint), writing is lane <-> z through a padded shared-memory tile, so every store instruction writes 32 consecutive z of
+// one (x, y) -- 32 * sizeof(OUT) contiguous bytes instead of one element per lane every sz * sy * sizeof(OUT) bytes.
+template <typename OUT, bool MASK, int ZT>
+__global__ void __launch_bounds__(256) k_paint_c_tiled(Geom g, const u32* __restrict__ DV, const u32* __restrict__ wordPrefix,
+                                                        const u32* __restrict__ rowBase, const u64* __restrict__ runBase,
+                                                        const u64* __restrict__ runLabel, u64 label, OUT* __restrict__ out) {
+  __shared__ OUT tile[ZT][33];
+  const u32 tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 8 warps
+  const u32 ztiles = (g.sz + ZT - 1) / ZT;
+  const u64 ntiles = (u64)g.W * g.sy * ztiles;
+  for (u64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const u32 zt = (u32)(t % ztiles);
+    const u64 t2 = t / ztiles;
+    const u32 y = (u32)(t2 % g.sy), w = (u32)(t2 / g.sy);
+    const u32 z0 = zt * ZT, x = w * 32 + tx;
+#pragma unroll 4
+    for (u32 zi = ty; zi < ZT; zi += 8) {
+      const u32 z = z0 + zi;
+      OUT r = 0;
+      if (z < g.sz && x < g.sx) {
+        const u64 row = (u64)z * g.sy + y;
+        const u64 i = row * g.W + w;
+        const u32 dv = DV[i];
+        const u64 v = runLabel[runBase[z] + rowBase[row] + wordPrefix[i] + __popc(dv & ((2u << tx) - 1u))];
+        r = MASK ? (OUT)(v == label) : (OUT)v;
+      }
+      tile[zi][tx] = r;
+    }
+    __syncthreads();
+    for (u32 xi = ty; xi < 32; xi += 8) {
+      const u32 xx = w * 32 + xi;
+      if (xx >= g.sx) continue;
+      OUT* o = out + (u64)g.sz * ((u64)y + (u64)g.sy * xx) + z0;
+#pragma unroll
+      for (u32 zz = 0; zz < ZT; zz += 32)
+        if (z0 + zz + tx < g.sz) __stcs(o + zz + tx, tile[zz + tx][xi]);
+    }
+    __syncthreads();
+  }
+}
+
 // Band form with direct stores (sx a multiple of 256): the same decomposition as above without the staging -- the eight label
 // gathers of a row are issued together (no running popcount along the row: wordPrefix gives every word its first run), the
 // next row's plane words are already in flight, and each word is one coalesced 32-lane store.
@@ -1195,6 +1238,21 @@ void launch_paint(const Geom& g, const u32* DV, const CclBufs& B, const u64* run
   if (fortran_order && ((u64)out & 15) == 0 && !has_label && out_width == 4) {
     if (g.sx % 512 == 0) { paint_tma<u32, false, 16, 4>(g, DV, B, runLabel, label, out, st); return; }
     if (g.sx % 256 == 0) { paint_tma<u32, false, 8, 4>(g, DV, B, runLabel, label, out, st); return; }
+  }
+  static int cscatter = -1;
+  if (cscatter < 0) { const char* e = getenv("CKL_PAINT_C_SCATTER"); cscatter = e ? atoi(e) : 0; }      // tuning aid: 1 = per-lane scatter
+  if (!fortran_order && !cscatter) {
+    constexpr int ZT = 32;                                  // slices per tile: 128 * sizeof(OUT) contiguous bytes per (x, y)
+    const u64 ntiles = (u64)g.W * g.sy * ((g.sz + ZT - 1) / ZT);
+    const u32 gridc = grid1(ntiles, 1, 148 * 6);
+    const u32* wpc = B.wordPrefix.as<u32>(); const u32* rbc = B.rowBase.as<u32>(); const u64* rBc = B.runBase.as<u64>();
+#define PAINTC(T, M) k_paint_c_tiled<T, M, ZT><<<gridc, 256, 0, st>>>(g, DV, wpc, rbc, rBc, runLabel, label, (T*)out)
+    if (has_label) PAINTC(u8, true);
+    else switch (out_width) { case 1: PAINTC(u8, false); break; case 2: PAINTC(u16, false); break;
+                              case 4: PAINTC(u32, false); break; default: PAINTC(u64, false); break; }
+#undef PAINTC
+    LAUNCH_CHECK();
+    return;
   }
   const u32 grid = grid1(g.words(), 8, 148 * 8);
   const u32* wp = B.wordPrefix.as<u32>();
