@@ -368,7 +368,7 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   c->lb.mapping.ensure(J.ncomp * 8 + 8);
   c->prof.begin("labels_sort_unique", st);
   launch_gather_mapping(J.labels, J.width, g, c->ccl, J.ncomp, c->lb.mapping.as<u64>(), st);
-  J.nuniq_local = labels_sort_unique(c->lb, J.ncomp, stored_width, st);
+  labels_sort_unique(c->lb, J.ncomp, stored_width, st, &c->scal[SC_UNIQUE]);      // count picked up by the read-back below
   c->prof.end(st);
   CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_join, 0));     // join: everything below sees the tracer's results
   launch_code_sizes_order0(g, c->tr, c->scal, st);        // order-0 code offsets / total: final unless a markov model re-codes them
@@ -376,6 +376,7 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   if (c->hscal[SC_ERROR]) throw CklError(CKL_ERR_CUDA, "crackle_b200: internal tracer capacity error " + std::to_string(c->hscal[SC_ERROR]));
   J.ncp = c->hscal[SC_CODEPOINTS];
   J.codes_bytes0 = c->hscal[SC_CODE_BYTES];
+  J.nuniq_local = c->hscal[SC_UNIQUE];
   if (order > 0) {
     const u64 rows = 1ull << (2 * order);
     c->mk.stats.ensure(rows * 16);
@@ -1020,7 +1021,10 @@ extern "C" int ckl_compress(ckl_ctx* c, const void* labels, int labels_on_device
   k_store_bytes_u32<<<1, 1, 0, st>>>(R + off_codes + J.codes_bytes, crc_tmp + 1);
   launch_write_le_u32(c->ccl.sliceCrc.as<u32>(), g.sz, 4, R + off_codes + J.codes_bytes + 4, st);
   LAUNCH_CHECK();
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  // Device-resident input on a caller-owned stream (ckl_ctx_set_stream): the result is complete in stream order
+  // (ckl_result_copy drains; a ckl_decompress of ckl_result_device() on this context is ordered behind it) and the caller
+  // orders its own use of the input on that stream -- no drain here.  Otherwise the call returns with the work finished.
+  if (!(labels_on_device && c->ext_stream) || c->prof.on) CUDA_CHECK(cudaStreamSynchronize(st));
   c->prof.collect();
   c->result_bytes = total;
   if (out_bytes) *out_bytes = total;
@@ -1260,7 +1264,10 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
   if (h.format_version > 0) {   // crackle.hpp:599-611
     k_crc_compare<<<(g.sz + 255) / 256, 256, 0, st>>>(c->ccl.sliceCrc.as<u32>(), dstream + num_bytes - 4ull * h.sz + 4ull * (u64)z_start, g.sz, c->scal);
     LAUNCH_CHECK();
-    read_scalars(c);
+  }
+  // the verdict of the crc check is read with the final drain: the paint is queued behind it without a host round trip
+  auto check_crc = [&]() {
+    if (h.format_version == 0) return;
     if (c->hscal[SC_CRC_BAD] != none) {
       const u64 zi = c->hscal[SC_CRC_BAD];
       u32 computed = 0;
@@ -1270,7 +1277,7 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
       throw CklError(CKL_ERR_STREAM, "crackle: crack code crc mismatch on z=" + std::to_string((u64)z_start + zi) + " computed: " +
                                          std::to_string(computed) + " stored: " + std::to_string(stored));
     }
-  }
+  };
   if (stats) {      // operations.hpp:321-665: per-label voxel counts, coordinate sums and bounding boxes, straight from the runs
     stats->n_unique = nu;
     if (stats->capacity < nu) throw CklError(CKL_ERR_ARG, "crackle_b200: statistics buffers hold fewer entries than the stream has labels");
@@ -1286,7 +1293,8 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
       if (stats->sums) CUDA_CHECK(cudaMemcpyAsync(stats->sums, d_sums, nu * 24, k, st));
       if (stats->bbox) CUDA_CHECK(cudaMemcpyAsync(stats->bbox, d_bbox, nu * 24, k, st));
     }
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    read_scalars(c);
+    check_crc();
     if (!c->is_kid) c->prof.collect();
     return;
   }
@@ -1294,7 +1302,8 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
   if (!out_on_device) { c->out_dev.ensure(voxels * (u64)ow); dout = c->out_dev.p; }
   STAGE(c, "d_paint", launch_paint(g, c->DV.as<u32>(), c->ccl, D.runLabel.as<u64>(), ow, has_label, label, (int)h.fortran_order, dout, st));
   if (!out_on_device) CUDA_CHECK(cudaMemcpyAsync(out, dout, voxels * (u64)ow, cudaMemcpyDeviceToHost, st));
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  read_scalars(c);                                       // the one drain at the end of the call
+  check_crc();
   if (!c->is_kid) c->prof.collect();
 }
 

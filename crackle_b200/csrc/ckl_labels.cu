@@ -41,8 +41,13 @@ void launch_gather_mapping(const void* labels, int width, const Geom& g, const C
   LAUNCH_CHECK();
 }
 
-u64 labels_sort_unique(LabelBufs& L, u64 n, int stored_width, cudaStream_t st) {
-  if (n == 0) return 0;
+// count_dev != nullptr: the number of unique labels is left in *count_dev (device, u64) and NOT read back -- no stream drain;
+// the caller picks it up with its next scalar read-back.  Returns 0 in that case.
+u64 labels_sort_unique(LabelBufs& L, u64 n, int stored_width, cudaStream_t st, ull* count_dev) {
+  if (n == 0) {
+    if (count_dev) CUDA_CHECK(cudaMemsetAsync(count_dev, 0, 8, st));
+    return 0;
+  }
   if (n > 0x7FFFFFFFull) throw CklError(CKL_ERR_ARG, "crackle_b200: more than 2^31 components in one shard");
   L.sorted.ensure(n * 8);
   L.uniq.ensure(n * 8);
@@ -56,6 +61,10 @@ u64 labels_sort_unique(LabelBufs& L, u64 n, int stored_width, cudaStream_t st) {
   CUDA_CHECK(cub::DeviceRadixSort::SortKeys(L.tmp.p, t, L.mapping.as<u64>(), L.sorted.as<u64>(), (int)n, 0, end_bit, st));
   t = L.tmp.cap;
   CUDA_CHECK(cub::DeviceSelect::Unique(L.tmp.p, t, L.sorted.as<u64>(), L.uniq.as<u64>(), L.flags.as<u64>(), (int)n, st));
+  if (count_dev) {
+    CUDA_CHECK(cudaMemcpyAsync(count_dev, L.flags.p, 8, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
   u64 count = 0;
   CUDA_CHECK(cudaMemcpyAsync(&count, L.flags.p, 8, cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaStreamSynchronize(st));

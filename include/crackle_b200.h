@@ -82,7 +82,10 @@ CKL_API const char* ckl_ctx_error(const ckl_ctx* ctx);           /* message of t
 CKL_API int ckl_device_count(void);
 
 /* Compress; `labels` is a host (labels_on_device == 0) or device pointer.  The stream is left in a
- * context-owned device buffer; fetch it with ckl_result_copy / ckl_result_device. */
+ * context-owned device buffer; fetch it with ckl_result_copy / ckl_result_device.  A ckl_ctx is single-threaded (one
+ * call at a time).  With a device pointer AND a caller-owned stream (ckl_ctx_set_stream) the call returns when the last
+ * kernels are queued: *out_bytes is final, the bytes are complete in stream order, and the caller orders its own
+ * reuse of `labels` on that stream. */
 CKL_API int ckl_compress(ckl_ctx* ctx, const void* labels, int labels_on_device, int data_width,
                  uint64_t sx, uint64_t sy, uint64_t sz, int fortran_order, int markov_model_order,
                  uint64_t* out_bytes);
