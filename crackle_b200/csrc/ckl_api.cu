@@ -45,6 +45,24 @@ struct ShardJob {
 unsigned long long g_ckl_launches = 0;
 int g_ckl_grid_mult = 1;
 
+int ckl_num_sms() {
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!sms[dev]) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
+  }
+  return sms[dev];
+}
+u32 ckl_grid(u64 items, u32 per_block, u32 blocks_per_sm, bool fine) {
+  u64 need = (items + per_block - 1) / per_block;
+  const u64 cap = (u64)ckl_num_sms() * blocks_per_sm * (u64)(fine ? g_ckl_grid_mult : 1);
+  if (need < 1) need = 1;
+  return (u32)(need < cap ? need : cap);
+}
+
 // The chunk pipeline drives up to 2 streams per chunk; with the default of 8 hardware work queues the streams would
 // alias and serialise each other.  Honoured only if the CUDA context is created after this library is loaded.
 namespace { struct EnvInit { EnvInit() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); } } g_env_init; }
@@ -413,11 +431,11 @@ static void shard_finish_impl(ckl_ctx* c, const u64* guniq_dev, u64 nuniq_global
     c->mk.model.ensure(rows * 4);
     c->mk.stored.ensure(model_bytes_for(order) + 16);
     launch_markov_model(order, gstats_dev, c->mk.model.as<u8>(), c->mk.stored.as<u8>(), model_bytes_for(order), st);
-    launch_markov_sizes(g, c->tr, order, c->mk.model.as<u8>(), c->mk, c->scal, st);
+    launch_markov_sizes(g, c->tr, c->mk, c->scal, st);
     const u64 scratch_words = (3 * J.ncp) / 32 + 3ull * g.sz + 64;
     c->mk.scratch.ensure(scratch_words * 4);
     CUDA_CHECK(cudaMemsetAsync(c->mk.scratch.p, 0, scratch_words * 4, st));
-    STAGE(c, "markov_encode", launch_markov_encode(g, c->tr, order, c->mk.model.as<u8>(), c->mk, nullptr, st));
+    STAGE(c, "markov_encode", launch_markov_encode(g, c->tr, order, c->mk.model.as<u8>(), c->mk, st));
   }
   launch_code_sizes_order0(g, c->tr, c->scal, st);     // scans sliceInfo[.codeBytes] (either format)
   read_scalars(c);
@@ -690,11 +708,7 @@ static void ensure_kids(ckl_ctx* c, int K) {
     int lo = 0, hi = 0;
     CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     const int idx = (int)c->kids.size();
-    int p2 = std::min(hi + idx, lo), p1 = std::min(hi + idx + 1, lo);
-    {
-      const char* e = getenv("CKL_PRIO");      // tuning aid: 0 = every chunk alike (side stream high, main stream default)
-      if (e && atoi(e) == 0) { p2 = hi; p1 = lo; }
-    }
+    const int p2 = std::min(hi + idx, lo), p1 = std::min(hi + idx + 1, lo);
     cudaStreamDestroy(k->st2);
     cudaStreamDestroy(k->own_st);
     k->st2 = k->own_st = k->st = nullptr;
@@ -707,9 +721,7 @@ static void ensure_kids(ckl_ctx* c, int K) {
 struct GridMultScope {        // finer grids while chunks run concurrently (see g_ckl_grid_mult)
   int saved;
   GridMultScope() : saved(g_ckl_grid_mult) {
-    static int env = -1;
-    if (env < 0) { const char* e = getenv("CKL_GRID_MULT"); env = e ? atoi(e) : 0; if (env < 0) env = 0; }
-    g_ckl_grid_mult = env ? env : 8;
+    g_ckl_grid_mult = 8;
   }
   ~GridMultScope() { g_ckl_grid_mult = saved; }
 };
@@ -1438,11 +1450,11 @@ extern "C" int ckl_reencode(ckl_ctx* c, const void* binary, int binary_on_device
     c->mk.stats.ensure(rows * 16); c->mk.model.ensure(rows * 4); c->mk.stored.ensure(mbytes_new + 16);
     launch_markov_stats(g, T, new_order, c->mk.stats.as<u32>(), st);
     launch_markov_model(new_order, c->mk.stats.as<u32>(), c->mk.model.as<u8>(), c->mk.stored.as<u8>(), mbytes_new, st);
-    launch_markov_sizes(g, T, new_order, c->mk.model.as<u8>(), c->mk, c->scal, st);
+    launch_markov_sizes(g, T, c->mk, c->scal, st);
     const u64 scratch_words = (3 * tw * 16) / 32 + 3ull * g.sz + 64;
     c->mk.scratch.ensure(scratch_words * 4);
     CUDA_CHECK(cudaMemsetAsync(c->mk.scratch.p, 0, scratch_words * 4, st));
-    launch_markov_encode(g, T, new_order, c->mk.model.as<u8>(), c->mk, nullptr, st);
+    launch_markov_encode(g, T, new_order, c->mk.model.as<u8>(), c->mk, st);
   }
   launch_code_sizes_order0(g, T, c->scal, st);
   read_scalars(c);

@@ -227,7 +227,7 @@ void launch_decode_slices(const Geom& g, const u8* stream, const u64* codeOff, i
 
 // ---------------------------------------------------------------------------------------------------------
 // Scan-parallel decoder (validated against the oracle by tests/bringup/proto_decode.py).
-//   k_dec_markov   order > 0 only: serial bit decoder per slice -> packed 2-bit difference fields
+//   k_mk_scan / k_mk_decode   order > 0 only: parallel bit decoder -> packed 2-bit difference fields
 //   k_dec_classify per 16-field word: absolute moves (prefix sum mod 4) and the second-of-escape-pair mask S
 //                  (S[i] = opp[i] & ~S[i-1], solved per 32-field window with an add-carry trick); counts events
 //   k_dec_compact  event list: codepoint index | move << 30
@@ -262,54 +262,6 @@ __device__ __forceinline__ u32 dec_word(const DecSlice& d, const u8* __restrict_
   const u64 rem = nb - wi * 4;
   if (rem < 4) w &= (1u << (8 * (u32)rem)) - 1u;
   return w;
-}
-
-// order > 0: markov::decode_codepoints (markov.hpp:268-323) -> difference fields, 16 per word
-__global__ void __launch_bounds__(32) k_dec_markov(const DecSlice* __restrict__ ds, u32 sz, const u8* __restrict__ stream, int order,
-                                                    const u8* __restrict__ model, u32* __restrict__ fields, u32* __restrict__ ncpOut) {
-  __shared__ u8 smodel[DECODE_SMEM_MODEL];
-  const u32 z = blockIdx.x;
-  const u64 mbytes = 4ull << (2 * order);      // order <= 12 (checked by the caller)
-  const bool msm = mbytes <= DECODE_SMEM_MODEL;
-  if (msm) {
-    for (u32 i = threadIdx.x; i < mbytes; i += blockDim.x) smodel[i] = model[i];
-    __syncwarp();
-  }
-  if (threadIdx.x != 0 || z >= sz) return;
-  const DecSlice d = ds[z];
-  u32* out = fields + d.wordOff;
-  u64 n = 0;
-  if (d.blen) {
-    // Lean serial loop (a lone warp issues about one instruction every four cycles, so the instruction count is the cost):
-    // a two-word bit window read with one funnel shift, code length and rank of the 0 / 10 / 110 / 111 code from two 16-bit
-    // tables indexed by the next three bits, the model row read through an explicit shared-space address, 32-bit counters.
-    u32 ma = (u32)__cvta_generic_to_shared(smodel);
-    asm volatile("" : "+r"(ma));
-    const u32 top2 = 2 * (order - 1) + 2;            // the context is kept pre-multiplied by 4 (the model row offset)
-    u64 wi = 0;
-    u32 cur = dec_word(d, stream, nullptr, 0, wi++), nxt = dec_word(d, stream, nullptr, 0, wi++);
-    u32 bp = 2;                                       // bit position inside `cur`; the window is (nxt : cur) >> bp
-    u32 acc = cur & 3u;                               // first symbol: 2 raw bits (it is the absolute move; the running sum starts at 0)
-    u32 ctx4 = acc << top2, sh = 2, cnt = 1;
-    int rem = (int)(d.blen * 8u) - 2;                 // code sizes are far below 2^28 bytes (checked by the caller)
-    u32* o = out;
-    while (rem > 0) {
-      const u32 v2 = (__funnelshift_r(cur, nxt, bp) & 7u) * 2u;
-      const u32 len = (0xD9D9u >> v2) & 3u, rank = (0xC484u >> v2) & 3u;     // 0 -> (1, 0); 10 -> (2, 1); 110 -> (3, 2); 111 -> (3, 3)
-      u32 dsym;
-      if (msm) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(dsym) : "r"(ma + ctx4 + rank));
-      else dsym = model[(u64)ctx4 + rank];
-      bp += len; rem -= (int)len;
-      ctx4 = ((ctx4 >> 2) & ~3u) + (dsym << top2);
-      acc |= dsym << sh;
-      sh += 2; cnt++;
-      if (sh == 32) { *o++ = acc; acc = 0; sh = 0; }
-      if (bp >= 32) { bp -= 32; cur = nxt; nxt = dec_word(d, stream, nullptr, 0, wi++); }
-    }
-    if (sh) *o = acc;
-    n = cnt;
-  }
-  ncpOut[z] = (u32)n;
 }
 
 // ---- order > 0, parallel form -------------------------------------------------------------------------------
@@ -866,15 +818,7 @@ __global__ void __launch_bounds__(256) k_dec_mark(Geom g, const DecSlice* __rest
   }
 }
 
-static u32 dec_grid(u64 n, u32 bs, u32 per_sm) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  u64 b = (n + bs - 1) / bs;
-  if (b < 1) b = 1;
-  const u64 cap = (u64)sms * per_sm;
-  return (u32)(b < cap ? b : cap);
-}
+static u32 dec_grid(u64 n, u32 bs, u32 per_sm) { return ckl_grid(n, bs, per_sm, false); }
 
 // per-slice descriptors from the code offsets: index size read from the stream (crackcodes.hpp:283-316)
 __global__ void k_dec_slices_init(Geom g, const u8* __restrict__ stream, const u64* __restrict__ codeOff, const u64* __restrict__ wordOff,
@@ -1239,9 +1183,7 @@ void launch_paint(const Geom& g, const u32* DV, const CclBufs& B, const u64* run
     if (g.sx % 512 == 0) { paint_tma<u32, false, 16, 4>(g, DV, B, runLabel, label, out, st); return; }
     if (g.sx % 256 == 0) { paint_tma<u32, false, 8, 4>(g, DV, B, runLabel, label, out, st); return; }
   }
-  static int cscatter = -1;
-  if (cscatter < 0) { const char* e = getenv("CKL_PAINT_C_SCATTER"); cscatter = e ? atoi(e) : 0; }      // tuning aid: 1 = per-lane scatter
-  if (!fortran_order && !cscatter) {
+  if (!fortran_order) {      // measured (1024x1024x512 uint64): 3.2 ms, against 24.5 ms for one scattered element per lane
     constexpr int ZT = 32;                                  // slices per tile: 128 * sizeof(OUT) contiguous bytes per (x, y)
     const u64 ntiles = (u64)g.W * g.sy * ((g.sz + ZT - 1) / ZT);
     const u32 gridc = grid1(ntiles, 1, 148 * 6);
@@ -1259,9 +1201,7 @@ void launch_paint(const Geom& g, const u32* DV, const CclBufs& B, const u64* run
   const u32* rb = B.rowBase.as<u32>();
   const u64* rB = B.runBase.as<u64>();
 #define PAINT(T, M, F) k_paint<T, M, F><<<grid, 256, 0, st>>>(g, DV, wp, rb, rB, runLabel, label, (T*)out)
-  static int stream_st = -1;
-  if (stream_st < 0) { const char* e = getenv("CKL_PAINT_CS"); stream_st = e ? atoi(e) : 1; }
-#define PAINTR(T, M) k_paint_rows<T, M><<<grid1(g.rows(), 8, 148 * 8), 256, 0, st>>>(g, DV, rb, rB, runLabel, label, (T*)out, stream_st != 0)
+#define PAINTR(T, M) k_paint_rows<T, M><<<grid1(g.rows(), 8, 148 * 8), 256, 0, st>>>(g, DV, rb, rB, runLabel, label, (T*)out, true)
   if (has_label) {
     if (fortran_order) PAINTR(u8, true); else PAINT(u8, true, false);
   } else if (fortran_order) {

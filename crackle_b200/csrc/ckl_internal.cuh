@@ -2,6 +2,11 @@
 #pragma once
 #include "ckl_common.cuh"
 
+// one place for the SM count and the grid size of grid-stride kernels (ckl_api.cu): min(blocks needed, SMs x blocks per SM
+// [x g_ckl_grid_mult while z-chunks run concurrently])
+int ckl_num_sms();
+u32 ckl_grid(u64 items, u32 per_block, u32 blocks_per_sm, bool fine = true);
+
 struct Geom {
   u32 sx, sy, sz;     // sz = slices held by this context (a z-slab for sharded jobs)
   u32 W;              // 32-pixel words per row = ceil(sx/32)
@@ -81,8 +86,8 @@ struct MarkovBufs {
 };
 void launch_markov_stats(const Geom& g, TraceBufs& T, int order, u32* stats, cudaStream_t st);
 void launch_markov_model(int order, const u32* stats, u8* model, u8* stored, u64 stored_bytes, cudaStream_t st);
-void launch_markov_sizes(const Geom& g, TraceBufs& T, int order, const u8* model, MarkovBufs& M, ull* scal, cudaStream_t st);
-void launch_markov_encode(const Geom& g, TraceBufs& T, int order, const u8* model, MarkovBufs& M, u8* dst, cudaStream_t st);
+void launch_markov_sizes(const Geom& g, TraceBufs& T, MarkovBufs& M, ull* scal, cudaStream_t st);
+void launch_markov_encode(const Geom& g, TraceBufs& T, int order, const u8* model, MarkovBufs& M, cudaStream_t st);
 
 // ---- label table (ckl_labels.cu) -------------------------------------------------------------------------
 struct LabelBufs {

@@ -20,16 +20,7 @@ static TraceParamsM mk(const Geom& g, TraceBufs& T) {
   P.g = g; P.offs = T.offs.as<u64>(); P.cp = T.cp.as<u8>(); P.sliceInfo = T.sliceInfo.as<u32>();
   return P;
 }
-static int g_sms_m = 0;
-static u32 grid_slices(u32 sz, u32 per_sm) {
-  if (!g_sms_m) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sms_m, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sms_m <= 0) g_sms_m = 148;
-  }
-  u32 cap = (u32)g_sms_m * per_sm;
-  return sz < cap ? (sz ? sz : 1) : cap;
-}
+static u32 grid_slices(u32 sz, u32 per_sm) { return ckl_grid(sz, 1, per_sm, false); }
 void launch_exscan_u32_u64(const u32* in, u32 n, u32 stride, u64* out, ull* total_out, u64 add_each, cudaStream_t st);
 void launch_write_boc_only(const Geom& g, TraceBufs& T, u8* dst, cudaStream_t st);
 
@@ -159,7 +150,7 @@ __global__ void k_markov_caps(u32 sz, const u32* __restrict__ sliceInfo, u32* __
   if (z < sz) caps[z] = (u32)((2ull + 3ull * sliceInfo[(u64)z * 4 + 0] + 31) / 32 + 1);
 }
 
-void launch_markov_sizes(const Geom& g, TraceBufs& T, int order, const u8* model, MarkovBufs& M, ull* scal, cudaStream_t st) {
+void launch_markov_sizes(const Geom& g, TraceBufs& T, MarkovBufs& M, ull* scal, cudaStream_t st) {
   // scratch capacity per slice (words), offsets, then encode into scratch; sizes fall out of the encode
   M.bitlen.ensure((u64)g.sz * 8 + (u64)g.sz * 4);
   M.scratchOff.ensure(((u64)g.sz + 1) * 8);
@@ -167,18 +158,13 @@ void launch_markov_sizes(const Geom& g, TraceBufs& T, int order, const u8* model
   k_markov_caps<<<(g.sz + 255) / 256, 256, 0, st>>>(g.sz, T.sliceInfo.as<u32>(), caps);
   LAUNCH_CHECK();
   launch_exscan_u32_u64(caps, g.sz, 1, M.scratchOff.as<u64>(), &scal[SC_CPCAP], 0, st);
-  // worst case: 3 bits per codepoint -> the codepoint buffer capacity bounds the scratch size
-  (void)order; (void)model;
 }
 
-void launch_markov_encode(const Geom& g, TraceBufs& T, int order, const u8* model, MarkovBufs& M, u8* dst, cudaStream_t st) {
-  // dst == nullptr: encode into scratch and compute sizes; dst != nullptr: copy BOC + bitstreams to the stream
-  if (!dst) {
-    k_markov_encode<<<grid_slices(g.sz, 8), 256, 0, st>>>(mk(g, T), order, model, M.scratchOff.as<u64>(), M.scratch.as<u32>(),
-                                                          M.bitlen.as<u64>(), T.sliceInfo.as<u32>());
-    LAUNCH_CHECK();
-    return;
-  }
+// bitstreams of all slices into the word-aligned scratch (sizes land in sliceInfo[.codeBytes]); launch_markov_copy places them
+void launch_markov_encode(const Geom& g, TraceBufs& T, int order, const u8* model, MarkovBufs& M, cudaStream_t st) {
+  k_markov_encode<<<grid_slices(g.sz, 8), 256, 0, st>>>(mk(g, T), order, model, M.scratchOff.as<u64>(), M.scratch.as<u32>(),
+                                                        M.bitlen.as<u64>(), T.sliceInfo.as<u32>());
+  LAUNCH_CHECK();
 }
 
 __global__ void __launch_bounds__(256) k_markov_copy(Geom g, const u32* __restrict__ sliceInfo, const u64* __restrict__ codeOff,

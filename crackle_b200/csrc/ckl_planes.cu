@@ -235,30 +235,11 @@ __global__ void __launch_bounds__(32 * EDT_WARPS) k_edges_tma(const T* __restric
   }
 }
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
-static u32 grid_for(u64 items, u32 per_block, u32 blocks_per_sm) {
-  u64 need = (items + per_block - 1) / per_block;
-  u64 cap = (u64)num_sms() * blocks_per_sm * (u64)g_ckl_grid_mult;
-  if (need < 1) need = 1;
-  return (u32)(need < cap ? need : cap);
-}
+static u32 grid_for(u64 items, u32 per_block, u32 blocks_per_sm) { return ckl_grid(items, per_block, blocks_per_sm); }
 
 void launch_edges(const void* labels, int width, const Geom& g, u32* DV, u32* DH, ull* scal, cudaStream_t st) {
-  // strip height x block size: taller strips keep more loads in flight per register (one `up` row and one set of
-  // addressing registers per strip).  Measured on B200 (1024^3 uint64): 8 rows 2106 us, 16 rows 1774 us, 32 rows 2072 us
-  // (250 registers); CKL_EDGES_VARIANT = 1 / 2 / 3 selects 8 rows x 256, 16 rows x 128, 8 rows x 128 threads for re-tuning
-  static int variant = -1;
-  if (variant < 0) { const char* e = getenv("CKL_EDGES_VARIANT"); variant = e ? atoi(e) : 0; }
-  if (variant == 0 && g.sx % (32 * EDT_WORDS) == 0 && width >= 4 && ((u64)labels & 15) == 0) {
+  // TMA-staged form for uint32 / uint64 rows that are a multiple of 256 pixels
+  if (g.sx % (32 * EDT_WORDS) == 0 && width >= 4 && ((u64)labels & 15) == 0) {
     const u64 items = (u64)g.sz * ((g.sy + EDT_ROWS - 1) / EDT_ROWS) * (g.sx / (32 * EDT_WORDS));
     const size_t smem = (size_t)EDT_WARPS * EDT_STAGES * (32 * EDT_WORDS * width + 16);
     const u32 per_sm = (u32)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024)));
@@ -273,16 +254,13 @@ void launch_edges(const void* labels, int width, const Geom& g, u32* DV, u32* DH
     LAUNCH_CHECK();
     return;
   }
-  const int rs = (variant == 1 || variant == 3) ? 8 : 16;                    // default: 16-row strips, 256 threads
-  const u32 threads = (variant == 2 || variant == 3) ? 128u : 256u;
-  const u64 items = (u64)g.sz * ((g.sy + rs - 1) / rs);
-  const u32 grid = grid_for(items, threads / 32, threads == 128 ? 12 : 4);
+  // register-strip form (any shape, any width): one warp = 32 px x 16 rows, 16 loads in flight per lane.  Measured on B200
+  // (1024^3 uint64): 8 rows 2106 us, 16 rows 1774 us, 32 rows 2072 us (250 registers)
+  const u32 threads = 256u;
+  const u64 items = (u64)g.sz * ((g.sy + 15) / 16);
+  const u32 grid = grid_for(items, threads / 32, 4);
 #define EDGES(T, R) k_edges<T, R><<<grid, threads, 0, st>>>((const T*)labels, g, DV, DH, scal)
-  if (rs == 16) {
-    switch (width) { case 1: EDGES(u8, 16); break; case 2: EDGES(u16, 16); break; case 4: EDGES(u32, 16); break; default: EDGES(u64, 16); break; }
-  } else {
-    switch (width) { case 1: EDGES(u8, 8); break; case 2: EDGES(u16, 8); break; case 4: EDGES(u32, 8); break; default: EDGES(u64, 8); break; }
-  }
+  switch (width) { case 1: EDGES(u8, 16); break; case 2: EDGES(u16, 16); break; case 4: EDGES(u32, 16); break; default: EDGES(u64, 16); break; }
 #undef EDGES
   LAUNCH_CHECK();
 }

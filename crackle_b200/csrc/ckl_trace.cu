@@ -33,22 +33,7 @@
 #define NONE32 0xFFFFFFFFu
 enum { EV_E = 0, EV_B = 1, EV_T = 2, EV_S = 3 };      // event type in bits 30..31, payload (local slot) below
 
-static int g_sms_t = 0;
-static int sms() {
-  if (!g_sms_t) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sms_t, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sms_t <= 0) g_sms_t = 148;
-  }
-  return g_sms_t;
-}
-static u32 grid_cap(u64 items, u32 per_block, u32 blocks_per_sm) {
-  u64 need = (items + per_block - 1) / per_block;
-  u64 cap = (u64)sms() * blocks_per_sm * (u64)g_ckl_grid_mult;
-  if (need < 1) need = 1;
-  return (u32)(need < cap ? need : cap);
-}
+static u32 grid_cap(u64 items, u32 per_block, u32 blocks_per_sm) { return ckl_grid(items, per_block, blocks_per_sm); }
 void launch_exscan_u32_u64(const u32* in, u32 n, u32 stride, u64* out, ull* total_out, u64 add_each, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------------
@@ -973,14 +958,7 @@ static TraceParams make_params(const Geom& g, TraceBufs& T, ull* scal) {
   P.ev = T.ev.as<u32>(); P.evRec = T.evRec.as<uint4>(); P.evCp = T.evCp.as<u32>(); P.stack = T.stack.as<uint2>(); P.chain = T.chain.as<ChainRec>();
   P.cp = T.cp.as<u8>(); P.sliceInfo = T.sliceInfo.as<u32>();
   P.scal = scal;
-  static u32 pwc = 0, exc = 0;
-  if (!pwc) {
-    const char* a = getenv("CKL_PW_CHUNK"); const char* b = getenv("CKL_EX_CHUNK");     // tuning aids
-    const int va = a ? atoi(a) : 0, vb = b ? atoi(b) : 0;
-    exc = vb >= 32 ? (u32)vb : EX_CHUNK;
-    pwc = va >= 32 ? (u32)va : PW_CHUNK;
-  }
-  P.pwChunk = pwc; P.exChunk = exc;
+  P.pwChunk = PW_CHUNK; P.exChunk = EX_CHUNK;
   return P;
 }
 
