@@ -362,6 +362,7 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   c->tr.stack.ensure(stackCap * 8);
   c->tr.chain.ensure(chainCap * sizeof(ChainRec));
   c->tr.cp.ensure(cpCap);
+  CUDA_CHECK(cudaMemsetAsync(c->tr.cp.p, 0, cpCap, st2));    // k_expand ORs the partial words at the ends of a super-edge into place
   c->prof.begin("trace_nodes", st2);
   const bool any_nodes = launch_trace_nodes(g, c->tr, c->scal, nodes, st2);
   c->prof.end(st2);

@@ -179,7 +179,7 @@ __global__ void k_trace_caps(u32 sz, const u32* __restrict__ bounds, const u32* 
   caps[(u64)z * 4 + 0] = S / 2 + 2 * B + C + 4;      // events: super-edges + b + t (t = b + chains)
   caps[(u64)z * 4 + 1] = B + 4;                      // revisit stack depth
   caps[(u64)z * 4 + 2] = C + 2;                      // chains
-  caps[(u64)z * 4 + 3] = E + 4 * B + 2 * C + 16;     // codepoints: moves + 2b + 2t
+  caps[(u64)z * 4 + 3] = (E + 4 * B + 2 * C + 16 + 3u) & ~3u;   // codepoints: moves + 2b + 2t; slice bases stay 4-byte aligned
   atomicMax(&scal[SC_MAXNODES], (ull)N);
 }
 
@@ -278,15 +278,30 @@ __global__ void __launch_bounds__(256) k_node_init(TraceParams P) {
 
 // one step along a super-edge: move in direction kk (0 right, 1 left, 2 down, 3 up: the walk priority), then pick the
 // exit of the vertex reached.  Returns true when that vertex is a node (its nibble does not have exactly two edges).
+__device__ __forceinline__ u32 bfind_u32(u32 x) { u32 r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x)); return r; }   // position of the highest set bit
 __device__ __forceinline__ bool nib_step(const u32* __restrict__ vn, u32 S, u32& p, u32& kk) {
-  const u32 d = 1u - 2u * (kk & 1u);                 // +1 / -1
-  p += (kk & 2u) ? d * S : d;
+  p += ((kk & 2u) ? S : 1u) * (1u - ((kk & 1u) << 1));
   const u32 nib = vertex_nibble(__ldg(vn + (p >> 3)), p & 7u);
   if ((0xE997u >> nib) & 1u) return true;            // popcount(nib) != 2
-  const u32 a = nib & ~(1u << (kk ^ 1u));            // not back along the edge we came by: one bit left
-  kk = (a >> 1) - (a >> 3);                          // one-hot {1,2,4,8} -> {0,1,2,3}
+  const u32 a = nib ^ (1u << (kk ^ 1u));             // not back along the edge we came by: one bit left
+  kk = bfind_u32(a);                                 // one-hot {1,2,4,8} -> {0,1,2,3}
   return false;
 }
+// the same step where the vertex reached is known to be a pass-through vertex (inside a super-edge of known length)
+__device__ __forceinline__ void nib_step_inner(const u32* __restrict__ vn, u32 S, u32& p, u32& kk) {
+  p += ((kk & 2u) ? S : 1u) * (1u - ((kk & 1u) << 1));
+  const u32 nib = vertex_nibble(__ldg(vn + (p >> 3)), p & 7u);
+  kk = bfind_u32(nib ^ (1u << (kk ^ 1u))) & 3u;
+}
+// predicated global store / OR-reduction of one word (no branch around them in the walkers' step)
+__device__ __forceinline__ void st_u32_if(u32* a, u32 v, bool p) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.global.u32 [%0], %1; }" ::"l"(a), "r"(v), "r"((u32)p) : "memory");
+}
+__device__ __forceinline__ void red_or_u32_if(u32* a, u32 v, bool p) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.global.or.b32 [%0], %1; }" ::"l"(a), "r"(v), "r"((u32)p) : "memory");
+}
+#define WALK_QUAD 4             // steps per control round of the walkers (ballot / refill / exit test)
+#define WALK_BLOCK 128          // threads per block of the walkers: a block waits for its slowest warp, so small blocks
 
 // 3b. super-edges: a (node, direction) slot with an edge follows degree-2 vertices to the far node and records
 // the result at BOTH ends.  Pass 0 walks the right / down slots; pass 1 walks the left / up slots that pass 0 did
@@ -300,7 +315,7 @@ __device__ __forceinline__ bool nib_step(const u32* __restrict__ vn, u32 S, u32&
 // 1024^2 slice) then stay L2-resident instead of streaming from DRAM once per step.
 #define PW_CHUNK 128u
 template <int PASS>
-__global__ void __launch_bounds__(256) k_path_walk(TraceParams P) {
+__global__ void __launch_bounds__(WALK_BLOCK) k_path_walk(TraceParams P) {
   const VGeom vg = P.vg;
   const u32 lane = threadIdx.x & 31;
   const u32 ltmask = (1u << lane) - 1u;
@@ -337,18 +352,20 @@ __global__ void __launch_bounds__(256) k_path_walk(TraceParams P) {
               active = true;
             }
           }
-          next += __popc(idle);
-        }
-        if (!__any_sync(FULL_MASK, active)) {
-          if (next >= end) break;
-          continue;
+          next = min(end, next + __popc(idle));
+          if (!__any_sync(FULL_MASK, active)) {
+            if (next >= end) break;
+            continue;
+          }
         }
         if (active) {
-          if (++len > limit) {
-            atomicExch(&P.scal[SC_ERROR], 4ull);
-            seFar[slot] = NONE32; seLen[slot] = 0;
-            active = false;
-          } else if (nib_step(vn, vg.S, pos, kk)) {
+          // WALK_QUAD steps per control round (ballot, refill and exit tests cost as much as a step); a lane that reaches
+          // its far node sits out the rest of the round
+          bool done = false;
+#pragma unroll
+          for (int q = 0; q < WALK_QUAD; q++)
+            if (!done) { len++; done = nib_step(vn, vg.S, pos, kk); }
+          if (done) {
             const u32 y = pos / vg.S, x = pos - y * vg.S;
             const u64 row = rowz + y;
             const u64 wi = row * vg.Wv + (x >> 5);
@@ -359,6 +376,10 @@ __global__ void __launch_bounds__(256) k_path_walk(TraceParams P) {
             const u32 twin = far * 4 + fk;
             seFar[twin] = slot;                                      // (this node << 2) | departure direction
             seLen[twin] = len;
+            active = false;
+          } else if (len > limit) {                                  // cannot happen on a consistent vertex plane: every cycle holds a node
+            atomicExch(&P.scal[SC_ERROR], 4ull);
+            seFar[slot] = NONE32; seLen[slot] = 0;
             active = false;
           }
         }
@@ -706,7 +727,7 @@ __device__ __forceinline__ u8 dir_code(u32 kk) { return (u8)((0x0231u >> (4 * kk
 // 6a. per event (fully parallel): the walk task of a super-edge event -- output position, start vertex, direction,
 // length, reversed/flipped inside a removed initial branch -- as one 16-byte record; 'b' / 't' escape pairs are
 // written here directly (they depend only on the previous kept symbol; kept 't's in between alternate).
-#define EX_CHUNK 128u
+#define EX_CHUNK 256u
 #define EX_LEN_MASK 0x1FFFFFFFu        // record.w = length | direction << 29 | flip << 31
 __global__ void __launch_bounds__(256) k_event_setup(TraceParams P) {
   const Geom g = P.g;
@@ -773,8 +794,12 @@ __global__ void __launch_bounds__(256) k_event_setup(TraceParams P) {
 }
 
 // 6b. the walk: grid = (chunks, slices); a lane takes the next task record of its warp's chunk as soon as its current
-// super-edge is written out, so the refill is one 16-byte load and the loop body is the step itself.
-__global__ void __launch_bounds__(256) k_expand(TraceParams P) {
+// super-edge is written out, so the refill is one 16-byte load and the loop body is the step itself.  Codepoints are
+// gathered into the 32-bit word of `cp` they belong to and leave with ONE store per word: a plain store for a word the
+// super-edge covers entirely, an OR-reduction for the partial words at its two ends (neighbouring events own the other bytes;
+// `cp` is zeroed before k_event_setup writes the escape pairs).  The body is branch-free apart from the reversed initial
+// branch (rare, written back to front byte by byte).  The slice bases of `cp` are multiples of 4 (k_trace_caps).
+__global__ void __launch_bounds__(WALK_BLOCK) k_expand(TraceParams P) {
   const Geom g = P.g;
   const VGeom vg = P.vg;
   const u64 n1 = (u64)g.sz + 1;
@@ -787,14 +812,14 @@ __global__ void __launch_bounds__(256) k_expand(TraceParams P) {
     const u32 nev = chains[nch - 1].symEnd;
     const uint4* recs = P.evRec + P.offs[z];
     u8* cpz = P.cp + P.offs[3 * n1 + z];
+    u32* cpw = reinterpret_cast<u32*>(cpz);
     const u32* vn = reinterpret_cast<const u32*>(P.VW + (u64)z * vg.sye * vg.Wv);
     const u32 EXC = P.exChunk;
     const u32 nchunks = (nev + EXC - 1) / EXC;
     for (u32 chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); chunk < nchunks; chunk += gridDim.x * (blockDim.x >> 5)) {
       u32 next = chunk * EXC;
       const u32 end = min(nev, next + EXC);
-      u32 pos = 0, kk = 0, left = 0, flip = 0;
-      u8* o = nullptr;
+      u32 pos = 0, kk = 0, left = 0, flip = 0, off = 0, acc = 0, full = 0;
       for (;;) {
         const u32 idle = __ballot_sync(FULL_MASK, left == 0);
         if ((__popc(idle) >= WALK_REFILL && next < end) || idle == FULL_MASK) {
@@ -804,18 +829,32 @@ __global__ void __launch_bounds__(256) k_expand(TraceParams P) {
             left = r.w & EX_LEN_MASK;
             kk = (r.w >> 29) & 3u; flip = r.w >> 31;
             pos = r.y;
-            o = cpz + r.x;
+            off = r.x; acc = 0;
+            full = (off & 3u) == 0 ? 1u : 0u;                      // the word being gathered started at its first byte
           }
-          next += __popc(idle);
+          next = min(end, next + __popc(idle));
+          if (!__any_sync(FULL_MASK, left != 0)) {
+            if (next >= end) break;
+            continue;
+          }
         }
-        if (!__any_sync(FULL_MASK, left != 0)) {
-          if (next >= end) break;
-          continue;
-        }
-        if (left) {
-          *o = dir_code(kk ^ flip);
-          o += flip ? -1 : 1;
-          if (--left) nib_step(vn, vg.S, pos, kk);
+#pragma unroll
+        for (int q = 0; q < WALK_QUAD; q++) {
+          if (left) {
+            const u32 code = dir_code(kk ^ flip);
+            --left;
+            if (flip) { cpz[off] = (u8)code; off--; }
+            else {
+              acc |= code << (8u * (off & 3u));
+              u32* wa = cpw + (off >> 2);
+              off++;
+              const bool wordEnd = (off & 3u) == 0;
+              st_u32_if(wa, acc, wordEnd && full);                         // all four bytes are this super-edge's
+              red_or_u32_if(wa, acc, (wordEnd && !full) || (!wordEnd && left == 0));   // partial word at either end
+              if (wordEnd) { acc = 0; full = 1u; }
+            }
+            if (left) nib_step_inner(vn, vg.S, pos, kk);
+          }
         }
       }
     }
@@ -841,12 +880,13 @@ bool launch_trace_nodes(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes,
 void launch_trace_paths(const Geom& g, TraceBufs& T, ull* scal, u32 max_nodes, cudaStream_t st) {
   TraceParams P = make_params(g, T, scal);
   const u32 gy = g.sz < 65535u ? g.sz : 65535u;
-  u32 gx = (2u * max_nodes + 8 * P.pwChunk - 1) / (8 * P.pwChunk);
-  if (gx > 64) gx = 64;
+  const u32 bs = WALK_BLOCK, wpb = bs / 32;
+  u32 gx = (2u * max_nodes + wpb * P.pwChunk - 1) / (wpb * P.pwChunk);
+  if (gx > 256) gx = 256;
   if (gx < 1) gx = 1;
-  k_path_walk<0><<<dim3(gx, gy), 256, 0, st>>>(P);
+  k_path_walk<0><<<dim3(gx, gy), bs, 0, st>>>(P);
   LAUNCH_CHECK();
-  k_path_walk<1><<<dim3(gx, gy), 256, 0, st>>>(P);
+  k_path_walk<1><<<dim3(gx, gy), bs, 0, st>>>(P);
   LAUNCH_CHECK();
 }
 // the serial chain replay: slices are replayed by the instantiation matching their node count (the others return at once)
@@ -879,8 +919,9 @@ void launch_trace_post(const Geom& g, TraceBufs& T, ull* scal, u64 total_ev_cap,
   LAUNCH_CHECK();
   if (total_ev_cap) {
     const u64 per_slice = (total_ev_cap + g.sz - 1) / g.sz;
-    u32 gx = (u32)((per_slice + 8 * P.exChunk - 1) / (8 * P.exChunk));
-    if (gx > 64) gx = 64;
+    const u32 bs = WALK_BLOCK, wpb = bs / 32;
+    u32 gx = (u32)((per_slice + wpb * P.exChunk - 1) / (wpb * P.exChunk));
+    if (gx > 256) gx = 256;
     if (gx < 1) gx = 1;
     const u32 gy = g.sz < 65535u ? g.sz : 65535u;
     u32 gs = (u32)((per_slice + 255) / 256);
@@ -888,7 +929,7 @@ void launch_trace_post(const Geom& g, TraceBufs& T, ull* scal, u64 total_ev_cap,
     if (gs < 1) gs = 1;
     k_event_setup<<<dim3(gs, gy), 256, 0, st>>>(P);
     LAUNCH_CHECK();
-    k_expand<<<dim3(gx, gy), 256, 0, st>>>(P);
+    k_expand<<<dim3(gx, gy), bs, 0, st>>>(P);
     LAUNCH_CHECK();
   }
   // total codepoints (for the "all slices empty" rule, crackle.hpp:107-118)
