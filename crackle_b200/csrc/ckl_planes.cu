@@ -429,10 +429,12 @@ __device__ __forceinline__ void unite_word(const Geom& g, const u32* __restrict_
 // (plain store, one writer per run; upper ids are smaller, so the forest is rooted at component minima-to-be).
 // PHASE 2: every further group is a real merge -> union-find.  Most runs of a segmentation touch exactly one upper
 // run, so almost all of the work is the atomic-free phase 1.
+// PHASE 3 = phase 1 that also queues the candidates of phase 2 as (run << 16 | upper run) pairs of band-local ids, so the
+// second sweep over the words is replaced by a walk over the (short) queue; *qn counts every queued pair, stored or not.
 template <int PHASE>
 __device__ __forceinline__ void link_word(const Geom& g, const u32* __restrict__ DV, const u32* __restrict__ DH,
                                           const u32* __restrict__ wordPrefix, const u32* __restrict__ rowBase, u64 row, u32 w,
-                                          volatile u32* par, u32 base) {
+                                          volatile u32* par, u32 base, u32* queue = nullptr, u32* qn = nullptr, u32 qcap = 0) {
   const u64 i = row * g.W + w;
   const u32 valid = (w == g.W - 1 && (g.sx & 31)) ? ((1u << (g.sx & 31)) - 1u) : 0xFFFFFFFFu;
   const u32 dv = DV[i], dvu = DV[i - g.W];
@@ -465,6 +467,10 @@ __device__ __forceinline__ void link_word(const Geom& g, const u32* __restrict__
     const bool first = !(conn & seg) && !(below == 0 && hadIn);
     const u32 r = rb + __popc(below), u = rbu + __popc(dvu & mask_le(b));
     if (PHASE == 1) { if (first) par[r] = u; }
+    else if (PHASE == 3) {
+      if (first) par[r] = u;
+      else { const u32 q = atomicAdd(qn, 1u); if (q < qcap) queue[q] = (r << 16) | u; }
+    }
     else if (!first) ufc_unite(par, r, u);
   }
 }
@@ -472,12 +478,15 @@ __device__ __forceinline__ void link_word(const Geom& g, const u32* __restrict__
 // Band pass: one block owns CCL_BAND rows of one slice and solves them in shared memory (global memory when the
 // band has too many runs); the band's trees are flattened and written out with slice-local run ids.
 #define CCL_BAND 64
-#define CCL_SMEM_RUNS 12288
+#define CCL_SMEM_RUNS 10240     // 40 KB of parents + the 4 KB queue and its counter stay inside the 48 KB a kernel gets without opting in
+#define CCL_QUEUE 1024       // queued phase-2 unions per band (shared memory); a band with more takes the second sweep
 __global__ void __launch_bounds__(256) k_band_ccl(Geom g, u32 nbands, const u32* __restrict__ DV, const u32* __restrict__ DH,
                                                    const u32* __restrict__ wordPrefix, const u32* __restrict__ rowBase,
                                                    const u32* __restrict__ sliceRuns, const u64* __restrict__ runBase, u32* parent,
                                                    const u32 smem_runs) {
   extern __shared__ u32 spar[];                          // smem_runs entries
+  __shared__ u32 queue[CCL_QUEUE];
+  __shared__ u32 qn;
   const u64 nitems = (u64)g.sz * nbands;
   for (u64 item = blockIdx.x; item < nitems; item += gridDim.x) {
     const u32 z = (u32)(item / nbands), band = (u32)(item - (u64)z * nbands);
@@ -490,20 +499,28 @@ __global__ void __launch_bounds__(256) k_band_ccl(Geom g, u32 nbands, const u32*
     const bool sm = n <= smem_runs;
     volatile u32* par = sm ? spar : gpar;
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) par[i] = i;
+    if (threadIdx.x == 0) qn = 0;
     __syncthreads();
     const u32 nw = (y1 - y0 - 1) * g.W;                  // words of rows y0+1 .. y1-1
+    const bool queued = n <= 65535u;                     // band-local ids fit the 16-bit halves of a queue entry
     for (u32 k = threadIdx.x; k < nw; k += blockDim.x) {
       const u32 r = k / g.W, w = k - r * g.W;
-      link_word<1>(g, DV, DH, wordPrefix, rowBase, row0 + 1 + r, w, par, base);
+      if (queued) link_word<3>(g, DV, DH, wordPrefix, rowBase, row0 + 1 + r, w, par, base, queue, &qn, CCL_QUEUE);
+      else link_word<1>(g, DV, DH, wordPrefix, rowBase, row0 + 1 + r, w, par, base);
     }
     __syncthreads();
     // pointer jumping: any ancestor is a valid parent, so the rounds need no barriers in between
     for (int round = 0; round < 3; round++)
       for (u32 i = threadIdx.x; i < n; i += blockDim.x) { const u32 p = par[i]; const u32 pp = par[p]; if (pp != p) par[i] = pp; }
     __syncthreads();
-    for (u32 k = threadIdx.x; k < nw; k += blockDim.x) {
-      const u32 r = k / g.W, w = k - r * g.W;
-      link_word<2>(g, DV, DH, wordPrefix, rowBase, row0 + 1 + r, w, par, base);
+    const u32 nq = qn;
+    if (queued && nq <= CCL_QUEUE) {
+      for (u32 k = threadIdx.x; k < nq; k += blockDim.x) { const u32 e = queue[k]; ufc_unite(par, e >> 16, e & 0xFFFFu); }
+    } else {
+      for (u32 k = threadIdx.x; k < nw; k += blockDim.x) {
+        const u32 r = k / g.W, w = k - r * g.W;
+        link_word<2>(g, DV, DH, wordPrefix, rowBase, row0 + 1 + r, w, par, base);
+      }
     }
     __syncthreads();
     if (sm) {
@@ -733,7 +750,7 @@ void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, c
     const u64 avg = total_runs / ((u64)g.sz * nbands) + 1;
     u32 cap = (u32)std::min<u64>(CCL_SMEM_RUNS, std::max<u64>(3072, 2 * avg));
     cap = (cap + 1023u) & ~1023u;
-    const u32 per_sm = std::min<u32>(8u, (u32)((200u * 1024u) / (cap * 4u)));
+    const u32 per_sm = std::min<u32>(8u, (u32)((200u * 1024u) / (cap * 4u + CCL_QUEUE * 4u + 1024u)));
     k_band_ccl<<<grid_for((u64)g.sz * nbands, 1, per_sm), 256, (size_t)cap * 4, st>>>(g, nbands, DV, DH, B.wordPrefix.as<u32>(),
                                                                                        B.rowBase.as<u32>(), B.sliceRuns.as<u32>(),
                                                                                        B.runBase.as<u64>(), parent, cap);
