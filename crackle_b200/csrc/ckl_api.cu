@@ -34,6 +34,7 @@ struct ShardJob {
   int width = 0;
   int permissible = 0, stored_width = 0, order = 0;
   u64 runs = 0, ncomp = 0, nuniq_local = 0, ncp = 0;
+  u64 label_or = 0;                // OR of the shard's labels (same bit length as its largest label)
   u64 keys_bytes = 0, codes_bytes = 0;
   u64 codes_bytes0 = 0;            // order-0 code size of the shard, known at the end of the encode stage
   int key_width = 0;
@@ -314,6 +315,7 @@ static void shard_begin_impl(ckl_ctx* c, const void* labels, int on_device, int 
   read_scalars(c);
   J.runs = c->hscal[SC_RUNS];
   s->max_label = c->hscal[SC_MAX];
+  J.label_or = c->hscal[SC_MAX];
   s->pairs = c->hscal[SC_PAIRS];
   s->first_voxel = fl[0];
   s->last_voxel = fl[1];
@@ -387,7 +389,10 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   c->lb.mapping.ensure(J.ncomp * 8 + 8);
   c->prof.begin("labels_sort_unique", st);
   launch_gather_mapping(J.labels, J.width, g, c->ccl, J.ncomp, c->lb.mapping.as<u64>(), st);
-  labels_sort_unique(c->lb, J.ncomp, stored_width, st, &c->scal[SC_UNIQUE]);      // count picked up by the read-back below
+  // radix passes only over the bits the shard's labels have (40-bit ids in uint64 voxels: 5 passes instead of 8)
+  int label_bits = 1;
+  while (label_bits < 64 && (J.label_or >> label_bits)) label_bits++;
+  labels_sort_unique(c->lb, J.ncomp, label_bits, st, &c->scal[SC_UNIQUE]);      // count picked up by the read-back below
   c->prof.end(st);
   CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_join, 0));     // join: everything below sees the tracer's results
   launch_code_sizes_order0(g, c->tr, c->scal, st);        // order-0 code offsets / total: final unless a markov model re-codes them
@@ -888,7 +893,7 @@ static void compress_chunked(ckl_ctx* c, const void* labels, int labels_on_devic
       if (n) CUDA_CHECK(cudaMemcpyAsync(c->lb.mapping.as<u64>() + o, c->kids[k]->lb.uniq.p, n * 8, cudaMemcpyDeviceToDevice, st));
       o += n;
     }
-    nu = labels_sort_unique(c->lb, nloc, stored, st);
+    nu = labels_sort_unique(c->lb, nloc, stored * 8, st);
   }
   if (order > 0) {                                                       // markov.hpp:193-220: counters summed over all slices
     const u64 cells = 4ull << (2 * order);
@@ -1624,7 +1629,7 @@ extern "C" int ckl_zstack(ckl_ctx* c, int n, const void* const* binaries, const 
   c->lb.mapping.ensure(std::max(nloc, ncomp) * 8 + 8);
   u64 o = 0;
   for (auto& v : V) { launch_unpack_le(v.dev + v.off_uniq, v.sw, v.nu, c->lb.mapping.as<u64>() + o, st); o += v.nu; }
-  const u64 nu = labels_sort_unique(c->lb, nloc, 8, st);
+  const u64 nu = labels_sort_unique(c->lb, nloc, 64, st);
   const u64* guniq = c->lb.uniq.as<u64>();
   const int stored = ckl_byte_width(read_max_label(c, guniq, nu));
   const int kw = ckl_byte_width(nu), cw = V[0].cw;
@@ -1677,7 +1682,7 @@ extern "C" int ckl_zslice(ckl_ctx* c, const void* binary, int on_device, uint64_
   labs.ensure(nk * 8 + 8);
   stream_component_labels(c, v, k0, k1, c->dc.uniq64, c->dc.keys64, labs.as<u64>());
   if (nk) CUDA_CHECK(cudaMemcpyAsync(c->lb.mapping.p, labs.p, nk * 8, cudaMemcpyDeviceToDevice, st));
-  const u64 nu = labels_sort_unique(c->lb, nk, 8, st);
+  const u64 nu = labels_sort_unique(c->lb, nk, 64, st);
   const u64* guniq = c->lb.uniq.as<u64>();
   const int stored = ckl_byte_width(read_max_label(c, guniq, nu));
   const int kw = ckl_byte_width(nu), cw = v.cw;
@@ -1767,7 +1772,7 @@ extern "C" int ckl_sort_unique_u64(ckl_ctx* c, uint64_t* data_device, uint64_t n
   tmp.mapping.p = data_device; tmp.mapping.cap = n * 8;      // borrowed, not owned
   u64 cnt = 0;
   try {
-    cnt = labels_sort_unique(tmp, n, key_bytes, c->st);
+    cnt = labels_sort_unique(tmp, n, key_bytes * 8, c->st);
     if (cnt) CUDA_CHECK(cudaMemcpyAsync(data_device, tmp.uniq.p, cnt * 8, cudaMemcpyDeviceToDevice, c->st));
     CUDA_CHECK(cudaStreamSynchronize(c->st));
   } catch (...) { tmp.mapping.p = nullptr; tmp.mapping.cap = 0; throw; }

@@ -99,7 +99,7 @@ struct LabelBufs {
 };
 void launch_gather_mapping(const void* labels, int width, const Geom& g, const CclBufs& B, u64 ncomp, u64* mapping, cudaStream_t st);
 // sorts + uniques `mapping` (n items) into L.uniq; returns count on host (synchronises the stream)
-u64 labels_sort_unique(LabelBufs& L, u64 n, int stored_width, cudaStream_t st, ull* count_dev = nullptr);
+u64 labels_sort_unique(LabelBufs& L, u64 n, int key_bits, cudaStream_t st, ull* count_dev = nullptr);
 // keys[i] = index of mapping[i] in uniq (n_uniq entries), written little-endian with key_width bytes
 void launch_write_keys(const u64* mapping, u64 n, const u64* uniq, u64 n_uniq, int key_width, u8* dst, cudaStream_t st);
 // uniq table written little-endian with `stored_width` bytes per entry

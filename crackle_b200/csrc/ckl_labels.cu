@@ -43,7 +43,7 @@ void launch_gather_mapping(const void* labels, int width, const Geom& g, const C
 
 // count_dev != nullptr: the number of unique labels is left in *count_dev (device, u64) and NOT read back -- no stream drain;
 // the caller picks it up with its next scalar read-back.  Returns 0 in that case.
-u64 labels_sort_unique(LabelBufs& L, u64 n, int stored_width, cudaStream_t st, ull* count_dev) {
+u64 labels_sort_unique(LabelBufs& L, u64 n, int key_bits, cudaStream_t st, ull* count_dev) {
   if (n == 0) {
     if (count_dev) CUDA_CHECK(cudaMemsetAsync(count_dev, 0, 8, st));
     return 0;
@@ -52,7 +52,7 @@ u64 labels_sort_unique(LabelBufs& L, u64 n, int stored_width, cudaStream_t st, u
   L.sorted.ensure(n * 8);
   L.uniq.ensure(n * 8);
   L.flags.ensure(16);
-  const int end_bit = stored_width * 8;
+  const int end_bit = key_bits < 1 ? 1 : (key_bits > 64 ? 64 : key_bits);     // every key is below 2^key_bits
   size_t t1 = 0, t2 = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, t1, L.mapping.as<u64>(), L.sorted.as<u64>(), (int)n, 0, end_bit, st);
   cub::DeviceSelect::Unique(nullptr, t2, L.sorted.as<u64>(), L.uniq.as<u64>(), L.flags.as<u64>(), (int)n, st);
