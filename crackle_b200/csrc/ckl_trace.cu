@@ -66,18 +66,22 @@ static VGeom vgeom(const Geom& g) {
 // of vertex b sit at bits b, 8 + b, 16 + b, 24 + b; the multiply gathers them into the top byte (no carries: sums <= 15)
 __device__ __forceinline__ u32 vertex_nibble(u32 word, u32 b) { return ((((word >> b) & 0x01010101u) * 0x01020408u) >> 24); }
 // 1. vertex words + node mask + per-slice bounds: bounds[z] = {E edges, S node slots with an edge, C start-capable nodes}
+// grid = (vertex words of one slice / 256, slices): 32-bit index arithmetic, and a block's three bound sums meet in shared
+// memory before they go to the slice's counters.
 __global__ void __launch_bounds__(256) k_vw_build(Geom g, VGeom vg, const u32* __restrict__ DV, const u32* __restrict__ DH, int perm,
                                                    uint4* __restrict__ VW, u32* __restrict__ NM, u32* __restrict__ cnt, u32* bounds) {
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  const u64 nloop = (vg.wordsAll + stride - 1) / stride;
-  for (u64 it = 0; it < nloop; it++) {
-    const u64 i = it * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u32 z = NONE32, e = 0, s = 0, c = 0;
-    if (i < vg.wordsAll) {
-      const u64 row = fdiv(i, vg.Wv);
-      const u32 w = (u32)(i - row * vg.Wv);
-      z = (u32)fdiv(row, vg.sye);
-      const u32 y = (u32)(row - (u64)z * vg.sye);
+  __shared__ u32 sb[3];
+  const u32 perSlice = vg.Wv * vg.sye;                      // < 2^32: checked by the caller
+  const u32 il = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = il < perSlice;
+  const u32 y = in ? il / vg.Wv : 0u;
+  const u32 w = il - y * vg.Wv;
+  for (u32 z = blockIdx.y; z < g.sz; z += gridDim.y) {
+    if (threadIdx.x < 3) sb[threadIdx.x] = 0;
+    __syncthreads();
+    u32 e = 0, s = 0, c = 0;
+    if (in) {
+      const u64 i = (u64)z * perSlice + il;
       const u64 prow = ((u64)z * g.sy + y) * g.W;           // pixel-plane row (valid when y < sy)
       u32 r = 0, rp = 0, d = 0, u = 0;
       if (y < g.sy) {
@@ -90,7 +94,8 @@ __global__ void __launch_bounds__(256) k_vw_build(Geom g, VGeom vg, const u32* _
       const u32 s1 = r ^ l, c1 = r & l, s2 = d ^ u, c2 = d & u;
       const u32 sum0 = s1 ^ s2, carry = s1 & s2;
       const u32 two = c1 ^ c2 ^ carry, four = c1 & c2;
-      u32 n = (sum0 & ~two) | (sum0 & two) | four;          // degree 1, 3, 4
+      (void)two;
+      u32 n = sum0 | four;                                   // degree 1, 3, 4
       // (R,D)-only corners stay nodes unless their horizontal run to the right ends (inside this word) at a vertex
       // with an up edge (then the component reaches a higher row and the corner cannot be its minimum vertex)
       u32 cm = r & d & ~l & ~u;
@@ -118,21 +123,17 @@ __global__ void __launch_bounds__(256) k_vw_build(Geom g, VGeom vg, const u32* _
       s = __popc(n & r) + __popc(n & l) + __popc(n & d) + __popc(n & u);
       c = __popc(n & ~l & ~u);
     }
-    const u32 z0 = __shfl_sync(FULL_MASK, z, 0);
-    if (__all_sync(FULL_MASK, z == z0)) {
-      e = __reduce_add_sync(FULL_MASK, e);
-      s = __reduce_add_sync(FULL_MASK, s);
-      c = __reduce_add_sync(FULL_MASK, c);
-      if ((threadIdx.x & 31) == 0 && z0 != NONE32) {
-        if (e) atomicAdd(bounds + (u64)z0 * 4 + 0, e);
-        if (s) atomicAdd(bounds + (u64)z0 * 4 + 1, s);
-        if (c) atomicAdd(bounds + (u64)z0 * 4 + 2, c);
-      }
-    } else if (z != NONE32) {
-      if (e) atomicAdd(bounds + (u64)z * 4 + 0, e);
-      if (s) atomicAdd(bounds + (u64)z * 4 + 1, s);
-      if (c) atomicAdd(bounds + (u64)z * 4 + 2, c);
+    e = __reduce_add_sync(FULL_MASK, e);
+    s = __reduce_add_sync(FULL_MASK, s);
+    c = __reduce_add_sync(FULL_MASK, c);
+    if ((threadIdx.x & 31) == 0) {
+      if (e) atomicAdd(&sb[0], e);
+      if (s) atomicAdd(&sb[1], s);
+      if (c) atomicAdd(&sb[2], c);
     }
+    __syncthreads();
+    if (threadIdx.x < 3 && sb[threadIdx.x]) atomicAdd(bounds + (u64)z * 4 + threadIdx.x, sb[threadIdx.x]);
+    __syncthreads();
   }
 }
 
@@ -199,7 +200,8 @@ void launch_trace_prepare(const Geom& g, const u32* DV, const u32* DH, int permi
   u32* bounds = T.bounds.as<u32>();
   u32* caps = bounds + (u64)g.sz * 4;
   CUDA_CHECK(cudaMemsetAsync(bounds, 0, (u64)g.sz * 4 * 4, st));
-  k_vw_build<<<grid_cap(vg.wordsAll, 256, 8), 256, 0, st>>>(g, vg, DV, DH, permissible, T.VW.as<uint4>(), T.NM.as<u32>(), T.nodePrefix.as<u32>(), bounds);
+  if ((u64)vg.Wv * vg.sye > 0xFFFFFFFFull) throw CklError(CKL_ERR_ARG, "crackle_b200: slice too large");
+  k_vw_build<<<dim3((vg.Wv * vg.sye + 255) / 256, g.sz < 65535u ? g.sz : 65535u), 256, 0, st>>>(g, vg, DV, DH, permissible, T.VW.as<uint4>(), T.NM.as<u32>(), T.nodePrefix.as<u32>(), bounds);
   LAUNCH_CHECK();
   k_node_prefix<<<grid_cap(vg.rowsAll, 8, 8), 256, 0, st>>>(vg, T.nodePrefix.as<u32>(), T.rowNodes.as<u32>());
   LAUNCH_CHECK();
@@ -251,16 +253,17 @@ __device__ __forceinline__ u32 slice_of(const u64* __restrict__ base, u32 sz, u6
 }
 
 // 3a. node -> vertex, padded vertex index and static adjacency nibble
-__global__ void __launch_bounds__(256) k_node_init(TraceParams P) {
+__global__ void __launch_bounds__(256) k_node_init(TraceParams P) {      // grid = (vertex words of one slice / 256, slices)
   const VGeom vg = P.vg;
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < vg.wordsAll; i += stride) {
+  const u32 perSlice = vg.Wv * vg.sye;
+  const u32 il = blockIdx.x * blockDim.x + threadIdx.x;
+  if (il >= perSlice) return;
+  const u32 y = il / vg.Wv, w = il - y * vg.Wv;
+  for (u32 z = blockIdx.y; z < P.g.sz; z += gridDim.y) {
+    const u64 i = (u64)z * perSlice + il;
     u32 n = P.NM[i];
     if (!n) continue;
-    const u64 row = fdiv(i, vg.Wv);
-    const u32 w = (u32)(i - row * vg.Wv);
-    const u32 z = (u32)fdiv(row, vg.sye), y = (u32)(row - (u64)z * vg.sye);
-    u64 id = P.nodeBase[z] + P.rowBase[row] + P.nodePrefix[i];
+    u64 id = P.nodeBase[z] + P.rowBase[(u64)z * vg.sye + y] + P.nodePrefix[i];
     const uint4 word = P.VW[i];
     while (n) {
       const u32 b = __ffs(n) - 1;
@@ -867,7 +870,7 @@ static TraceParams make_params(const Geom& g, TraceBufs& T, ull* scal);
 bool launch_trace_nodes(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes, cudaStream_t st) {
   TraceParams P = make_params(g, T, scal);
   const VGeom vg = P.vg;
-  k_node_init<<<grid_cap(vg.wordsAll, 256, 8), 256, 0, st>>>(P);
+  k_node_init<<<dim3((vg.Wv * vg.sye + 255) / 256, g.sz < 65535u ? g.sz : 65535u), 256, 0, st>>>(P);
   LAUNCH_CHECK();
   if (!total_nodes) {
     CUDA_CHECK(cudaMemsetAsync(T.sliceInfo.p, 0, (u64)g.sz * 16, st));
