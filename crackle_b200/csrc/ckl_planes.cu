@@ -478,7 +478,7 @@ __device__ __forceinline__ void link_word(const Geom& g, const u32* __restrict__
 // Band pass: one block owns CCL_BAND rows of one slice and solves them in shared memory (global memory when the
 // band has too many runs); the band's trees are flattened and written out with slice-local run ids.
 #define CCL_BAND 64
-#define CCL_SMEM_RUNS 10240     // 40 KB of parents + the 4 KB queue and its counter stay inside the 48 KB a kernel gets without opting in
+#define CCL_SMEM_RUNS 12288     // 48 KB of parents; with the 4 KB queue beside them the launch opts in to more than 48 KB
 #define CCL_QUEUE 1024       // queued phase-2 unions per band (shared memory); a band with more takes the second sweep
 __global__ void __launch_bounds__(256) k_band_ccl(Geom g, u32 nbands, const u32* __restrict__ DV, const u32* __restrict__ DH,
                                                    const u32* __restrict__ wordPrefix, const u32* __restrict__ rowBase,
@@ -751,6 +751,8 @@ void launch_ccl_solve(const Geom& g, const u32* DV, const u32* DH, CclBufs& B, c
     u32 cap = (u32)std::min<u64>(CCL_SMEM_RUNS, std::max<u64>(3072, 2 * avg));
     cap = (cap + 1023u) & ~1023u;
     const u32 per_sm = std::min<u32>(8u, (u32)((200u * 1024u) / (cap * 4u + CCL_QUEUE * 4u + 1024u)));
+    if ((size_t)cap * 4 + CCL_QUEUE * 4 + 64 > 48 * 1024)
+      CUDA_CHECK(cudaFuncSetAttribute(k_band_ccl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CCL_SMEM_RUNS * 4)));
     k_band_ccl<<<grid_for((u64)g.sz * nbands, 1, per_sm), 256, (size_t)cap * 4, st>>>(g, nbands, DV, DH, B.wordPrefix.as<u32>(),
                                                                                        B.rowBase.as<u32>(), B.sliceRuns.as<u32>(),
                                                                                        B.runBase.as<u64>(), parent, cap);
