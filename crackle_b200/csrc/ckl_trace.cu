@@ -68,8 +68,10 @@ __device__ __forceinline__ u32 vertex_nibble(u32 word, u32 b) { return ((((word 
 // 1. vertex words + node mask + per-slice bounds: bounds[z] = {E edges, S node slots with an edge, C start-capable nodes}
 // grid = (vertex words of one slice / 256, slices): 32-bit index arithmetic, and a block's three bound sums meet in shared
 // memory before they go to the slice's counters.
-__global__ void __launch_bounds__(256) k_vw_build(Geom g, VGeom vg, const u32* __restrict__ DV, const u32* __restrict__ DH, int perm,
+template <int PERM>      // crack format as a compile-time constant: the IMPERMISSIBLE form is the plain planes
+__global__ void __launch_bounds__(256) k_vw_build(Geom g, VGeom vg, const u32* __restrict__ DV, const u32* __restrict__ DH,
                                                    uint4* __restrict__ VW, u32* __restrict__ NM, u32* __restrict__ cnt, u32* bounds) {
+  constexpr int perm = PERM;
   __shared__ u32 sb[3];
   const u32 perSlice = vg.Wv * vg.sye;                      // < 2^32: checked by the caller
   const u32 il = blockIdx.x * blockDim.x + threadIdx.x;
@@ -201,7 +203,9 @@ void launch_trace_prepare(const Geom& g, const u32* DV, const u32* DH, int permi
   u32* caps = bounds + (u64)g.sz * 4;
   CUDA_CHECK(cudaMemsetAsync(bounds, 0, (u64)g.sz * 4 * 4, st));
   if ((u64)vg.Wv * vg.sye > 0xFFFFFFFFull) throw CklError(CKL_ERR_ARG, "crackle_b200: slice too large");
-  k_vw_build<<<dim3((vg.Wv * vg.sye + 255) / 256, g.sz < 65535u ? g.sz : 65535u), 256, 0, st>>>(g, vg, DV, DH, permissible, T.VW.as<uint4>(), T.NM.as<u32>(), T.nodePrefix.as<u32>(), bounds);
+  const dim3 vgrid((vg.Wv * vg.sye + 255) / 256, g.sz < 65535u ? g.sz : 65535u);
+  if (permissible) k_vw_build<1><<<vgrid, 256, 0, st>>>(g, vg, DV, DH, T.VW.as<uint4>(), T.NM.as<u32>(), T.nodePrefix.as<u32>(), bounds);
+  else k_vw_build<0><<<vgrid, 256, 0, st>>>(g, vg, DV, DH, T.VW.as<uint4>(), T.NM.as<u32>(), T.nodePrefix.as<u32>(), bounds);
   LAUNCH_CHECK();
   k_node_prefix<<<grid_cap(vg.rowsAll, 8, 8), 256, 0, st>>>(vg, T.nodePrefix.as<u32>(), T.rowNodes.as<u32>());
   LAUNCH_CHECK();
@@ -317,6 +321,7 @@ __device__ __forceinline__ void red_or_u32_if(u32* a, u32 v, bool p) {
 // Small chunks = many warps per slice = few slices in flight at once: the vertex words the walkers chase (541 KB per
 // 1024^2 slice) then stay L2-resident instead of streaming from DRAM once per step.
 #define PW_CHUNK 128u
+#define PW_PASS1_MULT 4u
 template <int PASS>
 __global__ void __launch_bounds__(WALK_BLOCK) k_path_walk(TraceParams P) {
   const VGeom vg = P.vg;
@@ -889,6 +894,10 @@ void launch_trace_paths(const Geom& g, TraceBufs& T, ull* scal, u32 max_nodes, c
   if (gx < 1) gx = 1;
   k_path_walk<0><<<dim3(gx, gy), bs, 0, st>>>(P);
   LAUNCH_CHECK();
+  // pass 1 finds most of its slots already filled from the other end: four times the slots per warp keep its lanes busy
+  P.pwChunk *= PW_PASS1_MULT;
+  gx = (2u * max_nodes + wpb * P.pwChunk - 1) / (wpb * P.pwChunk);
+  if (gx < 1) gx = 1;
   k_path_walk<1><<<dim3(gx, gy), bs, 0, st>>>(P);
   LAUNCH_CHECK();
 }
