@@ -445,7 +445,7 @@ def main():
             f"{names[0]}_gvox_s": V / (t_a * 1e-3) / 1e9, f"{names[0]}_ms": t_a, f"{names[0]}_hbm_frac": roof[names[0]]["frac"],
             f"{names[1]}_gvox_s": V / (t_b * 1e-3) / 1e9, f"{names[1]}_ms": t_b, f"{names[1]}_hbm_frac": roof[names[1]]["frac"]}
     if job is not None:
-        line["collectives_per_compress"] = "metadata all_gather + unique-table all_gather + ONE padded all_gather of the packed blocks" + \
+        line["collectives_per_compress"] = "metadata all_gather + unique-table all_gather (both beside the tracer's chain replay) + code-size all_gather + ONE padded all_gather of the packed blocks" + \
                                            (" + statistics all_reduce + code-size all_gather (order > 0)" if args.order > 0 else "")
 
     # end to end through the public host API: pinned HOST buffers, H2D + D2H inside the timed region, every rank through its

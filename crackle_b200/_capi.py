@@ -58,6 +58,8 @@ SYMBOLS = {
     "ckl_zslice": (cint, [vp, vp, cint, u64, u64, u64, ctypes.POINTER(u64)]),
     "ckl_shard_begin": (cint, [vp, vp, cint, cint, u64, u64, u64, ctypes.POINTER(ShardSummary)]),
     "ckl_shard_encode": (cint, [vp, cint, cint, cint, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(u64)]),
+    "ckl_shard_encode_async": (cint, [vp, cint, cint, cint, ctypes.POINTER(u64), ctypes.POINTER(u64)]),
+    "ckl_shard_encode_wait": (cint, [vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]),
     "ckl_shard_unique": (cint, [vp, vp, cint]),
     "ckl_shard_stats": (cint, [vp, vp, cint]),
     "ckl_shard_finish": (cint, [vp, vp, cint, u64, vp, cint, ctypes.POINTER(ShardPieces)]),

@@ -40,6 +40,7 @@ struct ShardJob {
   int key_width = 0;
   const u64* guniq = nullptr;      // global sorted unique table (device) the keys are written against
   u64 nuniq_global = 0;
+  bool queued = false;             // encode stage queued, CCL / label results read back, tracer possibly still running
   bool encoded = false, finished = false;
 };
 
@@ -324,9 +325,14 @@ static void shard_begin_impl(ckl_ctx* c, const void* labels, int on_device, int 
   J.active = true;
 }
 
-static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int order) {
+// The encode stage in two halves.  shard_encode_queue queues both chains and returns once the CCL / label chain is through
+// (component and unique-label counts known, the shard's sorted unique table ready) while the tracing chain may still be
+// running on its side streams; shard_encode_join waits for the tracer and reads the code sizes.  A z-sharded caller puts its
+// metadata and unique-table exchange between the two, beside the serial chain replay.
+static void shard_encode_queue(ckl_ctx* c, int permissible, int stored_width, int order) {
   ShardJob& J = c->job;
   if (!J.active) throw CklError(CKL_ERR_ARG, "crackle_b200: ckl_shard_encode without ckl_shard_begin");
+  J.queued = J.encoded = J.finished = false;
   if (order < 0 || order > 12) throw CklError(CKL_ERR_ARG, "crackle_b200: markov_model_order must be in [0, 12]");
   J.permissible = permissible ? 1 : 0;
   J.stored_width = stored_width;
@@ -394,6 +400,14 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
   while (label_bits < 64 && (J.label_or >> label_bits)) label_bits++;
   labels_sort_unique(c->lb, J.ncomp, label_bits, st, &c->scal[SC_UNIQUE]);      // count picked up by the read-back below
   c->prof.end(st);
+  J.queued = true;
+}
+static void shard_encode_join(ckl_ctx* c) {
+  ShardJob& J = c->job;
+  if (!J.queued) throw CklError(CKL_ERR_ARG, "crackle_b200: ckl_shard_encode_wait without ckl_shard_encode_async");
+  const Geom& g = J.g;
+  cudaStream_t st = c->st;
+  const int order = J.order;
   CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_join, 0));     // join: everything below sees the tracer's results
   launch_code_sizes_order0(g, c->tr, c->scal, st);        // order-0 code offsets / total: final unless a markov model re-codes them
   read_scalars(c);
@@ -406,7 +420,12 @@ static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int
     c->mk.stats.ensure(rows * 16);
     STAGE(c, "markov_stats", launch_markov_stats(g, c->tr, order, c->mk.stats.as<u32>(), st));
   }
+  J.queued = false;
   J.encoded = true;
+}
+static void shard_encode_impl(ckl_ctx* c, int permissible, int stored_width, int order) {
+  shard_encode_queue(c, permissible, stored_width, order);
+  shard_encode_join(c);
 }
 
 // keys_dst / codes_dst: device destinations (may point into the final stream)
@@ -478,9 +497,26 @@ extern "C" int ckl_shard_encode(ckl_ctx* c, int permissible, int stored_width, i
   if (n_codepoints_local) *n_codepoints_local = c->job.ncp;
   API_END(c)
 }
+extern "C" int ckl_shard_encode_async(ckl_ctx* c, int permissible, int stored_width, int markov_model_order, uint64_t* n_unique_local,
+                                      uint64_t* n_components_local) {
+  API_BEGIN(c)
+  shard_encode_queue(c, permissible, stored_width, markov_model_order);
+  read_scalars(c);                                        // drains the main stream only: the CCL / label chain
+  c->job.nuniq_local = c->hscal[SC_UNIQUE];
+  if (n_unique_local) *n_unique_local = c->job.nuniq_local;
+  if (n_components_local) *n_components_local = c->job.ncomp;
+  API_END(c)
+}
+extern "C" int ckl_shard_encode_wait(ckl_ctx* c, uint64_t* n_codepoints_local, uint64_t* codes_bytes_order0) {
+  API_BEGIN(c)
+  shard_encode_join(c);
+  if (n_codepoints_local) *n_codepoints_local = c->job.ncp;
+  if (codes_bytes_order0) *codes_bytes_order0 = c->job.codes_bytes0;
+  API_END(c)
+}
 extern "C" int ckl_shard_unique(ckl_ctx* c, uint64_t* dst, int dst_on_device) {
   API_BEGIN(c)
-  if (!c->job.encoded) throw CklError(CKL_ERR_ARG, "crackle_b200: no encoded shard");
+  if (!c->job.encoded && !c->job.queued) throw CklError(CKL_ERR_ARG, "crackle_b200: no encoded shard");
   if (c->job.nuniq_local) {
     CUDA_CHECK(cudaMemcpyAsync(dst, c->lb.uniq.p, c->job.nuniq_local * 8, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
     CUDA_CHECK(cudaStreamSynchronize(c->st));

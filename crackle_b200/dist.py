@@ -98,6 +98,21 @@ class CudaShardBackend:
         self.n_unique_local, self.ncomp = nu.value, nc.value
         return nu.value, nc.value, ncp.value
 
+    def encode_async(self, permissible, stored_width, order):
+        """queues the encode stage; returns when the CCL / label chain is through (the tracer may still be running)."""
+        nu, nc = ctypes.c_uint64(), ctypes.c_uint64()
+        self.order = order
+        self._check(self.L.ckl_shard_encode_async(self.ctx._h, int(permissible), int(stored_width), int(order), ctypes.byref(nu),
+                                                  ctypes.byref(nc)))
+        self.n_unique_local, self.ncomp = nu.value, nc.value
+        return nu.value, nc.value
+
+    def encode_wait(self):
+        """joins the tracer; -> (codepoints, order-0 code bytes) of the shard"""
+        ncp, cb = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self.L.ckl_shard_encode_wait(self.ctx._h, ctypes.byref(ncp), ctypes.byref(cb)))
+        return ncp.value, cb.value
+
     def info(self):
         c = _capi.ShardCounts()
         self._check(self.L.ckl_shard_info(self.ctx._h, ctypes.byref(c)))
@@ -186,7 +201,6 @@ class ShardedCodec:
     """compress(): every rank passes its z-slab and EVERY rank gets the complete .ckl stream (uint8 tensor on the
     backend's device), byte-identical to compressing the whole volume at once."""
 
-    META = 10      # int64 fields per rank in the one metadata all_gather
 
     def __init__(self, ctx_or_backend, dist, backend=None):
         self.dist = dist
@@ -234,11 +248,21 @@ class ShardedCodec:
         self._marks.append((name, (t - self._t0) * 1e3))
         self._t0 = t
 
-    def _meta(self, s, sz_local):
+    def _encode_async(self, permissible, stored_width, order):
+        """-> (n_unique_local, n_components); backends without the split stage (test stand-ins) encode in one go"""
         be = self.be
+        if hasattr(be, "encode_async"):
+            return be.encode_async(permissible, stored_width, order)
+        nu, nc, ncp = be.encode(permissible, stored_width, order)
+        return nu, nc
+
+    def _encode_wait(self):
+        """-> (n_codepoints, codes_bytes_order0) of this shard"""
+        be = self.be
+        if hasattr(be, "encode_wait"):
+            return be.encode_wait()
         info = be.info()
-        return [_i64(s["max_label"]), _i64(s["pairs"]), _i64(s["first_voxel"]), _i64(s["last_voxel"]), _i64(s["voxels"]), sz_local,
-                info["n_unique_local"], info["n_components"], info["n_codepoints"], info["codes_bytes_order0"]]
+        return info["n_codepoints"], info["codes_bytes_order0"]
 
     def compress(self, vol, z0, sz_total, markov_model_order=0, fortran_order=True):
         be, dist, W, R = self.be, self.dist, self.world, self.rank
@@ -247,14 +271,16 @@ class ShardedCodec:
         s = be.begin(vol)
         sx, sy, sz_local = be.shape
         data_width = be.width
-        # (1) encode with the crack format this shard's own statistics suggest (crackle.hpp:50-55); the global decision
-        # is checked right after the one metadata exchange
+        # (1) encode with the crack format this shard's own statistics suggest (crackle.hpp:50-55).  The stage is only QUEUED:
+        # the call returns when the CCL / label chain is through, and the first metadata exchange and the merge of the unique
+        # tables run beside the tracer's serial chain replay; the global decision is checked right after that exchange.
         guess = int(s["pairs"]) < int(s["voxels"]) // 2
-        be.encode(guess, byte_width(int(s["max_label"])), markov_model_order)
-        self._mark("begin+encode")
+        nu_local, ncomp_local = self._encode_async(guess, byte_width(int(s["max_label"])), markov_model_order)
+        self._mark("begin+encode_async")
         redone = False
         while True:
-            meta = self._all_gather_i64(self._meta(s, sz_local))
+            meta = self._all_gather_i64([_i64(s["max_label"]), _i64(s["pairs"]), _i64(s["first_voxel"]), _i64(s["last_voxel"]),
+                                         _i64(s["voxels"]), sz_local, nu_local, ncomp_local])
             max_label = max(int(a[0]) for a in meta)
             pairs = sum(int(a[1]) for a in meta)
             for r in range(1, W):                  # the flat-index pair straddling each shard boundary (lib.hpp:249-256)
@@ -268,20 +294,25 @@ class ShardedCodec:
             if not wrong or redone:
                 break
             if R in wrong:                             # rare: this shard's guess differs from the global decision
+                self._encode_wait()
                 s = be.begin(vol)
-                be.encode(permissible, stored, markov_model_order)
+                nu_local, ncomp_local = self._encode_async(permissible, stored, markov_model_order)
             redone = True
         nu_all = [int(a[6]) for a in meta]
         ncomp_all = [int(a[7]) for a in meta]
-        order = markov_model_order
-        if order > 0 and sum(int(a[8]) for a in meta) == 0:
-            order = 0                              # crackle.hpp:107-118
         self._mark("meta")
         # (2) global sorted unique label table: identical merge on every rank
         parts = self._all_gather_var(be.unique(), nu_all)
         guniq = be.sort_unique(torch.cat(parts) if W > 1 else parts[0].clone(), stored)
         nu = int(guniq.numel())
         self._mark("unique_merge")
+        # (2b) join the tracer; the code sizes travel in a second small exchange
+        ncp_local, codes0_local = self._encode_wait()
+        meta2 = self._all_gather_i64([ncp_local, codes0_local])
+        order = markov_model_order
+        if order > 0 and sum(int(a[0]) for a in meta2) == 0:
+            order = 0                              # crackle.hpp:107-118
+        self._mark("encode_wait+meta2")
         # (3) global markov statistics
         gstats = None
         if order > 0:
@@ -296,7 +327,7 @@ class ShardedCodec:
         if order > 0:
             codes_all = [int(a[0]) for a in self._all_gather_i64([pc["codes_bytes"]])]
         else:
-            codes_all = [int(a[9]) for a in meta]
+            codes_all = [int(a[1]) for a in meta2]
         assert pc["keys_bytes"] == keys_all[R] and pc["codes_bytes"] == codes_all[R]
         self._mark("finish")
         # (5) ONE padded all_gather of the packed blocks; every rank then holds every piece

@@ -148,6 +148,15 @@ CKL_API int ckl_shard_begin(ckl_ctx* ctx, const void* labels, int labels_on_devi
  * permissible / stored_width are the GLOBAL decisions.  markov stats (if order > 0) are accumulated locally. */
 CKL_API int ckl_shard_encode(ckl_ctx* ctx, int permissible, int stored_width, int markov_model_order,
                      uint64_t* n_unique_local, uint64_t* n_components_local, uint64_t* n_codepoints_local);
+/* The same stage in two halves, for callers that overlap their exchange with the serial part of the tracer:
+ * ckl_shard_encode_async queues the whole stage and returns when the CCL / label chain is through -- the two counts are
+ * final and ckl_shard_unique may be called -- while the crack-code tracing may still be running on the context's side
+ * streams; ckl_shard_encode_wait joins the tracer and returns the codepoint count and the order-0 code size.
+ * ckl_shard_encode == ckl_shard_encode_async followed by ckl_shard_encode_wait.  (Reference precedent for encoding slabs
+ * independently and merging their label tables afterwards: crackle/operations.py:258-295, 424-548.) */
+CKL_API int ckl_shard_encode_async(ckl_ctx* ctx, int permissible, int stored_width, int markov_model_order,
+                           uint64_t* n_unique_local, uint64_t* n_components_local);
+CKL_API int ckl_shard_encode_wait(ckl_ctx* ctx, uint64_t* n_codepoints_local, uint64_t* codes_bytes_order0);
 /* Copies the shard's sorted unique labels (uint64 each) to dst (host or device). */
 CKL_API int ckl_shard_unique(ckl_ctx* ctx, uint64_t* dst, int dst_on_device);
 /* Markov statistics of the shard: uint32[4^order * 4] (wrap mod 2^32 like the reference's atomics). */

@@ -147,7 +147,7 @@ def test_two_rank_sharded_compress_is_byte_identical(kind, split):
     assert sorted(r for r, _, _ in got) == [0, 1]
     for _, stream, ncoll in got:
         assert stream == want
-        assert ncoll == 3            # metadata, unique tables, packed blocks: no per-peer send/recv, no broadcast
+        assert ncoll == 4            # metadata, unique tables, code sizes, packed blocks: no per-peer send/recv, no broadcast
 
 
 def test_header_helper_matches_oracle():

@@ -150,7 +150,7 @@ def test_sharded_equals_monolithic_threads(order, world, kind):
     for r in range(world):
         assert results["stream", r] == want
         # metadata (+1 when a shard re-encodes), unique tables, packed blocks; order > 0 adds statistics + code sizes
-        assert results["collectives", r] == 3 + (kind == "mixed") + 2 * (order > 0)
+        assert results["collectives", r] == 4 + (kind == "mixed") + 2 * (order > 0)
     assert all(results[r] for r in range(world))
 
 
