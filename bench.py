@@ -59,7 +59,10 @@ def parse_args():
     ap.add_argument("--order", type=int, default=None, help="markov_model_order")
     ap.add_argument("--cpu-slices", type=int, default=128, help="z-slab size of the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-pipeline", default="auto", choices=["auto", "on", "off"],
+                    help="e2e: double-buffer the steps (compress of step i+1 beside decompress of step i); auto = on at N = 1")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-numpy-e2e", action="store_true", help="skip the pageable-numpy end-to-end measurement (N = 1)")
     ap.add_argument("--no-parity", action="store_true", help="skip the byte-parity checks of the warm-up (round trip is always checked)")
     ap.add_argument("--prof", action="store_true", help="print per-stage timings to stderr")
     ap.add_argument("--chunks", type=int, default=0, help="z-chunk pipelining: 0 = library default (host-resident volumes only), 1 = off, K = force")
@@ -476,32 +479,122 @@ def main():
             ctx.result_to(hstream.data_ptr(), 0, hstream.numel())
             ctx.decompress_into(hstream.data_ptr(), 0, n, 0, -1, None, hout.data_ptr(), 0, hout.numel() * width)
             return n
+
+        def timed_wall(fn, reps):
+            """wall clock of `reps` calls of fn between barriers (device drained both sides), max over ranks, per call"""
+            torch.cuda.synchronize()
+            if dist:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                r = fn()
+            torch.cuda.synchronize()
+            te = (time.perf_counter() - t0) / reps
+            if dist:
+                x = torch.tensor([te], device="cuda", dtype=torch.float64)
+                dist.all_reduce(x, op=dist.ReduceOp.MAX)
+                te = float(x.item())
+            return te, r
+
         e2e_step()
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        t0 = time.perf_counter()
         ne = max(1, min(args.steps, 3))
-        for _ in range(ne):
-            n = e2e_step()
-        torch.cuda.synchronize()
-        te = (time.perf_counter() - t0) / ne
-        if dist:
-            x = torch.tensor([te], device="cuda", dtype=torch.float64)
-            dist.all_reduce(x, op=dist.ReduceOp.MAX)
-            te = float(x.item())
+        te, n = timed_wall(e2e_step, ne)
         assert torch.equal(hout.view(torch.uint8), hvol.view(torch.uint8))
         if args.mode == "decode":
             h2d, d2h = 2 * ckl_bytes * world, V * width + V
         else:
             h2d, d2h = V * width + (n if world == 1 else 0), n + V * width
-        line["e2e"] = {"value": 2.0 * V / te / 1e9, "unit": "GVox/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                       "ms_per_step": te * 1e3,
-                       "api": ("ckl_decompress with pinned HOST stream and output buffers" if args.mode == "decode" else
-                               "ckl_compress / ckl_decompress with pinned HOST buffers (what fastcrackle.compress/decompress bind)" if world == 1 else
-                               "ShardedCodec.compress / decompress_shard with each rank's slab in pinned HOST memory (ckl_shard_* + ckl_decompress)"),
-                       "chunks": ("library default: 4 z-chunks on child contexts for host-resident volumes, so H2D / D2H copies of one chunk "
-                                  "overlap the kernels of the others" if args.chunks == 0 else args.chunks) if world == 1 else "one slab per rank"}
+        api = ("ckl_decompress with pinned HOST stream and output buffers" if args.mode == "decode" else
+               "ckl_compress / ckl_decompress with pinned HOST buffers (what fastcrackle.compress/decompress bind)" if world == 1 else
+               "ShardedCodec.compress / decompress_shard with each rank's slab in pinned HOST memory (ckl_shard_* + ckl_decompress)")
+        chunks = ("library default: 4 z-chunks on child contexts for host-resident volumes, so H2D / D2H copies of one chunk "
+                  "overlap the kernels of the others" if args.chunks == 0 else args.chunks) if world == 1 else "one slab per rank"
+        serial = {"value": 2.0 * V / te / 1e9, "unit": "GVox/s", "ms_per_step": te * 1e3, "steps": ne,
+                  "schedule": "one call after the other on one host thread: PCIe carries one direction at a time"}
+        line["e2e"] = {"value": serial["value"], "unit": "GVox/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "ms_per_step": te * 1e3, "api": api, "chunks": chunks, "schedule": serial["schedule"]}
+
+        # The same calls double-buffered over the steps, as a service that streams volumes through the codec runs them: the
+        # compress call of step i+1 (H2D-bound) beside the decompress call of step i (D2H-bound) on a second context and a
+        # second host thread, so both directions of the PCIe link are busy.  Every step still uploads its volume, downloads its
+        # stream and its decoded volume; K steps are timed from the first upload to the last download (fill and drain included).
+        pipelined = args.e2e_pipeline == "on" or (args.e2e_pipeline == "auto" and world == 1)
+        if pipelined and args.mode == "roundtrip":
+            ctx2 = cb.Context(local)                  # the decompress side: own stream, own workspaces
+            ctx2.set_chunks(args.chunks)
+            hs = [hstream, torch.empty(hstream.numel(), dtype=torch.uint8, pin_memory=True)]
+            ds = [torch.empty(ckl_bytes + 64, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
+            hout.zero_()
+            fails = []
+
+            def comp(i):
+                if world > 1:
+                    st = job.compress(hvol, z0=z0, sz_total=sz_total, markov_model_order=args.order)
+                    m = int(st.numel())
+                    ds[i & 1][:m].copy_(st)           # the context's result buffer is reused by the next compress
+                    if rank == 0:
+                        ctx.result_to(hs[i & 1].data_ptr(), 0, hs[i & 1].numel())
+                    torch.cuda.current_stream().synchronize()
+                    return m
+                m = ctx.compress_ptr(hvol.data_ptr(), 0, width, sx, sy, szl, True, args.order)
+                ctx.result_to(hs[i & 1].data_ptr(), 0, hs[i & 1].numel())
+                return m
+
+            def decomp(i, m):
+                try:
+                    if world > 1:
+                        ctx2.decompress_into(ds[i & 1].data_ptr(), 1, m, z0, z1, None, hout.data_ptr(), 0, hout.numel() * width)
+                    else:
+                        ctx2.decompress_into(hs[i & 1].data_ptr(), 0, m, 0, -1, None, hout.data_ptr(), 0, hout.numel() * width)
+                except Exception as e:                # surfaced after the join
+                    fails.append(e)
+
+            def pipeline(K):
+                m = comp(0)
+                for i in range(1, K):
+                    th = threading.Thread(target=decomp, args=(i - 1, m))
+                    th.start()
+                    m2 = comp(i)
+                    th.join()
+                    m = m2
+                decomp(K - 1, m)
+                if fails:
+                    raise fails[0]
+                return m
+
+            pipeline(2)                               # untimed: workspaces of the second context
+            K = max(2, args.steps)
+            tp, _ = timed_wall(lambda: pipeline(K), 1)
+            tp /= K
+            assert torch.equal(hout.view(torch.uint8), hvol.view(torch.uint8)), "pipelined e2e: round trip mismatch"
+            line["e2e"].update({"value": 2.0 * V / tp / 1e9, "ms_per_step": tp * 1e3, "steps": K,
+                                "schedule": f"double-buffered over {K} steps: the compress call of step i+1 runs beside the decompress call of "
+                                            "step i (second context, second host thread), both PCIe directions busy; every step uploads its "
+                                            "volume and downloads its stream and its decoded volume; fill and drain inside the timed region",
+                                "serial": serial})
+            ctx2.close()
+            del ctx2, hs, ds
+        # What a caller of the reference's Python interface sees (crackle.compress(ndarray) -> bytes, decompress(bytes) ->
+        # ndarray): PAGEABLE numpy memory, the stream returned as a bytes object, a fresh output array per call.
+        if world == 1 and args.mode == "roundtrip" and not args.no_numpy_e2e:
+            try:
+                arr = np.asfortranarray(np.array(hvol.numpy().transpose(2, 1, 0)))      # pageable copy, F order
+                del hout
+                hout = None
+                b = ctx.compress(arr, args.order)
+                t0 = time.perf_counter()
+                b = ctx.compress(arr, args.order)
+                t1 = time.perf_counter()
+                back = ctx.decompress(b)
+                t2 = time.perf_counter()
+                assert len(b) == ckl_bytes and np.array_equal(back.reshape(arr.shape, order="F"), arr)
+                line["e2e"]["numpy_api"] = {"value": 2.0 * V / (t2 - t0) / 1e9, "unit": "GVox/s", "compress_ms": (t1 - t0) * 1e3,
+                                            "decompress_ms": (t2 - t1) * 1e3,
+                                            "api": "Context.compress(ndarray) -> bytes / Context.decompress(bytes) -> ndarray (the calls behind "
+                                                   "crackle_b200.compress / decompress): pageable host memory, one step"}
+                del arr, back, b
+            except MemoryError as e:
+                line["e2e"]["numpy_api"] = {"skipped": f"host memory: {e}"}
         del hvol, hout, hstream
 
     if not args.no_cpu and rank == 0:

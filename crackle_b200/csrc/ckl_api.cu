@@ -147,6 +147,7 @@ struct ckl_ctx {
   bool is_kid = false;
   int chunks = 0;                          // 0 = automatic, 1 = off, K = force K chunks
   cudaEvent_t ev_done = nullptr;
+  struct HostStager* stager = nullptr;     // pinned staging ring for bulk copies from / to PAGEABLE host memory (lazy)
 };
 
 static void set_err(char* err, size_t n, const std::string& m) {
@@ -156,6 +157,100 @@ static void set_err(char* err, size_t n, const std::string& m) {
 static void read_scalars(ckl_ctx* c) {
   CUDA_CHECK(cudaMemcpyAsync(c->hscal, c->scal, SC_COUNT * sizeof(ull), cudaMemcpyDeviceToHost, c->st));
   CUDA_CHECK(cudaStreamSynchronize(c->st));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Bulk copies between PAGEABLE host memory and the device -- what a caller of the Python interface hands over (numpy
+// arrays, bytes objects; the reference's crackle.compress / decompress take and return exactly those).  cudaMemcpyAsync on
+// pageable memory is staged by the driver through one bounce buffer on the calling thread: measured on the bench box
+// 10 GB/s up and 4 GB/s down (into untouched pages of a fresh output array) for a 8.6 GB volume, against 55 GB/s for pinned
+// memory.  Here HS_THREADS host threads each move their share of the range through two pinned stages on their own stream:
+// a thread copies one stage (first touch of the destination pages included, in parallel) while the DMA engine moves
+// the other.  Pinned or registered memory, device pointers and small copies keep the plain asynchronous copy.
+struct ChunkErr { int code = 0; std::string msg; };
+#define HS_THREADS 8
+#define HS_STAGE (4ull << 20)
+#define HS_MIN_BYTES (16ull << 20)
+struct HostStager {
+  u8* pin = nullptr;
+  cudaStream_t st[HS_THREADS] = {};
+  cudaEvent_t ev[HS_THREADS][2] = {};
+  u8* stage(int t, int s) const { return pin + ((u64)t * 2 + s) * HS_STAGE; }
+  void create() {
+    CUDA_CHECK(cudaMallocHost(&pin, (u64)HS_THREADS * 2 * HS_STAGE));
+    for (int t = 0; t < HS_THREADS; t++) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&st[t], cudaStreamNonBlocking));
+      for (int s = 0; s < 2; s++) CUDA_CHECK(cudaEventCreateWithFlags(&ev[t][s], cudaEventDisableTiming));
+    }
+  }
+  ~HostStager() {
+    for (int t = 0; t < HS_THREADS; t++) {
+      for (int s = 0; s < 2; s++) if (ev[t][s]) cudaEventDestroy(ev[t][s]);
+      if (st[t]) cudaStreamDestroy(st[t]);
+    }
+    if (pin) cudaFreeHost(pin);
+  }
+};
+static bool host_ptr_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+// host <-> device copy of `bytes` ordered after everything queued on `st`.  Pinned host memory / small sizes: queued on `st`
+// like cudaMemcpyAsync.  Large pageable ranges: staged as described above; returns when the bytes have arrived.
+static void copy_host(ckl_ctx* c, void* dst, const void* src, u64 bytes, bool to_device, cudaStream_t st) {
+  if (!bytes) return;
+  const void* hptr = to_device ? src : dst;
+  if (bytes < HS_MIN_BYTES || !host_ptr_pageable(hptr)) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st));
+    return;
+  }
+  if (!c->stager) { c->stager = new HostStager(); c->stager->create(); }
+  HostStager& S = *c->stager;
+  CUDA_CHECK(cudaStreamSynchronize(st));               // down: the producer of the device buffer; up: its previous readers
+  const u64 per = (((bytes + HS_THREADS - 1) / HS_THREADS) + 4095) & ~4095ull;
+  ChunkErr errs[HS_THREADS];
+  auto worker = [&](int t) {
+    try {
+      CUDA_CHECK(cudaSetDevice(c->device));
+      const u64 lo = std::min(bytes, per * (u64)t), hi = std::min(bytes, lo + per);
+      const u64 nb = (hi - lo + HS_STAGE - 1) / HS_STAGE;
+      auto blk = [&](u64 i, u64& off, u64& n) { off = lo + i * HS_STAGE; n = std::min<u64>(HS_STAGE, hi - off); };
+      u64 off, n;
+      if (to_device) {
+        for (u64 i = 0; i < nb; i++) {
+          const int s = (int)(i & 1);
+          blk(i, off, n);
+          if (i >= 2) CUDA_CHECK(cudaEventSynchronize(S.ev[t][s]));      // the DMA out of this stage two blocks ago
+          memcpy(S.stage(t, s), (const u8*)src + off, n);
+          CUDA_CHECK(cudaMemcpyAsync((u8*)dst + off, S.stage(t, s), n, cudaMemcpyHostToDevice, S.st[t]));
+          CUDA_CHECK(cudaEventRecord(S.ev[t][s], S.st[t]));
+        }
+      } else {
+        auto issue = [&](u64 i) {
+          u64 o, m;
+          blk(i, o, m);
+          CUDA_CHECK(cudaMemcpyAsync(S.stage(t, (int)(i & 1)), (const u8*)src + o, m, cudaMemcpyDeviceToHost, S.st[t]));
+          CUDA_CHECK(cudaEventRecord(S.ev[t][i & 1], S.st[t]));
+        };
+        if (nb) issue(0);
+        for (u64 i = 0; i < nb; i++) {
+          if (i + 1 < nb) issue(i + 1);                                  // its stage was emptied in the previous round
+          blk(i, off, n);
+          CUDA_CHECK(cudaEventSynchronize(S.ev[t][i & 1]));
+          memcpy((u8*)dst + off, S.stage(t, (int)(i & 1)), n);
+        }
+      }
+      CUDA_CHECK(cudaStreamSynchronize(S.st[t]));
+    } catch (const CklError& e) { errs[t].code = e.code; errs[t].msg = e.what(); cudaGetLastError(); }
+    catch (const std::exception& e) { errs[t].code = CKL_ERR_CUDA; errs[t].msg = e.what(); }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < HS_THREADS; t++) th.emplace_back(worker, t);
+  worker(0);
+  for (auto& x : th) x.join();
+  for (int t = 0; t < HS_THREADS; t++)
+    if (errs[t].code) throw CklError(errs[t].code, errs[t].msg);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -259,6 +354,7 @@ extern "C" void ckl_ctx_destroy(ckl_ctx* c) {
   if (c->scal) cudaFree(c->scal);
   if (c->hscal) cudaFreeHost(c->hscal);
   if (c->hscal2) cudaFreeHost(c->hscal2);
+  delete c->stager;
   delete c;
 }
 extern "C" const char* ckl_ctx_error(const ckl_ctx* c) { return c ? c->err.c_str() : "null context"; }
@@ -295,7 +391,7 @@ static void shard_begin_impl(ckl_ctx* c, const void* labels, int on_device, int 
       while (c->stg->seq.load(std::memory_order_acquire) < c->stg_index) std::this_thread::yield();
       if (c->stg_index > 0) CUDA_CHECK(cudaStreamWaitEvent(c->st, c->stg->ev[c->stg_index - 1], 0));
     }
-    CUDA_CHECK(cudaMemcpyAsync(c->labels_dev.p, labels, voxels * (u64)width, cudaMemcpyHostToDevice, c->st));
+    copy_host(c, c->labels_dev.p, labels, voxels * (u64)width, true, c->st);
     if (c->stg) {
       CUDA_CHECK(cudaEventRecord(c->stg->ev[c->stg_index], c->st));
       int expect = c->stg_index;
@@ -736,7 +832,6 @@ extern "C" int ckl_shard_assemble(ckl_ctx* c, const uint8_t* gathered, const ckl
 
 // ---------------------------------------------------------------------------------------------------------
 // z-chunk pipelining helpers
-struct ChunkErr { int code = 0; std::string msg; };
 
 static void ensure_kids(ckl_ctx* c, int K) {
   while ((int)c->kids.size() < K) {
@@ -1090,7 +1185,8 @@ extern "C" int ckl_result_copy(ckl_ctx* c, void* dst, int dst_on_device, uint64_
   API_BEGIN(c)
   if (capacity < c->result_bytes) throw CklError(CKL_ERR_ARG, "crackle_b200: result buffer too small");
   if (c->result_bytes) {
-    CUDA_CHECK(cudaMemcpyAsync(dst, c->result.p, c->result_bytes, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
+    if (dst_on_device) CUDA_CHECK(cudaMemcpyAsync(dst, c->result.p, c->result_bytes, cudaMemcpyDeviceToDevice, c->st));
+    else copy_host(c, dst, c->result.p, c->result_bytes, false, c->st);
     CUDA_CHECK(cudaStreamSynchronize(c->st));
   }
   API_END(c)
@@ -1203,7 +1299,7 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
   const u8* dstream = dbin;
   if (!dstream) {
     c->stream_dev.ensure(num_bytes + 8);
-    CUDA_CHECK(cudaMemcpyAsync(c->stream_dev.p, hbin, num_bytes, cudaMemcpyHostToDevice, st));
+    copy_host(c, c->stream_dev.p, hbin, num_bytes, true, st);
     dstream = c->stream_dev.as<u8>();
   }
   // Large Fortran-order outputs: K z-chunks on child contexts (each a z-range decode into its own part of the output),
@@ -1355,7 +1451,7 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
   void* dout = out;
   if (!out_on_device) { c->out_dev.ensure(voxels * (u64)ow); dout = c->out_dev.p; }
   STAGE(c, "d_paint", launch_paint(g, c->DV.as<u32>(), c->ccl, D.runLabel.as<u64>(), ow, has_label, label, (int)h.fortran_order, dout, st));
-  if (!out_on_device) CUDA_CHECK(cudaMemcpyAsync(out, dout, voxels * (u64)ow, cudaMemcpyDeviceToHost, st));
+  if (!out_on_device) copy_host(c, out, dout, voxels * (u64)ow, false, st);
   read_scalars(c);                                       // the one drain at the end of the call
   check_crc();
   if (!c->is_kid) c->prof.collect();
@@ -1428,7 +1524,7 @@ extern "C" int ckl_reencode(ckl_ctx* c, const void* binary, int binary_on_device
   const u8* dstream = dbin;
   if (!dstream) {
     c->stream_dev.ensure(num_bytes + 8);
-    CUDA_CHECK(cudaMemcpyAsync(c->stream_dev.p, hbin, num_bytes, cudaMemcpyHostToDevice, st));
+    copy_host(c, c->stream_dev.p, hbin, num_bytes, true, st);
     dstream = c->stream_dev.as<u8>();
   }
   const u64 sxy = (u64)h.sx * h.sy;

@@ -126,3 +126,29 @@ def test_chunked_device_resident_and_automatic(cctx):
     cctx.set_chunks(1)
     cctx.compress_ptr(t.data_ptr(), 1, 8, 256, 256, 1024, True, 5)
     assert cctx.result_bytes() == five
+
+
+@pytest.mark.parametrize("K", [1, 3])
+def test_pageable_host_volumes_take_the_staged_copies(cctx, K):
+    """numpy arrays are pageable memory: copies of >= 16 MB run through the pinned staging ring (copy_host, ckl_api.cu) on
+    eight host threads.  Sizes that are no multiple of the stage or the page size, whole volume and a z-range, a label
+    mask, chunked and unchunked: the bytes and voxels must be those of the plain copies (small volumes, the other tests)."""
+    from oracle import oracle as O
+    from crackle_b200 import synth
+    v = synth.jittered_voronoi((331, 277, 53), 18, np.uint32, seed=5, id_bits=30)      # 19.4 MB: staged, ragged tail
+    assert v.nbytes >= (16 << 20) and v.nbytes % 4096 != 0
+    ref = O.ref_module()
+    want = bytes(ref.compress(v, False, True, 0, False, True, 0, 0)) if ref is not None else O.compress(v, 0)
+    cctx.set_chunks(K)
+    b = cctx.compress(v, 0)
+    assert b == want
+    out = cctx.decompress(b)
+    assert np.array_equal(out.reshape(v.shape, order="F"), v)
+    part = cctx.decompress(b, 3, 50)                                                   # 17.2 MB: staged as well
+    assert np.array_equal(part.reshape((331, 277, 47), order="F"), v[:, :, 3:50])
+    w = synth.jittered_voronoi((256, 256, 40), 16, np.uint64, seed=6, id_bits=40)      # 21 MB, 8-byte labels
+    lab = int(w[100, 100, 20])
+    bw = cctx.compress(w, 0)
+    assert bw == (bytes(ref.compress(w, False, True, 0, False, True, 0, 0)) if ref is not None else O.compress(w, 0))
+    assert np.array_equal(cctx.decompress(bw).reshape(w.shape, order="F"), w)
+    assert np.array_equal(cctx.decompress(bw, label=lab).reshape(w.shape, order="F").view(bool), w == lab)
