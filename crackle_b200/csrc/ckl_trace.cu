@@ -619,6 +619,7 @@ __global__ void __launch_bounds__(32) k_replay(TraceParams P) {
     nev = __shfl_sync(FULL_MASK, nev, 0);
     nch = __shfl_sync(FULL_MASK, nch, 0);
     ok = __shfl_sync(FULL_MASK, (u32)ok, 0) != 0;
+    __syncwarp();                                       // lane 0's record stores before the other lanes' has_edges() loads
     cursor = start;
   }
   if (lane == 0) { P.sliceInfo[(u64)z * 4 + 0] = nev; P.sliceInfo[(u64)z * 4 + 1] = nch; }
