@@ -8,8 +8,7 @@ tools=${@:-memcheck racecheck}
 for t in $tools; do
   extra=""
   [ "$t" = memcheck ] && extra="--leak-check no"
-  [ "$t" = initcheck ] && extra="--track-unused-memory no"
-  small=0; [ "$t" = racecheck ] && small=1
+  small=${SANITIZE_SMALL:-0}; [ "$t" = racecheck ] && small=1
   SANITIZE_SMALL=$small timeout ${SANITIZE_TIMEOUT:-200} compute-sanitizer --tool $t $extra --error-exitcode 9 --print-limit 30 \
     python tests/bringup/sanitize_run.py > gpurun_out/sanitize_$t.log 2>&1
   echo "== $t rc=$? =="
