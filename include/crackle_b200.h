@@ -92,7 +92,9 @@ CKL_API int ckl_compress(ckl_ctx* ctx, const void* labels, int labels_on_device,
 CKL_API int ckl_result_copy(ckl_ctx* ctx, void* dst, int dst_on_device, uint64_t capacity);
 CKL_API const void* ckl_result_device(ckl_ctx* ctx, uint64_t* bytes);
 
-/* Decompress; `binary` host or device, `out` host or device. */
+/* Decompress; `binary` host or device, `out` host or device.  Host pointers (here and in ckl_compress / ckl_result_copy)
+ * may be pageable or pinned: pageable ranges of 16 MiB and more are moved through a pinned staging ring by eight host
+ * threads, pinned / registered memory is copied in place.  Distinct contexts may be used from distinct threads at once. */
 CKL_API int ckl_decompress(ckl_ctx* ctx, const void* binary, int binary_on_device, uint64_t num_bytes,
                    int64_t z_start, int64_t z_end, int has_label, uint64_t label,
                    void* out, int out_on_device, uint64_t out_capacity);
