@@ -6,7 +6,7 @@ import os as _os
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from .codec import (Context, compress, decompress, decompress_binary_image, decompress_range, default_context,  # noqa: F401
-                    header, z_range_for_label, voxel_counts, centroids, bounding_boxes, labels, num_labels, contains, reencode, zstack, zsplit, zshatter)
+                    header, z_range_for_label, voxel_counts, centroids, bounding_boxes, labels, num_labels, contains, reencode, zstack, zsplit, zshatter, voxel_connectivity_graph)
 
 __all__ = ["Context", "compress", "decompress", "decompress_binary_image", "decompress_range", "default_context", "header",
-           "z_range_for_label", "voxel_counts", "centroids", "bounding_boxes", "labels", "num_labels", "contains", "reencode", "zstack", "zsplit", "zshatter"]
+           "z_range_for_label", "voxel_counts", "centroids", "bounding_boxes", "labels", "num_labels", "contains", "reencode", "zstack", "zsplit", "zshatter", "voxel_connectivity_graph"]

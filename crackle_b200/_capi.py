@@ -53,6 +53,7 @@ SYMBOLS = {
     "ckl_result_device": (vp, [vp, ctypes.POINTER(u64)]),
     "ckl_decompress": (cint, [vp, vp, cint, u64, i64, i64, cint, u64, vp, cint, u64]),
     "ckl_label_stats": (cint, [vp, vp, cint, u64, i64, i64, vp, vp, vp, vp, cint, u64, ctypes.POINTER(u64)]),
+    "ckl_voxel_connectivity_graph": (cint, [vp, vp, cint, u64, i64, i64, cint, vp, cint, u64]),
     "ckl_reencode": (cint, [vp, vp, cint, u64, cint, ctypes.POINTER(u64)]),
     "ckl_zstack": (cint, [vp, cint, ctypes.POINTER(vp), ctypes.POINTER(u64), cint, ctypes.POINTER(u64)]),
     "ckl_zslice": (cint, [vp, vp, cint, u64, u64, u64, ctypes.POINTER(u64)]),

@@ -136,6 +136,17 @@ class Context:
         return out
 
 
+    def voxel_connectivity_graph(self, binary, z_start=0, z_end=-1, connectivity=4) -> np.ndarray:
+        """fastcrackle.voxel_connectivity_graph(binary, z_start, z_end, parallel, connectivity) (src/fastcrackle.cpp:538-565):
+        uint8 array of shape (sx, sy, z_end - z_start), Fortran order; bits 00 -z +z -y +y -x +x, set = passable."""
+        h = header(binary)
+        szr = _clamp_range(h, z_start, z_end)
+        buf = np.frombuffer(binary, dtype=np.uint8)
+        out = np.empty((h["sx"], h["sy"], szr), dtype=np.uint8, order="F")
+        self._check(_capi.lib().ckl_voxel_connectivity_graph(self._h, buf.ctypes.data, 0, buf.size, int(z_start), int(z_end),
+                                                              int(connectivity), out.ctypes.data, 0, out.nbytes))
+        return out
+
     def reencode(self, binary, markov_model_order: int) -> bytes:
         """ckl_reencode: the same stream with its crack codes re-coded at another markov order (no voxel decode)"""
         buf = np.frombuffer(binary, dtype=np.uint8)
@@ -412,6 +423,15 @@ def bounding_boxes(binary, label: Optional[int] = None, parallel: int = 0, no_sl
     boxes = {k: (slice(int(b[0]), int(b[3]) + 1), slice(int(b[1]), int(b[4]) + 1), slice(int(b[2]), int(b[5]) + 1))
              for k, b in boxes.items()}
     return boxes[label] if label is not None else boxes
+
+
+def voxel_connectivity_graph(binary, connectivity: int = 6, parallel: int = 0) -> np.ndarray:
+    """crackle.voxel_connectivity_graph (operations.py:936-954): uint8 (sx, sy, sz) Fortran-order array,
+    bitset (right hand side is LSB) 00-z+z-y+y-x+x."""
+    if connectivity not in (4, 6):
+        raise ValueError(f"Only 4 and 6 connected are supported. Got: {connectivity}")
+    with _default_lock:
+        return default_context().voxel_connectivity_graph(binary, 0, -1, connectivity)
 
 
 def z_range_for_label(binary, label: int) -> Tuple[int, int]:

@@ -25,6 +25,7 @@ bool launch_trace_nodes(const Geom& g, TraceBufs& T, ull* scal, u64 total_nodes,
 void launch_trace_paths(const Geom& g, TraceBufs& T, ull* scal, u32 max_nodes, cudaStream_t st);
 void launch_trace_replay(const Geom& g, TraceBufs& T, ull* scal, u32 max_nodes, cudaStream_t st);
 void launch_trace_post(const Geom& g, TraceBufs& T, ull* scal, u64 total_ev_cap, cudaStream_t st);
+void launch_vcg(const Geom& g, const u32* DV, const u32* DH, int permissible, const u32* key, u8* out, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------------
 struct ShardJob {
@@ -1211,9 +1212,10 @@ __global__ void k_crc_compare(const u32* __restrict__ computed, const u8* __rest
 static std::vector<u8> decode_stored_model(const u8* ms, u64 mbytes, int order);
 // stats != nullptr: no paint -- the per-label tables of ckl_label_stats are produced instead (out / label are unused)
 struct StatsOut { u64 *labels, *counts, *sums; u32* bbox; int on_device; u64 capacity; u64 n_unique; };
+struct VcgOut { int connectivity; u8* out; int on_device; u64 capacity; };      // voxel connectivity graph instead of labels
 static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t num_bytes, int64_t z_start, int64_t z_end,
                             int has_label, uint64_t label, void* out, int out_on_device, uint64_t out_capacity,
-                            StatsOut* stats = nullptr) {
+                            StatsOut* stats = nullptr, VcgOut* vcg = nullptr) {
   cudaStream_t st = c->st;
   timeline_base(c);
   if (num_bytes < 29) throw CklError(CKL_ERR_STREAM, "crackle: Input too small to be a valid stream. Bytes: " + std::to_string(num_bytes));
@@ -1246,7 +1248,8 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
   if (voxels == 0) return;
   if (sxy >= (1ull << 30)) throw CklError(CKL_ERR_ARG, "crackle_b200: slice too large (sx*sy must be < 2^30)");
   const int ow = has_label ? 1 : (int)h.data_width;
-  if (!stats && out_capacity < voxels * (u64)ow) throw CklError(CKL_ERR_ARG, "crackle_b200: output buffer too small");
+  if (!stats && !vcg && out_capacity < voxels * (u64)ow) throw CklError(CKL_ERR_ARG, "crackle_b200: output buffer too small");
+  if (vcg && vcg->capacity < voxels) throw CklError(CKL_ERR_ARG, "crackle_b200: output buffer too small");
   const u64 hbytes = h.format_version == 0 ? 24 : 29;
   const u64 zbytes = 4ull * (h.sz + (h.format_version == 0 ? 0 : 1));
   if (hbytes + zbytes > num_bytes) throw CklError(CKL_ERR_STREAM, "crackle: get_crack_code_offsets: Unable to read past end of buffer.");
@@ -1305,7 +1308,7 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
   // Large Fortran-order outputs: K z-chunks on child contexts (each a z-range decode into its own part of the output),
   // so one chunk's decode chains / CCL overlap another chunk's paint and, for host outputs, its device->host copy.
   {
-    const int K = (h.fortran_order && !stats) ? pick_chunks(c, sxy, szr, (u64)ow, !out_on_device) : 1;
+    const int K = (h.fortran_order && !stats && !vcg) ? pick_chunks(c, sxy, szr, (u64)ow, !out_on_device) : 1;
     if (K > 1) {
       ensure_kids(c, K);
       GridMultScope fine_grids;
@@ -1395,6 +1398,24 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
     if (h.crack_format) throw CklError(CKL_ERR_STREAM, "crackle: decode_permissible_crack_code: index out of range.");
     throw CklError(CKL_ERR_STREAM, "crackle: decode_impermissible_crack_code: index out of range.");
   }
+  // voxel connectivity graph (operations.hpp:667-826): the 2-D bits come straight from the planes; connectivity 6 goes on
+  // through the CCL / label stages for the keys of every voxel (key volume in out_dev, the graph bytes behind it)
+  auto emit_vcg = [&](const u32* keyvol) {
+    u8* dv = vcg->out;
+    if (!vcg->on_device) {
+      const u64 off = keyvol ? voxels * 4 : 0;             // the key volume (connectivity 6) lives in front of the graph bytes
+      c->out_dev.ensure(off + voxels + 64);
+      dv = c->out_dev.as<u8>() + off;
+    }
+    STAGE(c, "d_vcg", launch_vcg(g, c->DV.as<u32>(), c->DH.as<u32>(), (int)h.crack_format, keyvol, dv, st));
+    if (!vcg->on_device) copy_host(c, vcg->out, dv, voxels, false, st);
+  };
+  if (vcg && (vcg->connectivity == 4 || h.sz == 1)) {     // operations.hpp:756-758
+    emit_vcg(nullptr);
+    read_scalars(c);
+    if (!c->is_kid) c->prof.collect();
+    return;
+  }
   const u64 runs = c->hscal[SC_RUNS];
   c->ccl.parent.ensure(runs * 4); c->ccl.runStart.ensure(runs * 4); c->ccl.compRank.ensure(runs * 4);
   c->ccl.compPix.ensure(runs * 4);
@@ -1409,7 +1430,7 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
   launch_unpack_le(dsrc.uniq, sw, nu, D.uniq64.as<u64>(), st);
   launch_unpack_le(dsrc.keys, kw, n_keys, D.keys64.as<u64>(), st);
   dsrc.uniq64 = D.uniq64.as<u64>(); dsrc.keys64 = D.keys64.as<u64>();
-  dsrc.keys_only = stats != nullptr;
+  dsrc.keys_only = stats != nullptr || vcg != nullptr;
   STAGE(c, "d_ccl_finish", launch_ccl_finish(g, c->ccl, runs, c->dtab, init_term, &dsrc, st));
   if (h.format_version > 0) {   // crackle.hpp:599-611
     k_crc_compare<<<(g.sz + 255) / 256, 256, 0, st>>>(c->ccl.sliceCrc.as<u32>(), dstream + num_bytes - 4ull * h.sz + 4ull * (u64)z_start, g.sz, c->scal);
@@ -1448,6 +1469,16 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
     if (!c->is_kid) c->prof.collect();
     return;
   }
+  if (vcg) {        // connectivity 6: labels of vertically adjacent voxels agree <=> their unique-table keys do
+    c->out_dev.ensure(voxels * 5 + 64);
+    u32* keyvol = c->out_dev.as<u32>();
+    STAGE(c, "d_paint", launch_paint(g, c->DV.as<u32>(), c->ccl, D.runLabel.as<u64>(), 4, 0, 0, 1, keyvol, st));
+    emit_vcg(keyvol);
+    read_scalars(c);
+    check_crc();
+    if (!c->is_kid) c->prof.collect();
+    return;
+  }
   void* dout = out;
   if (!out_on_device) { c->out_dev.ensure(voxels * (u64)ow); dout = c->out_dev.p; }
   STAGE(c, "d_paint", launch_paint(g, c->DV.as<u32>(), c->ccl, D.runLabel.as<u64>(), ow, has_label, label, (int)h.fortran_order, dout, st));
@@ -1462,6 +1493,17 @@ extern "C" int ckl_decompress(ckl_ctx* c, const void* binary, int binary_on_devi
   API_BEGIN(c)
   decompress_impl(c, binary_on_device ? nullptr : (const u8*)binary, binary_on_device ? (const u8*)binary : nullptr, num_bytes, z_start, z_end,
                   has_label, label, out, out_on_device, out_capacity);
+  API_END(c)
+}
+
+extern "C" int ckl_voxel_connectivity_graph(ckl_ctx* c, const void* binary, int binary_on_device, uint64_t num_bytes, int64_t z_start,
+                                            int64_t z_end, int connectivity, uint8_t* out, int out_on_device, uint64_t out_capacity) {
+  API_BEGIN(c)
+  if (connectivity != 4 && connectivity != 6)      // operations.hpp:675-679 (the reference appends the byte count to the text)
+    throw CklError(CKL_ERR_ARG, "crackle: voxel_connectivity_graph: only connectivity 4 and 6 are currently supported." + std::to_string(num_bytes));
+  VcgOut vo{connectivity, out, out_on_device, out_capacity};
+  decompress_impl(c, binary_on_device ? nullptr : (const u8*)binary, binary_on_device ? (const u8*)binary : nullptr, num_bytes, z_start, z_end,
+                  0, 0, nullptr, 1, 0, nullptr, &vo);
   API_END(c)
 }
 

@@ -1341,3 +1341,56 @@ void launch_reencode_emit(const Geom& g, const u8* stream, DecodeBufs& D, const 
   k_reenc_emit<<<dec_grid(g.sz, 1, 8), 256, 0, st>>>(g, D.slices.as<DecSlice>(), stream, sliceInfo, cpOff, cp, codeOff, pack0, dst);
   LAUNCH_CHECK();
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Voxel connectivity graph (operations.hpp:667-826; bit layout of crackcodes.hpp:706-862): one byte per voxel, a set bit =
+// the neighbour in that direction is reachable, 00 -z +z -y +y -x +x.  The 2-D bits are the crack planes read the other way
+// round: an interior edge is passable where the differ-plane bit is clear; the edges on the image border were never
+// touched by a crack, so they keep the reference's fill value -- passable (1) for the IMPERMISSIBLE format (planes start at
+// 0b1111 and cracks clear bits), closed (0) for PERMISSIBLE (planes start at 0 and cracks set bits).  Connectivity 6 adds
+// +z / -z where the labels of vertically adjacent voxels agree (compared through their unique-table keys, painted as a
+// uint32 volume) and opens the outer faces of the first and last decoded slice.  One thread per 4 pixels of a row.
+template <bool Z>
+__global__ void __launch_bounds__(256) k_vcg(Geom g, const u32* __restrict__ DV, const u32* __restrict__ DH, u32 border,
+                                              const u32* __restrict__ key, u8* __restrict__ out) {
+  const u32 q = (g.sx + 3) / 4;
+  const u64 n = g.rows() * q, stride = (u64)gridDim.x * blockDim.x;
+  const bool aligned = (g.sx & 3u) == 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 row = fdiv(i, q);
+    const u32 x0 = (u32)(i - row * q) * 4u;
+    const u32 z = (u32)fdiv(row, g.sy), y = (u32)(row - (u64)z * g.sy);
+    const u64 wi = row * g.W + (x0 >> 5);
+    const u32 sh = x0 & 31u;
+    u32 v5 = (DV[wi] >> sh) & 0x1Fu;                              // differ bits of pixels x0 .. x0+4
+    if (sh == 28u && x0 + 4 < g.sx) v5 |= (DV[wi + 1] & 1u) << 4;
+    const u32 dh = (DH[wi] >> sh) & 0xFu;
+    const u32 dhb = (y + 1 < g.sy) ? (DH[wi + g.W] >> sh) & 0xFu : 0u;
+    const u64 o = (u64)z * g.sxy + (u64)y * g.sx + x0;
+    u32 word = 0;
+#pragma unroll
+    for (u32 j = 0; j < 4; j++) {
+      const u32 x = x0 + j;
+      if (x >= g.sx) break;
+      u32 b = (x + 1 < g.sx) ? (~(v5 >> (j + 1)) & 1u) : border;
+      b |= ((x > 0) ? (~(v5 >> j) & 1u) : border) << 1;
+      b |= ((y + 1 < g.sy) ? (~(dhb >> j) & 1u) : border) << 2;
+      b |= ((y > 0) ? (~(dh >> j) & 1u) : border) << 3;
+      if (Z) {
+        const u32 k = key[o + j];
+        b |= ((z + 1 < g.sz) ? (u32)(key[o + j + g.sxy] == k) : 1u) << 4;
+        b |= ((z > 0) ? (u32)(key[o + j - g.sxy] == k) : 1u) << 5;
+      }
+      if (aligned) word |= b << (8u * j);
+      else out[o + j] = (u8)b;
+    }
+    if (aligned) *reinterpret_cast<u32*>(out + o) = word;
+  }
+}
+void launch_vcg(const Geom& g, const u32* DV, const u32* DH, int permissible, const u32* key, u8* out, cudaStream_t st) {
+  const u64 n = g.rows() * (u64)((g.sx + 3) / 4);
+  const u32 grid = grid1(n, 256, 148 * 16);
+  if (key) k_vcg<true><<<grid, 256, 0, st>>>(g, DV, DH, permissible ? 0u : 1u, key, out);
+  else k_vcg<false><<<grid, 256, 0, st>>>(g, DV, DH, permissible ? 0u : 1u, nullptr, out);
+  LAUNCH_CHECK();
+}

@@ -112,6 +112,16 @@ CKL_API int ckl_label_stats(ckl_ctx* ctx, const void* binary, int binary_on_devi
                     int64_t z_start, int64_t z_end, uint64_t* labels, uint64_t* counts, uint64_t* sums, uint32_t* bbox,
                     int out_on_device, uint64_t capacity_entries, uint64_t* n_unique);
 
+/* Voxel connectivity graph of slices [z_start, z_end) -- crackle::operations::voxel_connectivity_graph
+ * (src/operations.hpp:667-826; binding src/fastcrackle.cpp:538-565; bit layout src/crackcodes.hpp:706-862): one byte per
+ * voxel in Fortran order (x fastest), a set bit = the neighbour in that direction is reachable, 00 -z +z -y +y -x +x.
+ * connectivity 4: the crack planes read per voxel (no CCL, no labels).  connectivity 6 (streams with sz > 1): +z / -z are
+ * set where the labels of vertically adjacent voxels agree, and the outer faces of the first and last decoded slice are
+ * open.  Edges on the image border keep the reference's fill value: open for the IMPERMISSIBLE crack format, closed for
+ * PERMISSIBLE.  Any other connectivity fails with CKL_ERR_ARG and the reference's text. */
+CKL_API int ckl_voxel_connectivity_graph(ckl_ctx* ctx, const void* binary, int binary_on_device, uint64_t num_bytes,
+                    int64_t z_start, int64_t z_end, int connectivity, uint8_t* out, int out_on_device, uint64_t out_capacity);
+
 /* Re-code a stream's crack codes with another markov model order without decoding to voxels
  * (crackle::reencode_with_markov_order, src/crackle.hpp:860-984; fastcrackle.reencode_markov src/fastcrackle.cpp:643).
  * Labels, labels crc and slice crcs are carried over verbatim; the result is left in the context's result buffer

@@ -43,7 +43,12 @@ def main():
             labels, counts, sums, bbox = ctx.label_stats(b)
             u, c = np.unique(v, return_counts=True)
             assert np.array_equal(labels, u.astype(np.uint64)) and np.array_equal(counts, c.astype(np.uint64))
+            for conn in (4, 6):
+                g = ctx.voxel_connectivity_graph(b, 0, -1, conn)
+                assert g.shape == v.shape and (conn == 4 or v.shape[2] == 1 or (g[:, :, 0] & 32).all())
             ref = O.ref_module()
+            if ref is not None:
+                assert np.array_equal(g, np.asarray(ref.voxel_connectivity_graph(b, 0, -1, 1, 6)))
             r2 = ctx.reencode(b, 2)
             if ref is not None:
                 assert r2 == bytes(ref.reencode_markov(b, 2, 1))

@@ -1,6 +1,6 @@
 """INTEGRATION.md Option B, as a module: the name `fastcrackle` the reference's Python package imports
 (crackle/codec.py:8, crackle/operations.py:9).  The hot path -- compress / decompress of flat-label streams, and the
-compressed-domain statistics voxel_counts / centroids / bounding_boxes -- goes to the B200 library (the in-tree pybind11
+compressed-domain statistics voxel_counts / centroids / bounding_boxes and voxel_connectivity_graph -- goes to the B200 library (the in-tree pybind11
 module crackle_b200.fastcrackle and the C-ABI); every other name of src/fastcrackle.cpp:641-669, and the pin label formats
 this path does not cover, come from the reference's own compiled module (oracle/_ref/_fastcrackle_ref).
 
@@ -77,3 +77,11 @@ def bounding_boxes(binary, z_start=-1, z_end=-1, parallel=1):
         return {int(k): bbox[i].copy() for i, k in enumerate(lab)}
     CALLS["ref"] += 1
     return _ref.bounding_boxes(binary, z_start, z_end, parallel)
+
+
+def voxel_connectivity_graph(buffer, z_start=0, z_end=-1, parallel=1, connectivity=4):
+    if _USE_GPU and _flat(buffer):
+        CALLS["b200"] += 1
+        return _cb.default_context().voxel_connectivity_graph(bytes(buffer), z_start, z_end, connectivity)
+    CALLS["ref"] += 1
+    return _ref.voxel_connectivity_graph(buffer, z_start, z_end, parallel, connectivity)
