@@ -368,17 +368,21 @@ def main():
     ms_step = ms / args.steps
     value = 2.0 * V / (ms_step * 1e-3) / 1e9
 
+    drains = []                       # host-side stream drains per call (the library's ckl_sync_count), in the order timed() is called
+
     def timed(fn):
         """per-call time of `fn` over args.steps calls: CUDA events on the stream, barrier both sides, max over ranks"""
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0 = cb.codec.sync_count()
         a.record(stream)
         for _ in range(args.steps):
             fn()
         b.record(stream)
         torch.cuda.synchronize()
+        drains.append((cb.codec.sync_count() - s0) / args.steps)
         tt = a.elapsed_time(b) / args.steps
         if dist:
             x = torch.tensor([tt], device="cuda", dtype=torch.float64)
@@ -447,6 +451,8 @@ def main():
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_kernels": kern,
             f"{names[0]}_gvox_s": V / (t_a * 1e-3) / 1e9, f"{names[0]}_ms": t_a, f"{names[0]}_hbm_frac": roof[names[0]]["frac"],
             f"{names[1]}_gvox_s": V / (t_b * 1e-3) / 1e9, f"{names[1]}_ms": t_b, f"{names[1]}_hbm_frac": roof[names[1]]["frac"]}
+    line["host_drains_per_call"] = {names[0]: drains[0], names[1]: drains[1],
+                                    "what": "cudaStreamSynchronize calls the library issues inside one call (rank 0; ckl_sync_count)"}
     if job is not None:
         line["collectives_per_compress"] = "metadata all_gather + unique-table all_gather (both beside the tracer's chain replay) + code-size all_gather + ONE padded all_gather of the packed blocks" + \
                                            (" + statistics all_reduce + code-size all_gather (order > 0)" if args.order > 0 else "")

@@ -73,6 +73,7 @@ SYMBOLS = {
     "ckl_prof_enable": (cint, [vp, cint]),
     "ckl_prof_read": (cint, [vp, ctypes.c_char_p, ctypes.c_size_t]),
     "ckl_launch_count": (u64, []),
+    "ckl_sync_count": (u64, []),
     "ckl_ctx_set_stream": (cint, [vp, vp]),
     "ckl_ctx_own_stream": (cint, [vp]),
     "ckl_ctx_set_chunks": (cint, [vp, cint]),

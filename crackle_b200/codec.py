@@ -191,6 +191,11 @@ _default: Optional[Context] = None
 _default_lock = threading.RLock()      # the module-level API shares one context: one call at a time (ctypes drops the GIL)
 
 
+def sync_count() -> int:
+    """host-side waits on a compute stream issued by the library since load (ckl_sync_count)"""
+    return int(_capi.lib().ckl_sync_count())
+
+
 def default_context() -> Context:
     global _default
     with _default_lock:

@@ -46,6 +46,7 @@ struct ShardJob {
 };
 
 unsigned long long g_ckl_launches = 0;
+unsigned long long g_ckl_syncs = 0;
 int g_ckl_grid_mult = 1;
 
 int ckl_num_sms() {
@@ -157,7 +158,7 @@ static void set_err(char* err, size_t n, const std::string& m) {
 
 static void read_scalars(ckl_ctx* c) {
   CUDA_CHECK(cudaMemcpyAsync(c->hscal, c->scal, SC_COUNT * sizeof(ull), cudaMemcpyDeviceToHost, c->st));
-  CUDA_CHECK(cudaStreamSynchronize(c->st));
+  CUDA_CHECK(ckl_sync(c->st));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -208,7 +209,7 @@ static void copy_host(ckl_ctx* c, void* dst, const void* src, u64 bytes, bool to
   }
   if (!c->stager) { c->stager = new HostStager(); c->stager->create(); }
   HostStager& S = *c->stager;
-  CUDA_CHECK(cudaStreamSynchronize(st));               // down: the producer of the device buffer; up: its previous readers
+  CUDA_CHECK(ckl_sync(st));               // down: the producer of the device buffer; up: its previous readers
   const u64 per = (((bytes + HS_THREADS - 1) / HS_THREADS) + 4095) & ~4095ull;
   ChunkErr errs[HS_THREADS];
   auto worker = [&](int t) {
@@ -451,7 +452,7 @@ static void shard_encode_queue(ckl_ctx* c, int permissible, int stored_width, in
   // alone.  The CCL / label chain is queued once the replay is -- that kernel keeps one warp per scheduler busy a fifth of
   // the time, and the CCL work fits into the issue slots it leaves free.
   CUDA_CHECK(cudaMemcpyAsync(c->hscal2, c->scal, SC_COUNT * sizeof(ull), cudaMemcpyDeviceToHost, st2));
-  CUDA_CHECK(cudaStreamSynchronize(st2));
+  CUDA_CHECK(ckl_sync(st2));
   const u64 evCap = c->hscal2[SC_SYMCAP], stackCap = c->hscal2[SC_STACKCAP], chainCap = c->hscal2[SC_CHAINCAP], cpCap = c->hscal2[SC_CPCAP];
   const u64 nodes = c->hscal2[SC_NODES];
   const u32 maxNodes = (u32)c->hscal2[SC_MAXNODES];
@@ -616,7 +617,7 @@ extern "C" int ckl_shard_unique(ckl_ctx* c, uint64_t* dst, int dst_on_device) {
   if (!c->job.encoded && !c->job.queued) throw CklError(CKL_ERR_ARG, "crackle_b200: no encoded shard");
   if (c->job.nuniq_local) {
     CUDA_CHECK(cudaMemcpyAsync(dst, c->lb.uniq.p, c->job.nuniq_local * 8, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
-    CUDA_CHECK(cudaStreamSynchronize(c->st));
+    CUDA_CHECK(ckl_sync(c->st));
   }
   API_END(c)
 }
@@ -625,7 +626,7 @@ extern "C" int ckl_shard_stats(ckl_ctx* c, uint32_t* dst, int dst_on_device) {
   if (!c->job.encoded || c->job.order <= 0) throw CklError(CKL_ERR_ARG, "crackle_b200: no markov statistics for this shard");
   const u64 rows = 1ull << (2 * c->job.order);
   CUDA_CHECK(cudaMemcpyAsync(dst, c->mk.stats.p, rows * 16, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
-  CUDA_CHECK(cudaStreamSynchronize(c->st));
+  CUDA_CHECK(ckl_sync(c->st));
   API_END(c)
 }
 extern "C" int ckl_shard_finish(ckl_ctx* c, const uint64_t* global_unique, int unique_on_device, uint64_t n_unique_global,
@@ -660,7 +661,7 @@ extern "C" int ckl_shard_model(ckl_ctx* c, uint8_t* dst, int dst_on_device, uint
   if (dst && n) {
     if (capacity < n) throw CklError(CKL_ERR_ARG, "crackle_b200: model buffer too small");
     CUDA_CHECK(cudaMemcpyAsync(dst, c->mk.stored.p, n, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
-    CUDA_CHECK(cudaStreamSynchronize(c->st));
+    CUDA_CHECK(ckl_sync(c->st));
   }
   API_END(c)
 }
@@ -686,7 +687,7 @@ extern "C" int ckl_shard_fetch(ckl_ctx* c, uint8_t* keys, uint64_t* components_p
     LAUNCH_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(code_sizes, c->tmp32.p, (u64)sz * 4, k, c->st));
   }
-  CUDA_CHECK(cudaStreamSynchronize(c->st));
+  CUDA_CHECK(ckl_sync(c->st));
   if (components_per_slice) for (u32 z = 0; z < sz; z++) components_per_slice[z] = nz[z];
   API_END(c)
 }
@@ -1084,7 +1085,7 @@ static void compress_chunked(ckl_ctx* c, const void* labels, int labels_on_devic
   launch_crc_bytes(R + off_lab, labels_bytes, c->dtab, c->htab, crc_tmp + 1, st);
   k_store_bytes_u32<<<1, 1, 0, st>>>(R + off_codes + codes_bytes, crc_tmp + 1);
   LAUNCH_CHECK();
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(ckl_sync(st));
   merge_kid_prof(c, K);
   c->prof.collect();
   for (int k = 0; k < K; k++) c->kids[k]->job.active = false;
@@ -1109,7 +1110,7 @@ extern "C" int ckl_compress(ckl_ctx* c, const void* labels, int labels_on_device
     header_bytes_v1(hb, data_width, 1, 0, fortran_order, markov_model_order, (u32)sx, (u32)sy, (u32)sz, 0);
     c->result.ensure(29);
     CUDA_CHECK(cudaMemcpyAsync(c->result.p, hb, 29, cudaMemcpyHostToDevice, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(ckl_sync(st));
     c->result_bytes = 29;
     if (out_bytes) *out_bytes = 29;
     return CKL_OK;
@@ -1174,7 +1175,7 @@ extern "C" int ckl_compress(ckl_ctx* c, const void* labels, int labels_on_device
   // Device-resident input on a caller-owned stream (ckl_ctx_set_stream): the result is complete in stream order
   // (ckl_result_copy drains; a ckl_decompress of ckl_result_device() on this context is ordered behind it) and the caller
   // orders its own use of the input on that stream -- no drain here.  Otherwise the call returns with the work finished.
-  if (!(labels_on_device && c->ext_stream) || c->prof.on) CUDA_CHECK(cudaStreamSynchronize(st));
+  if (!(labels_on_device && c->ext_stream) || c->prof.on) CUDA_CHECK(ckl_sync(st));
   c->prof.collect();
   c->result_bytes = total;
   if (out_bytes) *out_bytes = total;
@@ -1188,7 +1189,7 @@ extern "C" int ckl_result_copy(ckl_ctx* c, void* dst, int dst_on_device, uint64_
   if (c->result_bytes) {
     if (dst_on_device) CUDA_CHECK(cudaMemcpyAsync(dst, c->result.p, c->result_bytes, cudaMemcpyDeviceToDevice, c->st));
     else copy_host(c, dst, c->result.p, c->result_bytes, false, c->st);
-    CUDA_CHECK(cudaStreamSynchronize(c->st));
+    CUDA_CHECK(ckl_sync(c->st));
   }
   API_END(c)
 }
@@ -1220,13 +1221,20 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
   timeline_base(c);
   if (num_bytes < 29) throw CklError(CKL_ERR_STREAM, "crackle: Input too small to be a valid stream. Bytes: " + std::to_string(num_bytes));
   // the small sections are parsed on the host; a device-resident stream is read back piecewise (never as a whole)
-  std::vector<u8> buf_head, buf_z, buf_lab, buf_nz, buf_model;
+  // (the first read brings the first 64 KB over in one go: header, z index and the label count of any ordinary stream)
+  std::vector<u8> buf_head, buf_z, buf_lab, buf_nz, buf_model, prefix;
   auto fetch = [&](u64 offset, u64 n, std::vector<u8>& buf) -> const u8* {
     if (hbin) return hbin + offset;
+    if (prefix.empty()) {
+      prefix.resize((size_t)std::min<u64>(num_bytes, 65536));
+      CUDA_CHECK(cudaMemcpyAsync(prefix.data(), dbin, prefix.size(), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(ckl_sync(st));
+    }
+    if (offset + n <= prefix.size()) return prefix.data() + offset;
     buf.resize(n ? n : 1);
     if (n) {
       CUDA_CHECK(cudaMemcpyAsync(buf.data(), dbin + offset, n, cudaMemcpyDeviceToHost, st));
-      CUDA_CHECK(cudaStreamSynchronize(st));
+      CUDA_CHECK(ckl_sync(st));
     }
     return buf.data();
   };
@@ -1326,7 +1334,7 @@ static void decompress_impl(ckl_ctx* c, const u8* hbin, const u8* dbin, uint64_t
       } catch (...) { for (int k = 0; k < K; k++) c->kids[k]->stg = nullptr; throw; }
       for (int k = 0; k < K; k++) c->kids[k]->stg = nullptr;
       join_kids(c, K);
-      CUDA_CHECK(cudaStreamSynchronize(st));
+      CUDA_CHECK(ckl_sync(st));
       merge_kid_prof(c, K);
       return;
     }
@@ -1553,7 +1561,7 @@ extern "C" int ckl_reencode(ckl_ctx* c, const void* binary, int binary_on_device
   auto fetch = [&](u64 offset, u64 n, std::vector<u8>& buf) -> const u8* {
     if (hbin) return hbin + offset;
     buf.resize(n ? n : 1);
-    if (n) { CUDA_CHECK(cudaMemcpyAsync(buf.data(), dbin + offset, n, cudaMemcpyDeviceToHost, st)); CUDA_CHECK(cudaStreamSynchronize(st)); }
+    if (n) { CUDA_CHECK(cudaMemcpyAsync(buf.data(), dbin + offset, n, cudaMemcpyDeviceToHost, st)); CUDA_CHECK(ckl_sync(st)); }
     return buf.data();
   };
   const u8* hhead = fetch(0, 29, buf_head);
@@ -1573,7 +1581,7 @@ extern "C" int ckl_reencode(ckl_ctx* c, const void* binary, int binary_on_device
   if (order == new_order || sxy * h.sz == 0) {                     // crackle.hpp:888-890: a copy
     c->result.ensure(num_bytes + 16);
     CUDA_CHECK(cudaMemcpyAsync(c->result.p, dstream, num_bytes, cudaMemcpyDeviceToDevice, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(ckl_sync(st));
     c->result_bytes = num_bytes;
     if (out_bytes) *out_bytes = num_bytes;
     return CKL_OK;
@@ -1664,7 +1672,7 @@ extern "C" int ckl_reencode(ckl_ctx* c, const void* binary, int binary_on_device
   launch_reencode_emit(g, dstream, D, T.sliceInfo.as<u32>(), cpOff, T.cp.as<u8>(), T.codeOff.as<u64>(), new_order == 0, R + off_codes, st);
   if (new_order > 0) launch_markov_copy_body(g, T, c->mk, R + off_codes, st);
   if (tail) CUDA_CHECK(cudaMemcpyAsync(R + off_codes + codes_bytes, dstream + codeOff[sz], tail, cudaMemcpyDeviceToDevice, st));
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(ckl_sync(st));
   c->result_bytes = total;
   if (out_bytes) *out_bytes = total;
   API_END(c)
@@ -1687,7 +1695,7 @@ static void ensure_copy(ckl_ctx* c, std::vector<u8>& dst, const u8* hbin, const 
   dst.resize(n ? n : 1);
   if (!n) return;
   if (hbin) memcpy(dst.data(), hbin + off, n);
-  else { CUDA_CHECK(cudaMemcpyAsync(dst.data(), dbin + off, n, cudaMemcpyDeviceToHost, c->st)); CUDA_CHECK(cudaStreamSynchronize(c->st)); }
+  else { CUDA_CHECK(cudaMemcpyAsync(dst.data(), dbin + off, n, cudaMemcpyDeviceToHost, c->st)); CUDA_CHECK(ckl_sync(c->st)); }
 }
 static FlatStreamView view_flat_stream(ckl_ctx* c, const u8* hbin, const u8* dbin, u64 nbytes, const char* who) {
   FlatStreamView v;
@@ -1767,7 +1775,7 @@ static void finish_flat_stream(ckl_ctx* c, u8* R, const ckl_header_info& h0, u32
 }
 static u64 read_max_label(ckl_ctx* c, const u64* guniq, u64 nu) {
   u64 m = 0;
-  if (nu) { CUDA_CHECK(cudaMemcpyAsync(&m, guniq + nu - 1, 8, cudaMemcpyDeviceToHost, c->st)); CUDA_CHECK(cudaStreamSynchronize(c->st)); }
+  if (nu) { CUDA_CHECK(cudaMemcpyAsync(&m, guniq + nu - 1, 8, cudaMemcpyDeviceToHost, c->st)); CUDA_CHECK(ckl_sync(c->st)); }
   return m;
 }
 
@@ -1828,7 +1836,7 @@ extern "C" int ckl_zstack(ckl_ctx* c, int n, const void* const* binaries, const 
     z0 += szi; k0 += nk; c0 += v.codes_bytes;
   }
   finish_flat_stream(c, R, V[0].h, (u32)sz, data_width, stored, nu, guniq, labels_bytes, off_codes, codes);
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(ckl_sync(st));
   c->result_bytes = total;
   if (out_bytes) *out_bytes = total;
   API_END(c)
@@ -1871,7 +1879,7 @@ extern "C" int ckl_zslice(ckl_ctx* c, const void* binary, int on_device, uint64_
   if (codes) CUDA_CHECK(cudaMemcpyAsync(R + off_codes, v.dev + v.off_codes + v.code_off[z_start], codes, cudaMemcpyDeviceToDevice, st));
   launch_write_keys(labs.as<u64>(), nk, guniq, nu, kw, R + off_keys, st);
   finish_flat_stream(c, R, v.h, (u32)sz, (int)v.h.data_width, stored, nu, guniq, labels_bytes, off_codes, codes);
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(ckl_sync(st));
   c->result_bytes = total;
   if (out_bytes) *out_bytes = total;
   API_END(c)
@@ -1903,6 +1911,7 @@ extern "C" int ckl_prof_read(ckl_ctx* c, char* buf, size_t cap) {
   return CKL_OK;
 }
 extern "C" uint64_t ckl_launch_count(void) { return g_ckl_launches; }
+extern "C" uint64_t ckl_sync_count(void) { return g_ckl_syncs; }
 // Run this context's work on a caller-owned stream (e.g. torch's current stream) so the caller's stream order and
 // CUDA events cover the kernels.  stream == 0 is the legacy default stream (what torch uses unless told otherwise).
 extern "C" int ckl_ctx_set_stream(ckl_ctx* c, void* stream) {
@@ -1934,7 +1943,7 @@ extern "C" int ckl_crc32c(ckl_ctx* c, const void* data, int on_device, uint64_t 
   c->tmp32.ensure(16);
   launch_crc_bytes(d, n, c->dtab, c->htab, c->tmp32.as<u32>(), c->st);
   CUDA_CHECK(cudaMemcpyAsync(out, c->tmp32.p, 4, cudaMemcpyDeviceToHost, c->st));
-  CUDA_CHECK(cudaStreamSynchronize(c->st));
+  CUDA_CHECK(ckl_sync(c->st));
   API_END(c)
 }
 
@@ -1948,7 +1957,7 @@ extern "C" int ckl_sort_unique_u64(ckl_ctx* c, uint64_t* data_device, uint64_t n
   try {
     cnt = labels_sort_unique(tmp, n, key_bytes * 8, c->st);
     if (cnt) CUDA_CHECK(cudaMemcpyAsync(data_device, tmp.uniq.p, cnt * 8, cudaMemcpyDeviceToDevice, c->st));
-    CUDA_CHECK(cudaStreamSynchronize(c->st));
+    CUDA_CHECK(ckl_sync(c->st));
   } catch (...) { tmp.mapping.p = nullptr; tmp.mapping.cap = 0; throw; }
   tmp.mapping.p = nullptr; tmp.mapping.cap = 0;
   *n_unique = cnt;

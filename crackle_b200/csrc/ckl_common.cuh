@@ -34,6 +34,9 @@ extern unsigned long long g_ckl_launches;
 // grid-cap multiplier of the grid-stride kernels: > 1 while z-chunks run concurrently, so blocks are short and the
 // hardware block scheduler can interleave the chunks by stream priority instead of queueing behind persistent grids
 extern int g_ckl_grid_mult;
+// every host-side wait on a compute stream goes through ckl_sync(): a process-wide drain counter (bench.py reports it per call)
+extern unsigned long long g_ckl_syncs;
+inline cudaError_t ckl_sync(cudaStream_t st) { __atomic_fetch_add(&g_ckl_syncs, 1ull, __ATOMIC_RELAXED); return cudaStreamSynchronize(st); }
 #define LAUNCH_CHECK() do { __atomic_fetch_add(&g_ckl_launches, 1ull, __ATOMIC_RELAXED); CUDA_CHECK(cudaGetLastError()); } while (0)
 
 // 64-bit index / 32-bit divisor: the full 64-bit division costs ~70 instructions; almost every index fits 32 bits

@@ -67,7 +67,7 @@ u64 labels_sort_unique(LabelBufs& L, u64 n, int key_bits, cudaStream_t st, ull* 
   }
   u64 count = 0;
   CUDA_CHECK(cudaMemcpyAsync(&count, L.flags.p, 8, cudaMemcpyDeviceToHost, st));
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(ckl_sync(st));
   return count;
 }
 

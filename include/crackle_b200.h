@@ -232,6 +232,8 @@ CKL_API int ckl_ctx_own_stream(ckl_ctx* ctx);
 CKL_API int ckl_ctx_set_chunks(ckl_ctx* ctx, int chunks);
 /* Number of kernels this library has launched in this process. */
 CKL_API uint64_t ckl_launch_count(void);
+/* host-side waits on a compute stream (cudaStreamSynchronize) issued by the library since load: the drains of the hot calls */
+CKL_API uint64_t ckl_sync_count(void);
 /* CRC-32C (Castagnoli) of a host or device buffer, computed on the GPU (src/crc.hpp:39-57). */
 CKL_API int ckl_crc32c(ckl_ctx* ctx, const void* data, int on_device, uint64_t n, uint32_t* out);
 /* In-place sort + unique of a DEVICE array of uint64 (only the low key_bytes*8 bits are compared). */
