@@ -77,3 +77,13 @@ def test_no_cpu_fallback():
 def test_signed_rejected_like_reference():
     with pytest.raises(TypeError, match="Signed integer"):
         codec._as_fortran_volume(np.zeros((2, 2, 2), dtype=np.int32))
+
+
+def test_counters_and_argument_checks_that_need_no_device():
+    """the launch / drain counters are plain host counters; crackle.voxel_connectivity_graph rejects other connectivities in
+    Python (operations.py:947-948) before anything touches the device"""
+    import crackle_b200 as cb
+    assert codec.launch_count() >= 0 and codec.sync_count() >= 0
+    g = load_golden("island_6x6")
+    with pytest.raises(ValueError, match="Only 4 and 6 connected are supported. Got: 8"):
+        cb.voxel_connectivity_graph(bytes(g["ckl_order0"]), connectivity=8)
