@@ -150,6 +150,7 @@ struct ckl_ctx {
   int chunks = 0;                          // 0 = automatic, 1 = off, K = force K chunks
   cudaEvent_t ev_done = nullptr;
   struct HostStager* stager = nullptr;     // pinned staging ring for bulk copies from / to PAGEABLE host memory (lazy)
+  bool stager_failed = false;              // the ring could not be allocated: pageable copies stay with the driver's staging
 };
 
 static void set_err(char* err, size_t n, const std::string& m) {
@@ -207,7 +208,15 @@ static void copy_host(ckl_ctx* c, void* dst, const void* src, u64 bytes, bool to
     CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st));
     return;
   }
-  if (!c->stager) { c->stager = new HostStager(); c->stager->create(); }
+  if (!c->stager && !c->stager_failed) {
+    HostStager* hs = new HostStager();
+    try { hs->create(); c->stager = hs; }
+    catch (const CklError&) { delete hs; cudaGetLastError(); c->stager_failed = true; }   // no pinned memory to be had: plain copies
+  }
+  if (!c->stager) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st));
+    return;
+  }
   HostStager& S = *c->stager;
   CUDA_CHECK(ckl_sync(st));               // down: the producer of the device buffer; up: its previous readers
   const u64 per = (((bytes + HS_THREADS - 1) / HS_THREADS) + 4095) & ~4095ull;
